@@ -1,0 +1,185 @@
+/*
+ * yolo_b200.h -- C-ABI of libyolo_b200.so: the sm_100a kernels behind the
+ * YOLOv3 detection hot path of GabeTsai/YOLO-For-Turbines.
+ *
+ * The reference has no native layer (it is 100 % Python on top of ATen/cuDNN),
+ * so every entry point below names the reference *Python* call site it
+ * replaces (paths are relative to the reference checkout).  The Python mirror
+ * of the reference's module surface (yolo_for_turbines_b200/{model,utils}.py)
+ * binds these with ctypes; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 (YB_OK) or a negative YB_ERR_* code and leaves a
+ *     human-readable message retrievable with yolo_last_error() (thread-local);
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - every launch is asynchronous on the given cudaStream_t, performs no host
+ *     synchronisation and no allocation: workspaces are sized by the
+ *     *_workspace_bytes() queries and owned by the caller (torch tensors);
+ *   - no global mutable state, so one thread per GPU may call concurrently;
+ *   - plain C types only (no torch types), so any FFI can bind it.
+ */
+#ifndef YOLO_B200_H_
+#define YOLO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef YOLO_B200_NO_CUDA_TYPES
+typedef struct CUstream_st* yb_stream_t; /* == cudaStream_t */
+#endif
+
+#define YB_OK 0
+#define YB_ERR_INVALID (-1)     /* bad argument                               */
+#define YB_ERR_CUDA (-2)        /* a CUDA runtime/driver call failed          */
+#define YB_ERR_UNSUPPORTED (-3) /* shape/feature outside what the kernels do  */
+#define YB_ERR_WORKSPACE (-4)   /* caller-provided workspace too small        */
+
+/* bits of the device status word the kernels OR into (see yolo_conv_fwd)      */
+#define YB_STATUS_NAN_INPUT 1u /* model.py:175  assert no NaN in the input     */
+#define YB_STATUS_NAN_LAYER 2u /* model.py:183  ValueError("Nan in layer")     */
+
+/* activation codes: model.py:62-70 (CNNBlock)                                 */
+#define YB_ACT_NONE 0
+#define YB_ACT_LEAKY 1 /* nn.LeakyReLU(0.1) */
+#define YB_ACT_MISH 2  /* nn.Mish()         */
+
+/* box formats of utils.py:38 calc_iou: "center" = cx,cy,w,h; anything else =
+ * top-left x,y + w,h (the reference's "corners" is NOT x1y1x2y2).             */
+#define YB_BOX_CENTER 0
+#define YB_BOX_CORNERS 1
+
+const char* yolo_last_error(void);
+int yolo_version(void);
+/* compute capability + SM count of `device`; fails unless it is sm_100.        */
+int yolo_device_info(int device, int* cc_major, int* cc_minor, int* sm_count);
+
+/* ------------------------------------------------------------------------- *
+ * K1/K2  fused conv + folded BN + activation (+ residual, + 2x nearest
+ * upsample on store, + zero-copy concat through channel pitches)
+ * replaces CNNBlock.forward (model.py:80-86), ResidualBlock.forward's add
+ * (model.py:115-121), nn.Upsample + torch.cat (model.py:189-191, :222).
+ * Activations are NHWC bf16 (channel pitch may exceed C so that a tensor can
+ * live inside a wider concat buffer); weights are [Cout_pad][kh][kw][Cin] bf16.
+ * ------------------------------------------------------------------------- */
+typedef struct yolo_conv_desc {
+  int32_t batch, h_in, w_in, c_in;    /* logical input (c_in multiple of 32)  */
+  int32_t in_pitch;                   /* elements between consecutive pixels  */
+  int32_t c_out;                      /* logical output channels              */
+  int32_t c_out_pad;                  /* rows of w_packed / scale / bias      */
+  int32_t out_pitch;                  /* elements between output pixels       */
+  int32_t ksize, stride, pad;         /* 1|3, 1|2, 0|1  (model.py:199-205)    */
+  int32_t act;                        /* YB_ACT_*                             */
+  int32_t has_residual, res_pitch;    /* y = act(..) + residual               */
+  int32_t upsample2x;                 /* store every pixel to a 2x2 block     */
+  int32_t out_fp32;                   /* 1: y is float (head), else bf16      */
+  int32_t check_nan;                  /* OR YB_STATUS_NAN_LAYER on NaN output */
+  int32_t a_mode;                     /* 0 auto, 1 force tiled-2D, 2 im2col   */
+  int32_t block_n_hint;               /* tuning: 0 auto | 32 | 64 | 128 | 256 */
+  int32_t stages_hint;                /* tuning: 0 auto | smem pipeline depth */
+} yolo_conv_desc;
+
+/* Size of the opaque, caller-owned plan blob (64-byte aligned storage).       */
+size_t yolo_conv_plan_bytes(void);
+/* Encodes the TMA tensor maps and picks the tile configuration.  All device
+ * pointers are baked into the plan (static buffers => CUDA-graph friendly).   */
+int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yolo_conv_desc* desc,
+                        const void* x, const void* w_packed, const float* scale,
+                        const float* bias, const void* residual, void* y);
+int yolo_conv_fwd(const void* plan_host, uint32_t* status, yb_stream_t stream);
+/* tile configuration chosen by plan_init: block_n, block_k, stages, grid x/y */
+int yolo_conv_plan_info(const void* plan_host, int32_t* info5);
+
+/* TEST-ONLY reference: the same math on CUDA cores (direct convolution, one
+ * thread per output element).  Never called by the product path.              */
+int yolo_conv_fwd_simt(const yolo_conv_desc* desc, const void* x, const void* w_packed,
+                       const float* scale, const float* bias, const void* residual,
+                       void* y, uint32_t* status, yb_stream_t stream);
+
+/* OIHW fp32 (nn.Conv2d.weight) -> [c_out_pad][k*k][c_in_pad] bf16, zero padded.
+ * Replaces nothing in the reference; it is the repack the loader
+ * (model.py:293-305) feeds.                                                   */
+int yolo_pack_weights(const float* w_oihw, int c_out, int c_in, int ksize, int c_out_pad,
+                      int c_in_pad, void* w_packed, yb_stream_t stream);
+/* Stem weights: OIHW (c_out,3,3,3) -> [c_out_pad][32] bf16 with K index
+ * (kh*3+kw)*3+c, matching yolo_input_patchify.                                */
+int yolo_pack_stem_weights(const float* w_oihw, int c_out, int c_in, int c_out_pad,
+                           void* w_packed, yb_stream_t stream);
+/* BatchNorm2d (eval) folding: scale = g/sqrt(var+eps), bias = b - mean*scale;
+ * gamma==NULL => scale=1, bias=conv bias (head conv).  model.py:61,84-86.     */
+int yolo_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var,
+                 const float* conv_bias, float eps, int c, int c_pad, float* scale,
+                 float* bias, yb_stream_t stream);
+/* NCHW fp32 -> NHWC bf16 (c padded with zeros to c_pad); ORs
+ * YB_STATUS_NAN_INPUT into *status when x holds a NaN (model.py:175).          */
+int yolo_nchw_to_nhwc_bf16(const float* x, int batch, int c, int h, int w, int c_pad,
+                           int out_pitch, void* y, uint32_t* status, yb_stream_t stream);
+/* NHWC bf16/fp32 -> NCHW fp32 (module-level drop-in outputs).                  */
+int yolo_nhwc_to_nchw_f32(const void* x, int in_is_fp32, int batch, int c, int h, int w,
+                          int in_pitch, float* y, yb_stream_t stream);
+/* Stem im2col: NCHW fp32 (B,c,H,W), 9*c <= 32 -> [B*H*W][32] bf16 rows holding
+ * the 9*c taps (kh,kw,c) of the pad-1 3x3 window, zero padded, so that the
+ * Cin=3 stem conv (model.py:21) runs as a K=32 GEMM on the tensor cores.  Also
+ * NaN-checks x (model.py:175).                                                */
+int yolo_input_patchify(const float* x, int batch, int c, int h, int w, void* y,
+                        uint32_t* status, yb_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * K3  anchor decode -- replaces utils.py:86-148 cells_to_boxes.
+ * head: (B,3,S,S,5+nc) with arbitrary element strides st[5]; fp32.
+ * anchors6: 3x(w,h) already multiplied by S (utils.py:303).  Rows
+ * [cx,cy,w,h,obj,cls] are written to out[(b*out_boxes_per_image + out_offset +
+ * a*S*S + i*S + j)*6].  is_pred=0 follows utils.py:114-116.  writeback=1
+ * reproduces the reference's in-place mutation of head[...,0:4] (:106-110).
+ * ------------------------------------------------------------------------- */
+int yolo_decode(const float* head, const int64_t* strides5_host, int batch, int S, int nc,
+                const float* anchors6_host, int is_pred, int writeback, float* out,
+                int out_boxes_per_image, int out_offset, yb_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * K4+K5+K6  threshold compaction, stable segmented sort, class-aware greedy
+ * NMS -- replaces utils.py:150-191 non_max_suppression for a whole batch.
+ * boxes: [total][6] fp32 rows [x,y,w,h,score,cls]; image b owns rows
+ * [img_offsets[b], img_offsets[b+1]).  On return keep_idx[keep_off[b] ..
+ * keep_off[b+1]) are the row indices the reference would return for image b,
+ * in the reference's order (descending score, ties by original position).
+ * ------------------------------------------------------------------------- */
+size_t yolo_nms_workspace_bytes(int total, int batch);
+int yolo_nms(const float* boxes, const int32_t* img_offsets, int batch, int total,
+             float iou_thr, double obj_thr, int box_format, int32_t* keep_idx,
+             int32_t* keep_off, void* workspace, size_t workspace_bytes, yb_stream_t stream);
+
+/* Element-wise IoU -- replaces utils.py:38-84 calc_iou (n1 or n2 may be 1 to
+ * broadcast) and utils.py:22-36 iou_aligned (aligned=1: rows are [w,h]).      */
+int yolo_iou(const float* boxes1, int n1, int stride1, const float* boxes2, int n2, int stride2,
+             int box_format, int aligned, float* out, yb_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * K7  mAP matching -- replaces the per-detection loop of utils.py:234-260.
+ * dets [D][7] / gts [G][7] rows [img,cx,cy,w,h,score,cls].  gts must be
+ * grouped by image (stable) and det_gt_lo/hi[d] give the gt range of det d's
+ * image.  det_rank[d] = position of det d in the reference's per-class
+ * descending-score order (any strictly order-preserving integer).  Outputs:
+ * tp[d] in {0,1} (fp32), best_iou[d], best_gt[d] (-1 if none).
+ * ------------------------------------------------------------------------- */
+int yolo_map_match(const float* dets, int D, const float* gts, int G, const int32_t* det_gt_lo,
+                   const int32_t* det_gt_hi, const int32_t* det_rank, float iou_thr,
+                   int box_format, float* tp, float* best_iou, int32_t* best_gt,
+                   int32_t* gt_claim /* [G] scratch */, yb_stream_t stream);
+
+/* Stable LSD radix sort of (u64 key, i32 value) pairs on bits [0,end_bit)
+ * (end_bit multiple of 8); K5's building block, exported for tests and for
+ * the mAP score ordering.  n_dev: device int32 holding the live count (<=max_n).
+ * Result lands in keys/vals (copied back if the pass count is odd).           */
+size_t yolo_sort_workspace_bytes(int max_n);
+int yolo_sort_pairs(uint64_t* keys, int32_t* vals, const int32_t* n_dev, int max_n, int end_bit,
+                    void* workspace, size_t workspace_bytes, yb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO_B200_H_ */

@@ -1,0 +1,379 @@
+// K4 + K5 + K6: confidence-threshold compaction (warp/block ballot scan, order
+// preserving), stable segmented sort and per-(image, class) greedy NMS for a
+// whole batch.  Replaces utils.py:150-191 (non_max_suppression) including its
+// filter (:165), its stable descending sort (:166) and its greedy loop
+// (:170-187).  Bit-exact contract: the kept rows and their order are the
+// reference's, because (a) the IoU is the reference's fp32 op sequence
+// (common.cuh yb_iou), (b) the sort is stable on (score desc, input position)
+// and (c) "box k survives iff no earlier surviving box of the same class has
+// !(iou < thr)" is the fixed point of the reference's loop.
+#include "sort.cuh"
+
+namespace {
+
+constexpr int NMS_THREADS = 512;
+
+__device__ __forceinline__ int find_image(const int32_t* __restrict__ off, int batch, int i) {
+  int lo = 0, hi = batch;  // largest b with off[b] <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// utils.py:165  `box[4] > obj_threshold` is a Python double comparison.
+__device__ __forceinline__ bool passes(float score, double thr) { return (double)score > thr; }
+
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_thr_count(const float* __restrict__ boxes, int total, double thr, int32_t* __restrict__ tile_cnt) {
+  const int base = blockIdx.x * COMPACT_TILE + threadIdx.x * COMPACT_ITEMS;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < COMPACT_ITEMS; ++k) {
+    const int i = base + k;
+    if (i < total && passes(boxes[size_t(i) * 6 + 4], thr)) ++c;
+  }
+  int tot;
+  block_exclusive_scan<COMPACT_THREADS>(c, &tot);
+  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_thr_write(const float* __restrict__ boxes, const int32_t* __restrict__ img_off, int batch,
+            int total, double thr, const int32_t* __restrict__ tile_off,
+            uint64_t* __restrict__ key, int32_t* __restrict__ val) {
+  const int base = blockIdx.x * COMPACT_TILE + threadIdx.x * COMPACT_ITEMS;
+  float sc[COMPACT_ITEMS];
+  unsigned flags = 0;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < COMPACT_ITEMS; ++k) {
+    const int i = base + k;
+    sc[k] = (i < total) ? boxes[size_t(i) * 6 + 4] : 0.f;
+    if (i < total && passes(sc[k], thr)) { flags |= 1u << k; ++c; }
+  }
+  int pos = tile_off[blockIdx.x] + block_exclusive_scan<COMPACT_THREADS>(c, nullptr);
+  if (!flags) return;
+  int b = find_image(img_off, batch, base);
+#pragma unroll
+  for (int k = 0; k < COMPACT_ITEMS; ++k) {
+    if (flags & (1u << k)) {
+      const int i = base + k;
+      while (b + 1 < batch && img_off[b + 1] <= i) ++b;  // skip empty images too
+      // descending score: invert the ascending key
+      key[pos] = (uint64_t(uint32_t(b)) << 32) | uint64_t(~yb_float_key_asc(sc[k]));
+      val[pos] = i;
+      ++pos;
+    }
+  }
+}
+
+// After sort #1 (image, score desc, position): p is the reference's output
+// order.  Build the (image, class) grouping key for sort #2.
+__global__ void k_class_keys(const float* __restrict__ boxes, const uint64_t* __restrict__ key1,
+                             const int32_t* __restrict__ val1, const int32_t* __restrict__ n_dev,
+                             uint64_t* __restrict__ key2, int32_t* __restrict__ val2,
+                             int32_t* __restrict__ idx1) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= *n_dev) return;
+  const int idx = val1[p];
+  idx1[p] = idx;
+  float cls = __fadd_rn(boxes[size_t(idx) * 6 + 5], 0.0f);  // -0.0 == 0.0 in utils.py:178
+  uint32_t cb = (cls != cls) ? 0x7fc00000u : __float_as_uint(cls);
+  key2[p] = (key1[p] & 0xffffffff00000000ull) | cb;
+  val2[p] = p;
+}
+
+__global__ void k_gather_segments(const float* __restrict__ boxes, const uint64_t* __restrict__ key2,
+                                  const int32_t* __restrict__ val2, const int32_t* __restrict__ idx1,
+                                  const int32_t* __restrict__ n_dev, int box_format,
+                                  float4* __restrict__ cbox, float* __restrict__ area,
+                                  uint8_t* __restrict__ suppressed, int32_t* __restrict__ seg_starts,
+                                  int32_t* __restrict__ nseg) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= *n_dev) return;
+  const float* r = boxes + size_t(idx1[val2[q]]) * 6;
+  const float w = r[2], h = r[3];
+  const CBox c = yb_make_cbox(r[0], r[1], w, h, box_format);
+  cbox[q] = make_float4(c.x1, c.y1, c.x2, c.y2);
+  area[q] = __fmul_rn(w, h);  // utils.py:79-80
+  suppressed[q] = 0;
+  if (q == 0 || key2[q] != key2[q - 1]) seg_starts[atomicAdd(nseg, 1)] = q;
+}
+
+// One CTA per (image, class) segment, boxes in descending-score order.  The
+// segment is walked in chunks of 32: warp 0 resolves the chunk serially from a
+// 32x32 IoU bit matrix held in registers (one row per lane, shuffled out), the
+// chunk's survivors are staged in shared memory, then the whole CTA applies
+// them to every later, still-alive box of the segment.
+__global__ void __launch_bounds__(NMS_THREADS)
+k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
+               const uint64_t* __restrict__ key2, const int32_t* __restrict__ val2,
+               const int32_t* __restrict__ seg_starts, const int32_t* __restrict__ nseg_dev,
+               const int32_t* __restrict__ n_dev, float thr, uint8_t* __restrict__ suppressed,
+               uint8_t* __restrict__ keep) {
+  __shared__ float4 s_box[32];
+  __shared__ float s_area[32];
+  __shared__ int s_nkept;
+  __shared__ int s_end;
+  const int n = *n_dev, nseg = *nseg_dev;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
+    const int s0 = seg_starts[s];
+    const uint64_t k = key2[s0];
+    if (tid == 0) {  // upper bound of k in the sorted keys
+      int lo = s0, hi = n;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (key2[mid] == k) lo = mid; else hi = mid;
+      }
+      s_end = hi;
+    }
+    __syncthreads();
+    const int s1 = s_end;
+    if (uint32_t(k) == 0x7fc00000u) {  // NaN class: != is always true (utils.py:178) => all kept
+      for (int q = s0 + tid; q < s1; q += NMS_THREADS) keep[val2[q]] = 1;
+      __syncthreads();
+      continue;
+    }
+    for (int c0 = s0; c0 < s1; c0 += 32) {
+      if (warp == 0) {
+        const int qi = c0 + lane;
+        const bool valid = qi < s1;
+        float4 b = valid ? cbox[qi] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float a = valid ? area[qi] : 0.f;
+        const bool sup = valid ? (suppressed[qi] != 0) : true;
+        CBox me{b.x, b.y, b.z, b.w};
+        unsigned row = 0;  // bit j: I suppress chunk member j (j later than me)
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+          CBox o;
+          o.x1 = __shfl_sync(0xffffffffu, b.x, j);
+          o.y1 = __shfl_sync(0xffffffffu, b.y, j);
+          o.x2 = __shfl_sync(0xffffffffu, b.z, j);
+          o.y2 = __shfl_sync(0xffffffffu, b.w, j);
+          const float ao = __shfl_sync(0xffffffffu, a, j);
+          if (j > lane && c0 + j < s1) {
+            const float iou = yb_iou(me, a, o, ao);
+            if (!(iou < thr)) row |= 1u << j;  // utils.py:179 keeps only iou < thr
+          }
+        }
+        unsigned alive = __ballot_sync(0xffffffffu, !sup);
+        unsigned kept = 0;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const unsigned ri = __shfl_sync(0xffffffffu, row, i);
+          if ((alive >> i) & 1u) { kept |= 1u << i; alive &= ~ri; }
+        }
+        if (valid) keep[val2[qi]] = (kept >> lane) & 1u;
+        if ((kept >> lane) & 1u) {
+          const int slot = __popc(kept & ((1u << lane) - 1u));
+          s_box[slot] = b;
+          s_area[slot] = a;
+        }
+        if (lane == 0) s_nkept = __popc(kept);
+      }
+      __syncthreads();
+      const int nk = s_nkept;
+      for (int q = c0 + 32 + tid; q < s1; q += NMS_THREADS) {
+        if (suppressed[q]) continue;
+        const float4 b = cbox[q];
+        const CBox later{b.x, b.y, b.z, b.w};
+        const float al = area[q];
+        for (int t = 0; t < nk; ++t) {
+          const float4 e = s_box[t];
+          const CBox early{e.x, e.y, e.z, e.w};
+          const float iou = yb_iou(early, s_area[t], later, al);
+          if (!(iou < thr)) { suppressed[q] = 1; break; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_keep_count(const uint8_t* __restrict__ keep, const int32_t* __restrict__ n_dev,
+             int32_t* __restrict__ tile_cnt) {
+  const int n = *n_dev;
+  const int base = blockIdx.x * COMPACT_TILE + threadIdx.x * COMPACT_ITEMS;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < COMPACT_ITEMS; ++k) c += (base + k < n && keep[base + k]) ? 1 : 0;
+  int tot;
+  block_exclusive_scan<COMPACT_THREADS>(c, &tot);
+  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_keep_write(const uint8_t* __restrict__ keep, const uint64_t* __restrict__ key1,
+             const int32_t* __restrict__ idx1, const int32_t* __restrict__ n_dev,
+             const int32_t* __restrict__ tile_off, int32_t* __restrict__ keep_idx,
+             int32_t* __restrict__ keep_off) {
+  const int n = *n_dev;
+  const int base = blockIdx.x * COMPACT_TILE + threadIdx.x * COMPACT_ITEMS;
+  unsigned flags = 0;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < COMPACT_ITEMS; ++k)
+    if (base + k < n && keep[base + k]) { flags |= 1u << k; ++c; }
+  int pos = tile_off[blockIdx.x] + block_exclusive_scan<COMPACT_THREADS>(c, nullptr);
+#pragma unroll
+  for (int k = 0; k < COMPACT_ITEMS; ++k) {
+    if (flags & (1u << k)) {
+      const int p = base + k;
+      keep_idx[pos++] = idx1[p];
+      atomicAdd(&keep_off[int(key1[p] >> 32)], 1);  // per-image counts, scanned afterwards
+    }
+  }
+}
+
+struct NmsWs {
+  int32_t* tile_cnt;
+  int32_t* scalars;  // [0] n_valid, [1] nseg
+  uint64_t* key1;
+  int32_t* val1;
+  uint64_t* key2;
+  int32_t* val2;
+  int32_t* idx1;
+  float4* cbox;
+  float* area;
+  uint8_t* suppressed;
+  uint8_t* keep;
+  int32_t* seg_starts;
+  SortBuffers sb;
+  int ctiles;
+};
+
+void nms_carve(WsCarver& ws, int total, NmsWs* w) {
+  const int t = total > 0 ? total : 1;
+  w->ctiles = yb_cdiv(t, COMPACT_TILE);
+  w->tile_cnt = ws.take<int32_t>(w->ctiles + 1);
+  w->scalars = ws.take<int32_t>(8);
+  w->key1 = ws.take<uint64_t>(t);
+  w->val1 = ws.take<int32_t>(t);
+  w->key2 = ws.take<uint64_t>(t);
+  w->val2 = ws.take<int32_t>(t);
+  w->idx1 = ws.take<int32_t>(t);
+  w->cbox = ws.take<float4>(t);
+  w->area = ws.take<float>(t);
+  w->suppressed = ws.take<uint8_t>(t);
+  w->keep = ws.take<uint8_t>(t);
+  w->seg_starts = ws.take<int32_t>(t);
+  sort_carve(ws, t, &w->sb);
+}
+
+}  // namespace
+
+extern "C" size_t yolo_nms_workspace_bytes(int total, int batch) {
+  (void)batch;
+  WsCarver ws(nullptr);
+  NmsWs w;
+  nms_carve(ws, total, &w);
+  return ws.bytes();
+}
+
+extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batch, int total,
+                        float iou_thr, double obj_thr, int box_format, int32_t* keep_idx,
+                        int32_t* keep_off, void* workspace, size_t workspace_bytes,
+                        yb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  YB_REQUIRE(batch >= 1 && total >= 0, "yolo_nms: batch must be >= 1 and total >= 0");
+  YB_REQUIRE(box_format == YB_BOX_CENTER || box_format == YB_BOX_CORNERS, "yolo_nms: bad box_format");
+  YB_REQUIRE(keep_off != nullptr, "yolo_nms: keep_off is null");
+  if (workspace_bytes < yolo_nms_workspace_bytes(total, batch)) {
+    yb_set_error("yolo_nms: workspace too small (%zu < %zu)", workspace_bytes,
+                 yolo_nms_workspace_bytes(total, batch));
+    return YB_ERR_WORKSPACE;
+  }
+  YB_CHECK_CUDA(cudaMemsetAsync(keep_off, 0, sizeof(int32_t) * (batch + 1), stream));
+  if (total == 0) return YB_OK;
+  YB_REQUIRE(boxes && img_offsets && keep_idx && workspace, "yolo_nms: null pointer");
+  WsCarver ws(workspace);
+  NmsWs w;
+  nms_carve(ws, total, &w);
+  int32_t* n_valid = w.scalars;
+  int32_t* nseg = w.scalars + 1;
+  YB_CHECK_CUDA(cudaMemsetAsync(w.scalars, 0, sizeof(int32_t) * 8, stream));
+
+  // K4: ordered threshold compaction -> (key, row index) pairs
+  k_thr_count<<<w.ctiles, COMPACT_THREADS, 0, stream>>>(boxes, total, obj_thr, w.tile_cnt);
+  YB_CHECK_LAUNCH();
+  int rc = exclusive_scan_small(w.tile_cnt, w.ctiles, n_valid, stream);
+  if (rc) return rc;
+  k_thr_write<<<w.ctiles, COMPACT_THREADS, 0, stream>>>(boxes, img_offsets, batch, total, obj_thr,
+                                                        w.tile_cnt, w.key1, w.val1);
+  YB_CHECK_LAUNCH();
+
+  // K5: (image, score desc, position) then regroup by (image, class)
+  int img_bits = 0;
+  while ((1 << img_bits) < batch) ++img_bits;
+  const int img_hi = 32 + ((img_bits + 7) / 8) * 8;
+  rc = radix_sort_pairs(w.key1, w.val1, n_valid, total, 0, 32, w.sb, stream);
+  if (rc) return rc;
+  rc = radix_sort_pairs(w.key1, w.val1, n_valid, total, 32, img_hi, w.sb, stream);
+  if (rc) return rc;
+  const int eb = 256, eg = yb_cdiv(total, eb);
+  k_class_keys<<<eg, eb, 0, stream>>>(boxes, w.key1, w.val1, n_valid, w.key2, w.val2, w.idx1);
+  YB_CHECK_LAUNCH();
+  rc = radix_sort_pairs(w.key2, w.val2, n_valid, total, 0, 32, w.sb, stream);
+  if (rc) return rc;
+  rc = radix_sort_pairs(w.key2, w.val2, n_valid, total, 32, img_hi, w.sb, stream);
+  if (rc) return rc;
+  k_gather_segments<<<eg, eb, 0, stream>>>(boxes, w.key2, w.val2, w.idx1, n_valid, box_format,
+                                           w.cbox, w.area, w.suppressed, w.seg_starts, nseg);
+  YB_CHECK_LAUNCH();
+
+  // K6: greedy NMS per (image, class) segment
+  int dev = 0, sms = 148;
+  YB_CHECK_CUDA(cudaGetDevice(&dev));
+  YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int grid = sms * 4;
+  if (grid > total) grid = total;
+  k_nms_segments<<<grid, NMS_THREADS, 0, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts,
+                                                   nseg, n_valid, iou_thr, w.suppressed, w.keep);
+  YB_CHECK_LAUNCH();
+
+  // survivors, in the reference's order, + per-image offsets
+  k_keep_count<<<w.ctiles, COMPACT_THREADS, 0, stream>>>(w.keep, n_valid, w.tile_cnt);
+  YB_CHECK_LAUNCH();
+  rc = exclusive_scan_small(w.tile_cnt, w.ctiles, nullptr, stream);
+  if (rc) return rc;
+  k_keep_write<<<w.ctiles, COMPACT_THREADS, 0, stream>>>(w.keep, w.key1, w.idx1, n_valid,
+                                                         w.tile_cnt, keep_idx, keep_off);
+  YB_CHECK_LAUNCH();
+  return exclusive_scan_small(keep_off, batch + 1, nullptr, stream);
+}
+
+// ---- element-wise IoU: utils.py:38-84 calc_iou / utils.py:22-36 iou_aligned --
+namespace {
+__global__ void k_iou(const float* __restrict__ b1, int n1, int st1, const float* __restrict__ b2,
+                      int n2, int st2, int fmt, int aligned, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = b1 + size_t(n1 == 1 ? 0 : i) * st1;
+  const float* q = b2 + size_t(n2 == 1 ? 0 : i) * st2;
+  if (aligned) {  // utils.py:34-36
+    const float inter = __fmul_rn(yb_nanmin(p[0], q[0]), yb_nanmin(p[1], q[1]));
+    const float uni = __fsub_rn(__fadd_rn(__fmul_rn(p[0], p[1]), __fmul_rn(q[0], q[1])), inter);
+    out[i] = __fdiv_rn(inter, uni);
+    return;
+  }
+  const CBox a = yb_make_cbox(p[0], p[1], p[2], p[3], fmt);
+  const CBox b = yb_make_cbox(q[0], q[1], q[2], q[3], fmt);
+  out[i] = yb_iou(a, __fmul_rn(p[2], p[3]), b, __fmul_rn(q[2], q[3]));
+}
+}  // namespace
+
+extern "C" int yolo_iou(const float* boxes1, int n1, int stride1, const float* boxes2, int n2,
+                        int stride2, int box_format, int aligned, float* out, yb_stream_t stream) {
+  YB_REQUIRE(n1 >= 0 && n2 >= 0, "yolo_iou: negative count");
+  YB_REQUIRE(n1 == n2 || n1 == 1 || n2 == 1, "yolo_iou: shapes do not broadcast");
+  const int n = (n1 == 0 || n2 == 0) ? 0 : (n1 > n2 ? n1 : n2);
+  if (n == 0) return YB_OK;
+  k_iou<<<yb_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(boxes1, n1, stride1, boxes2, n2, stride2,
+                                                          box_format, aligned, out, n);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
