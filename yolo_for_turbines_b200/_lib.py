@@ -1,0 +1,119 @@
+"""ctypes binding of libyolo_b200.so (the C-ABI declared in include/yolo_b200.h).
+
+The library is built in-tree by `python -m yolo_for_turbines_b200.build` (or
+`__graft_entry__.build()`).  There is deliberately NO fallback: if the shared object is missing
+or a call fails, an exception is raised -- the product path never routes through torch ops or the
+CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libyolo_b200.so")
+
+YB_OK = 0
+STATUS_NAN_INPUT = 1
+STATUS_NAN_LAYER = 2
+ACT_CODES = {None: 0, "none": 0, "leaky_relu": 1, "mish": 2}
+BOX_CENTER, BOX_CORNERS = 0, 1
+
+
+class YoloB200Error(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    """Mirror of `yolo_conv_desc` (include/yolo_b200.h)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "batch", "h_in", "w_in", "c_in", "in_pitch", "c_out", "c_out_pad", "out_pitch", "ksize", "stride", "pad",
+        "act", "has_residual", "res_pitch", "upsample2x", "out_fp32", "check_nan", "a_mode", "block_n_hint",
+        "stages_hint")]
+
+
+_P, _I, _F, _D, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t
+
+# name -> (restype, argtypes); every int-returning entry is error-checked by _Lib.__getattr__
+SIGNATURES = {
+    "yolo_last_error": (C.c_char_p, []),
+    "yolo_version": (_I, []),
+    "yolo_device_info": (_I, [_I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "yolo_conv_plan_bytes": (_SZ, []),
+    "yolo_conv_plan_init": (_I, [_P, _SZ, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "yolo_conv_fwd": (_I, [_P, _P, _P]),
+    "yolo_conv_plan_info": (_I, [_P, C.POINTER(C.c_int32)]),
+    "yolo_conv_fwd_simt": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "yolo_pack_weights": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "yolo_pack_stem_weights": (_I, [_P, _I, _I, _I, _P, _P]),
+    "yolo_fold_bn": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P]),
+    "yolo_nchw_to_nhwc_bf16": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "yolo_nhwc_to_nchw_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "yolo_input_patchify": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "yolo_decode": (_I, [_P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _I, _I, _P, _I, _I, _P]),
+    "yolo_nms_workspace_bytes": (_SZ, [_I, _I]),
+    "yolo_nms": (_I, [_P, _P, _I, _I, _F, _D, _I, _P, _P, _P, _SZ, _P]),
+    "yolo_iou": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
+    "yolo_map_match": (_I, [_P, _I, _P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P]),
+    "yolo_sort_workspace_bytes": (_SZ, [_I]),
+    "yolo_sort_pairs": (_I, [_P, _P, _P, _I, _I, _P, _SZ, _P]),
+}
+
+
+class _Lib:
+    def __init__(self):
+        self._dll = None
+
+    def _load(self):
+        if self._dll is None:
+            if not os.path.isfile(LIB_PATH):
+                raise YoloB200Error(
+                    f"{LIB_PATH} is missing: build it with `python -m yolo_for_turbines_b200.build` "
+                    "(nvcc, sm_100a).  There is no CPU/PyTorch fallback for this path.")
+            dll = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(dll, name)  # AttributeError => header and library disagree
+                fn.restype, fn.argtypes = res, args
+            self._dll = dll
+        return self._dll
+
+    def raw(self, name):
+        return getattr(self._load(), name)
+
+    def __getattr__(self, name):
+        if name.startswith("_") or name not in SIGNATURES:
+            raise AttributeError(name)
+        fn = self.raw(name)
+        if SIGNATURES[name][0] is not _I or name == "yolo_version":
+            return fn
+
+        def checked(*args):
+            rc = fn(*args)
+            if rc != YB_OK:
+                msg = self.raw("yolo_last_error")().decode(errors="replace")
+                raise YoloB200Error(f"{name} failed ({rc}): {msg}")
+            return rc
+
+        checked.__name__ = name
+        return checked
+
+
+lib = _Lib()
+
+
+def ptr(t):
+    """Device/host pointer of a tensor (or NULL)."""
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise YoloB200Error(
+            f"{what} must be a CUDA tensor: this package is the sm_100a path only and has no CPU fallback "
+            f"(got device {t.device}).")

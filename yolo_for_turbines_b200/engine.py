@@ -1,0 +1,340 @@
+"""Host-side executor of the YOLOv3 forward pass on the sm_100a conv kernels.
+
+What the reference does with one ATen/cuDNN call per op (code/model.py:172-193) is planned here
+once per (batch, H, W): every CNNBlock becomes ONE fused launch (conv + folded BN + activation
+[+ residual]) on NHWC bf16 buffers; nn.Upsample is a 2x2 replicated store of the producing conv
+and torch.cat is two producers writing disjoint channel ranges of one buffer (model.py:189-191,
+:222), so neither exists as a kernel.  The launch list is captured in a CUDA graph and replayed.
+Buffers, packed weights and TMA tensor maps are static per plan; torch owns all memory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from ._lib import ACT_CODES, STATUS_NAN_INPUT, STATUS_NAN_LAYER, ConvDesc, YoloB200Error, lib, ptr, stream_ptr
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def _act_name(block) -> str:
+    if not block.batch_norm_act:
+        return "none"
+    if isinstance(block.activation, nn.LeakyReLU):
+        if abs(block.activation.negative_slope - 0.1) > 1e-12:
+            raise YoloB200Error("only LeakyReLU(0.1) is implemented (code/model.py:64)")
+        return "leaky_relu"
+    if isinstance(block.activation, nn.Mish):
+        return "mish"
+    raise YoloB200Error(f"unsupported activation module {type(block.activation).__name__}")
+
+
+class PackedConv:
+    """bf16 K-major weights + folded-BN scale/bias of one CNNBlock, refreshed in place so that
+    plans and CUDA graphs that hold their addresses stay valid across weight updates."""
+
+    def __init__(self, block, device, as_stem: bool = False):
+        conv = block.conv
+        k, s, p = conv.kernel_size, conv.stride, conv.padding
+        if k[0] != k[1] or s[0] != s[1] or p[0] != p[1] or k[0] not in (1, 3) or s[0] not in (1, 2) \
+                or p[0] != (1 if k[0] == 3 else 0) or conv.groups != 1 or conv.dilation != (1, 1):
+            raise YoloB200Error(f"conv {k}/{s}/{p} is outside the YOLOv3 layer set (1x1/p0 or 3x3/p1, stride 1|2)")
+        self.block = block
+        self.ksize, self.stride, self.pad = k[0], s[0], p[0]
+        self.c_in, self.c_out = conv.in_channels, conv.out_channels
+        self.c_out_pad = _round_up(self.c_out, 32)
+        self.act = _act_name(block)
+        self.stem = bool(as_stem)
+        if self.stem:  # runs as a 1x1 conv over the 32-wide patch matrix (yolo_input_patchify)
+            assert self.ksize == 3 and self.stride == 1 and 9 * self.c_in <= 32
+            self.k_eff, self.stride_eff, self.pad_eff, self.c_in_eff = 1, 1, 0, 32
+        else:
+            self.k_eff, self.stride_eff, self.pad_eff = self.ksize, self.stride, self.pad
+            self.c_in_eff = _round_up(self.c_in, 32)
+        self.w = torch.empty(self.c_out_pad * self.k_eff * self.k_eff * self.c_in_eff, dtype=torch.bfloat16, device=device)
+        self.scale = torch.empty(self.c_out_pad, dtype=torch.float32, device=device)
+        self.bias = torch.empty(self.c_out_pad, dtype=torch.float32, device=device)
+
+    def tensors(self):
+        b = self.block
+        ts = [b.conv.weight]
+        if b.conv.bias is not None:
+            ts.append(b.conv.bias)
+        if b.batch_norm_act:
+            ts += [b.batch_norm.weight, b.batch_norm.bias, b.batch_norm.running_mean, b.batch_norm.running_var]
+        return ts
+
+    def refresh(self):
+        b = self.block
+        st = stream_ptr(self.w.device)
+        f32 = lambda t: t.detach().to(device=self.w.device, dtype=torch.float32).contiguous()  # noqa: E731
+        w = f32(b.conv.weight)
+        if self.stem:
+            lib.yolo_pack_stem_weights(ptr(w), self.c_out, self.c_in, self.c_out_pad, ptr(self.w), st)
+        else:
+            lib.yolo_pack_weights(ptr(w), self.c_out, self.c_in, self.ksize, self.c_out_pad, self.c_in_eff, ptr(self.w), st)
+        if b.batch_norm_act:
+            bn = b.batch_norm
+            g, be, mu, var = f32(bn.weight), f32(bn.bias), f32(bn.running_mean), f32(bn.running_var)
+            lib.yolo_fold_bn(ptr(g), ptr(be), ptr(mu), ptr(var), None, float(bn.eps), self.c_out, self.c_out_pad,
+                             ptr(self.scale), ptr(self.bias), st)
+        else:
+            cb = f32(b.conv.bias) if b.conv.bias is not None else None
+            lib.yolo_fold_bn(None, None, None, None, ptr(cb), 0.0, self.c_out, self.c_out_pad, ptr(self.scale),
+                             ptr(self.bias), st)
+
+
+class _Act:
+    """Symbolic NHWC activation; `root`/`ch_off` let it live inside a wider (concat) buffer."""
+    __slots__ = ("C", "H", "W", "fp32", "root", "ch_off", "first", "last", "buf")
+
+    def __init__(self, C_, H, W, fp32=False):
+        self.C, self.H, self.W, self.fp32 = C_, H, W, fp32
+        self.root, self.ch_off = None, 0
+        self.first, self.last, self.buf = None, None, None
+
+    def resolve(self):
+        t, off = self, 0
+        while t.root is not None:
+            off += t.ch_off
+            t = t.root
+        return t, off
+
+
+class _ConvOp:
+    __slots__ = ("pc", "src", "dst", "res", "upsample", "check_nan", "plan", "plan_ptr", "name")
+
+    def __init__(self, pc, src, dst, res=None, check_nan=True, name=""):
+        self.pc, self.src, self.dst, self.res = pc, src, dst, res
+        self.upsample, self.check_nan, self.name = False, check_nan, name
+        self.plan = self.plan_ptr = None
+
+
+def _aligned_blob(nbytes: int, align: int = 64):
+    raw = (C.c_uint8 * (nbytes + align))()
+    addr = C.addressof(raw)
+    off = (-addr) % align
+    return raw, C.c_void_p(addr + off)
+
+
+def make_conv_plan(desc: ConvDesc, x, w, scale, bias, residual, y):
+    raw, p = _aligned_blob(int(lib.yolo_conv_plan_bytes()))
+    lib.yolo_conv_plan_init(p, lib.yolo_conv_plan_bytes(), C.byref(desc), x, w, scale, bias, residual, y)
+    return raw, p
+
+
+class ForwardPlan:
+    """Everything static for one (batch, H, W): buffers, tensor maps, launch list, CUDA graph."""
+
+    def __init__(self, engine: "Engine", B: int, H: int, W: int, use_graph: bool = True):
+        from .model import CNNBlock, ResidualBlock, ScalePredictionBlock  # cycle-free at call time
+
+        self.engine, self.B, self.H, self.W = engine, B, H, W
+        model, dev = engine.model, engine.device
+        if H % 32 or W % 32:
+            raise YoloB200Error(f"input size {H}x{W} must be a multiple of 32 (five stride-2 stages)")
+        self.ops: List[_ConvOp] = []
+        self.heads: List[_Act] = []
+        layers = list(model.layers)
+        if not layers or not isinstance(layers[0], CNNBlock):
+            raise YoloB200Error("first layer must be a CNNBlock")
+        first_pc = engine.packed[id(layers[0])]
+        cur = _Act(first_pc.c_in_eff, H, W)
+        self.input_act, self.stem = cur, first_pc.stem
+        routes: List[_Act] = []
+
+        def conv(block, src, res=None, fp32=False, check_nan=True, name=""):
+            pc = engine.packed[id(block)]
+            ho = (src.H + 2 * pc.pad_eff - pc.k_eff) // pc.stride_eff + 1
+            wo = (src.W + 2 * pc.pad_eff - pc.k_eff) // pc.stride_eff + 1
+            dst = _Act(pc.c_out_pad if fp32 else pc.c_out, ho, wo, fp32)
+            if not fp32 and pc.c_out % 32:
+                raise YoloB200Error(f"{name}: intermediate channel count {pc.c_out} must be a multiple of 32")
+            if src.C != pc.c_in_eff:
+                raise YoloB200Error(f"{name}: expects {pc.c_in_eff} input channels, got {src.C}")
+            self.ops.append(_ConvOp(pc, src, dst, res, check_nan, name))
+            return dst
+
+        for li, layer in enumerate(layers):
+            if isinstance(layer, ScalePredictionBlock):  # model.py:177-179: does not advance x
+                t = conv(layer.pred_block[0], cur, check_nan=False, name=f"layers.{li}.pred_block.0")
+                self.heads.append(conv(layer.pred_block[1], t, fp32=True, check_nan=False, name=f"layers.{li}.pred_block.1"))
+                self.head_meta = getattr(self, "head_meta", []) + [(layer.anchors_per_scale, layer.num_classes)]
+            elif isinstance(layer, CNNBlock):
+                cur = conv(layer, cur, name=f"layers.{li}")
+            elif isinstance(layer, ResidualBlock):
+                for ri, seq in enumerate(layer.layers):
+                    t = conv(seq[0], cur, name=f"layers.{li}.layers.{ri}.0")
+                    cur = conv(seq[1], t, res=cur if layer.use_residual else None, name=f"layers.{li}.layers.{ri}.1")
+                if layer.num_blocks == 8:  # model.py:186-187
+                    routes.append(cur)
+            elif isinstance(layer, nn.Upsample):
+                sf = layer.scale_factor
+                if float(sf if not isinstance(sf, (tuple, list)) else sf[0]) != 2.0 or layer.mode != "nearest":
+                    raise YoloB200Error("only nn.Upsample(scale_factor=2, mode='nearest') is implemented")
+                prod = self.ops[-1]
+                if prod.dst is not cur or not routes:
+                    raise YoloB200Error("Upsample must directly follow a conv and have a pending route")
+                route = routes.pop()
+                cat = _Act(cur.C + route.C, 2 * cur.H, 2 * cur.W)
+                if (route.H, route.W) != (cat.H, cat.W):
+                    raise YoloB200Error("route / upsample size mismatch")
+                up = _Act(cur.C, cat.H, cat.W)
+                up.root, up.ch_off = cat, 0              # model.py:190: upsampled channels first
+                route.root, route.ch_off = cat, cur.C
+                prod.dst, prod.upsample = up, True
+                cur = cat
+            else:
+                raise YoloB200Error(f"unsupported layer type {type(layer).__name__}")
+
+        # ---- liveness on root buffers, then greedy reuse -------------------------------------
+        self.input_root = self.input_act.resolve()[0]
+        self.input_root.first = -1
+        for i, op in enumerate(self.ops):
+            for t in (op.src, op.dst, op.res):
+                if t is None:
+                    continue
+                r = t.resolve()[0]
+                r.first = i if r.first is None else r.first
+                r.last = i
+        for h in self.heads:
+            h.resolve()[0].last = len(self.ops) + 1  # head buffers outlive the forward
+        pool = []  # [tensor(uint8), free_from_op]
+        self.total_bytes = 0
+        roots = sorted({id(t.resolve()[0]): t.resolve()[0] for op in self.ops for t in (op.src, op.dst, op.res) if t}.values(),
+                       key=lambda r: r.first)
+        for r in roots:
+            need = B * r.H * r.W * r.C * (4 if r.fp32 else 2)
+            best = None
+            for ent in pool:
+                if ent[1] <= r.first and ent[0].numel() >= need and (best is None or ent[0].numel() < best[0].numel()):
+                    best = ent
+            if best is None:
+                best = [torch.empty(_round_up(need, 256), dtype=torch.uint8, device=dev), 0]
+                pool.append(best)
+                self.total_bytes += best[0].numel()
+            best[1] = r.last + 1
+            r.buf = best[0]
+        self.pool = pool
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        # ---- plans ---------------------------------------------------------------------------
+        for op in self.ops:
+            pc = op.pc
+            sroot, soff = op.src.resolve()
+            droot, doff = op.dst.resolve()
+            d = ConvDesc()
+            d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch = B, op.src.H, op.src.W, pc.c_in_eff, sroot.C
+            d.c_out, d.c_out_pad, d.out_pitch = pc.c_out, pc.c_out_pad, droot.C
+            d.ksize, d.stride, d.pad = pc.k_eff, pc.stride_eff, pc.pad_eff
+            d.act = ACT_CODES[pc.act]
+            d.upsample2x, d.out_fp32, d.check_nan = int(op.upsample), int(op.dst.fp32), int(op.check_nan)
+            d.a_mode, d.block_n_hint, d.stages_hint = 0, engine.block_n_hint, engine.stages_hint
+            x_ptr = sroot.buf.data_ptr() + soff * 2
+            y_ptr = droot.buf.data_ptr() + doff * (4 if op.dst.fp32 else 2)
+            r_ptr = None
+            if op.res is not None:
+                rroot, roff = op.res.resolve()
+                d.has_residual, d.res_pitch = 1, rroot.C
+                r_ptr = C.c_void_p(rroot.buf.data_ptr() + roff * 2)
+            op.plan, op.plan_ptr = make_conv_plan(d, C.c_void_p(x_ptr), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), r_ptr,
+                                                  C.c_void_p(y_ptr))
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.use_graph = use_graph
+        self.launches_per_forward = len(self.ops) + 1
+
+    # ------------------------------------------------------------------------------------------
+    def head_views(self):
+        """(B,3,S,S,5+nc) fp32 views of the NHWC head buffers -- the same non-contiguous layout the
+        reference's reshape+permute yields (model.py:147-148)."""
+        outs = []
+        for h, (na, nc) in zip(self.heads, self.head_meta):
+            root, _ = h.resolve()
+            ch = nc + 5
+            flat = root.buf[: self.B * h.H * h.W * root.C * 4].view(torch.float32)
+            outs.append(torch.as_strided(flat, (self.B, na, h.H, h.W, ch),
+                                         (h.H * h.W * root.C, ch, h.W * root.C, root.C, 1)))
+        return outs
+
+    def _launch_convs(self):
+        st = stream_ptr(self.engine.device)
+        sp = ptr(self.status)
+        for op in self.ops:
+            lib.yolo_conv_fwd(op.plan_ptr, sp, st)
+
+    def _launch_input(self, x):
+        st = stream_ptr(self.engine.device)
+        self.status.zero_()
+        dst = ptr(self.input_root.buf)
+        if self.stem:
+            lib.yolo_input_patchify(ptr(x), self.B, x.shape[1], self.H, self.W, dst, ptr(self.status), st)
+        else:
+            lib.yolo_nchw_to_nhwc_bf16(ptr(x), self.B, x.shape[1], self.H, self.W, self.input_act.C, self.input_root.C,
+                                       dst, ptr(self.status), st)
+
+    def run(self, x: torch.Tensor):
+        """Enqueues the forward on the current stream; no host sync."""
+        self._launch_input(x)
+        if not self.use_graph:
+            self._launch_convs()
+            return
+        if self.graph is None:
+            self._launch_convs()  # warm-up: sets the dynamic-smem attributes outside capture
+            torch.cuda.current_stream(self.engine.device).synchronize()
+            self._launch_input(x)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch_convs()
+            self.graph = g
+        self.graph.replay()
+
+    def check_status(self):
+        s = int(self.status.item())  # the ONE host sync of a forward (the reference has 28)
+        if s & STATUS_NAN_INPUT:
+            raise AssertionError("NaN in the input tensor")  # model.py:175
+        if s & STATUS_NAN_LAYER:
+            raise ValueError("Nan in layer")  # model.py:184
+
+
+class Engine:
+    """Per-model cache: packed weights (refreshed when parameters change) + plans per input shape."""
+
+    def __init__(self, model, device):
+        from .model import CNNBlock
+
+        self.model, self.device = model, torch.device(device)
+        self.block_n_hint, self.stages_hint = 0, 0
+        self.packed: Dict[int, PackedConv] = {}
+        blocks = [m for m in model.modules() if isinstance(m, CNNBlock)]
+        first = model.layers[0] if hasattr(model, "layers") and len(model.layers) else None
+        with torch.cuda.device(self.device):
+            for b in blocks:
+                stem = b is first and b.conv.kernel_size == (3, 3) and b.conv.stride == (1, 1) and 9 * b.conv.in_channels <= 32
+                self.packed[id(b)] = PackedConv(b, self.device, as_stem=stem)
+        self.plans: Dict[tuple, ForwardPlan] = {}
+        self._sig = None
+
+    def _signature(self):
+        return tuple((t._version, t.data_ptr()) for pc in self.packed.values() for t in pc.tensors())
+
+    def refresh_if_needed(self):
+        sig = self._signature()
+        if sig != self._sig:
+            with torch.cuda.device(self.device):
+                for pc in self.packed.values():
+                    pc.refresh()
+            self._sig = sig
+
+    def plan(self, B, H, W) -> ForwardPlan:
+        key = (B, H, W)
+        p = self.plans.get(key)
+        if p is None:
+            with torch.cuda.device(self.device):
+                p = ForwardPlan(self, B, H, W)
+            self.plans[key] = p
+        return p

@@ -1,0 +1,355 @@
+"""Drop-in mirror of the hot-path functions of the reference's `code/utils.py`, on sm_100a kernels.
+
+Reference signatures kept verbatim (paths relative to the reference checkout):
+    iou_aligned(box1, box2)                                              utils.py:22
+    calc_iou(boxes1, boxes2, box_format="center")                        utils.py:38
+    cells_to_boxes(predictions, anchors, grid_size, is_pred=True)        utils.py:86
+    non_max_suppression(boxes, iou_threshold, obj_threshold, box_format="corners")   utils.py:150
+    calc_mAP(pred_boxes, true_boxes, iou_threshold=0.5, box_format="center", num_classes=20)  utils.py:193
+    get_eval_boxes(loader, model, iou_threshold, anchors, obj_threshold, box_format="center", device=...)  utils.py:276
+plus the names BASELINE.json's north_star uses (cells_to_bboxes, intersection_over_union,
+mean_average_precision) as aliases, and tensor-in/tensor-out variants (decode_boxes, batched_nms,
+detect, map_match) that skip the Python-list materialisation the reference API forces.
+
+Everything runs through libyolo_b200.so; there is no CPU fallback -- inputs are moved to the CUDA
+device (lists/CPU tensors are accepted because the reference API passes Python lists) and a missing
+library or GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import config
+from ._lib import BOX_CENTER, BOX_CORNERS, YoloB200Error, lib, ptr, stream_ptr
+
+
+def _device(device=None) -> torch.device:
+    if device is not None:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise YoloB200Error("this package is the sm_100a path only: a CUDA device is required (no CPU fallback)")
+        return device
+    if not torch.cuda.is_available():
+        raise YoloB200Error("no CUDA device visible: the sm_100a kernels cannot run and there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _fmt(box_format: str) -> int:
+    # utils.py:57-67: only the literal "center" converts; every other string means top-left x,y + w,h
+    return BOX_CENTER if box_format == "center" else BOX_CORNERS
+
+
+def _as_f32_cuda(t, device=None) -> torch.Tensor:
+    if not torch.is_tensor(t):
+        t = torch.tensor(t, dtype=torch.float32)
+    dev = t.device if t.is_cuda else _device(device)
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
+# ---------------------------------------------------------------------------------------- IoU
+def calc_iou(boxes1, boxes2, box_format="center"):
+    """Element-wise IoU with the reference's exact fp32 op order and +1e-6 (utils.py:38-84)."""
+    b1, b2 = _as_f32_cuda(boxes1), _as_f32_cuda(boxes2)
+    b2 = b2.to(b1.device)
+    if b1.dim() == 1:
+        b1 = b1.unsqueeze(0)
+    if b2.dim() == 1:
+        b2 = b2.unsqueeze(0)
+    lead = torch.broadcast_shapes(b1.shape[:-1], b2.shape[:-1])
+    b1f = b1.expand(*lead, b1.shape[-1]).reshape(-1, b1.shape[-1]).contiguous()
+    b2f = b2.expand(*lead, b2.shape[-1]).reshape(-1, b2.shape[-1]).contiguous()
+    n = b1f.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=b1.device)
+    with torch.cuda.device(b1.device):
+        lib.yolo_iou(ptr(b1f), n, b1f.shape[1], ptr(b2f), n, b2f.shape[1], _fmt(box_format), 0, ptr(out),
+                     stream_ptr(b1.device))
+    return out.reshape(lead)
+
+
+def iou_aligned(box1, box2):
+    """IoU of [w, h] pairs sharing a centre (utils.py:22-36) -- used by anchor assignment."""
+    b1, b2 = _as_f32_cuda(box1), _as_f32_cuda(box2)
+    b2 = b2.to(b1.device)
+    lead = torch.broadcast_shapes(b1.shape[:-1], b2.shape[:-1])
+    b1f = b1.expand(*lead, 2).reshape(-1, 2).contiguous()
+    b2f = b2.expand(*lead, 2).reshape(-1, 2).contiguous()
+    n = b1f.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=b1.device)
+    with torch.cuda.device(b1.device):
+        lib.yolo_iou(ptr(b1f), n, 2, ptr(b2f), n, 2, 0, 1, ptr(out), stream_ptr(b1.device))
+    return out.reshape(lead)
+
+
+# ------------------------------------------------------------------------------------- decode
+def decode_boxes(predictions: torch.Tensor, anchors, grid_size: int, is_pred: bool = True,
+                 out: Optional[torch.Tensor] = None, out_offset: int = 0, writeback: bool = False) -> torch.Tensor:
+    """Tensor form of cells_to_boxes: (B,3,S,S,5+nc) fp32 (any strides) -> rows [cx,cy,w,h,obj,cls].
+    With `out` (B, N, 6) given, writes rows [out_offset, out_offset + 3*S*S) of every image so that
+    the three scales land in one candidate tensor in the reference's order (utils.py:300-309)."""
+    if not predictions.is_cuda:
+        raise YoloB200Error("decode_boxes needs a CUDA tensor (no CPU fallback)")
+    if predictions.dtype != torch.float32:
+        if writeback:
+            raise YoloB200Error("writeback needs an fp32 predictions tensor")
+        predictions = predictions.float()
+    B, A, S, S2, Cc = predictions.shape
+    if A != 3 or S != grid_size or S2 != grid_size:
+        raise YoloB200Error(f"predictions {tuple(predictions.shape)} do not match grid_size {grid_size} / 3 anchors")
+    anc = torch.as_tensor(anchors, dtype=torch.float32).reshape(-1).cpu()
+    if anc.numel() != 6:
+        raise YoloB200Error("anchors must hold 3 (w, h) pairs")
+    n = 3 * S * S
+    if out is None:
+        out = torch.empty(B, n, 6, dtype=torch.float32, device=predictions.device)
+        out_offset = 0
+    nc = Cc - 5
+    strides = (C.c_int64 * 5)(*predictions.stride())
+    anc_c = (C.c_float * 6)(*anc.tolist())
+    with torch.cuda.device(predictions.device):
+        lib.yolo_decode(ptr(predictions), strides, B, S, nc, anc_c, int(bool(is_pred)), int(bool(writeback)), ptr(out),
+                        out.shape[1], out_offset, stream_ptr(predictions.device))
+    return out
+
+
+def cells_to_boxes(predictions, anchors, grid_size, is_pred=True):
+    """utils.py:86-148: returns the nested list B x 3*S*S x [cx,cy,w,h,obj,cls] and, like the
+    reference, rewrites predictions[..., 0:4] in place when is_pred (utils.py:102-110)."""
+    if not torch.is_tensor(predictions):
+        raise TypeError("predictions must be a tensor")
+    if predictions.is_cuda and predictions.dtype == torch.float32:
+        return decode_boxes(predictions, anchors, grid_size, is_pred, writeback=bool(is_pred)).tolist()
+    dev = _device()
+    work = predictions.to(device=dev, dtype=torch.float32)
+    out = decode_boxes(work, anchors, grid_size, is_pred, writeback=bool(is_pred))
+    if is_pred:  # propagate the reference's input mutation back to the caller's tensor
+        predictions[..., :4] = work[..., :4].to(device=predictions.device, dtype=predictions.dtype)
+    return out.tolist()
+
+
+# ---------------------------------------------------------------------------------------- NMS
+@dataclass
+class NmsResult:
+    boxes: torch.Tensor      # [total, 6] candidates as given
+    keep_idx: torch.Tensor   # [total] int32: row indices of survivors, image-major, reference order
+    keep_off: torch.Tensor   # [B+1] int32: image b owns keep_idx[keep_off[b]:keep_off[b+1]]
+
+    def kept_rows(self) -> List[torch.Tensor]:
+        off = self.keep_off.tolist()
+        rows = self.boxes[self.keep_idx[: off[-1]].long()]
+        return [rows[off[b]:off[b + 1]] for b in range(len(off) - 1)]
+
+    def to_lists(self) -> List[list]:
+        return [r.tolist() for r in self.kept_rows()]
+
+
+class NmsWorkspace:
+    """Caller-owned scratch for yolo_nms (sort ping-pong buffers, masks, segment lists)."""
+
+    def __init__(self, total: int, batch: int, device):
+        self.total, self.batch = total, batch
+        self.nbytes = int(lib.yolo_nms_workspace_bytes(total, batch))
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.keep_idx = torch.empty(max(total, 1), dtype=torch.int32, device=device)
+        self.keep_off = torch.zeros(batch + 1, dtype=torch.int32, device=device)
+
+
+def batched_nms(boxes: torch.Tensor, img_offsets: torch.Tensor, iou_threshold: float, obj_threshold: float,
+                box_format: str = "corners", workspace: Optional[NmsWorkspace] = None) -> NmsResult:
+    """Class-aware greedy NMS of a whole batch in one pipeline (K4 compaction, K5 sort, K6 NMS).
+    boxes [total,6] fp32 CUDA rows [x,y,w,h,score,cls]; img_offsets [B+1] int32 CUDA."""
+    if not boxes.is_cuda:
+        raise YoloB200Error("batched_nms needs CUDA tensors (no CPU fallback)")
+    boxes = boxes.to(torch.float32).contiguous()
+    total, B = boxes.shape[0], img_offsets.numel() - 1
+    img_offsets = img_offsets.to(device=boxes.device, dtype=torch.int32).contiguous()
+    ws = workspace
+    if ws is None or ws.total < total or ws.batch != B or ws.buf.device != boxes.device:
+        ws = NmsWorkspace(total, B, boxes.device)
+    thr32 = float(torch.tensor(iou_threshold, dtype=torch.float32))  # utils.py:179 compares in fp32
+    with torch.cuda.device(boxes.device):
+        lib.yolo_nms(ptr(boxes), ptr(img_offsets), B, total, thr32, float(obj_threshold), _fmt(box_format),
+                     ptr(ws.keep_idx), ptr(ws.keep_off), ptr(ws.buf), ws.nbytes, stream_ptr(boxes.device))
+    return NmsResult(boxes, ws.keep_idx, ws.keep_off)
+
+
+def non_max_suppression(boxes, iou_threshold, obj_threshold, box_format="corners"):
+    """utils.py:150-191 for ONE image: list (or tensor) of [x,y,w,h,obj,cls] -> surviving rows as a
+    list of lists in descending-score order; [] when nothing passes."""
+    if not torch.is_tensor(boxes):
+        if len(boxes) == 0:
+            return []
+        boxes = torch.tensor(boxes, dtype=torch.float32)
+    if boxes.numel() == 0:
+        return []
+    dev = boxes.device if boxes.is_cuda else _device()
+    b = boxes.to(device=dev, dtype=torch.float32).reshape(-1, 6).contiguous()
+    off = torch.tensor([0, b.shape[0]], dtype=torch.int32, device=dev)
+    return batched_nms(b, off, iou_threshold, obj_threshold, box_format).to_lists()[0]
+
+
+# ---------------------------------------------------------------------------------------- mAP
+def map_match(dets: torch.Tensor, gts: torch.Tensor, iou_threshold: float = 0.5, box_format: str = "center"):
+    """K7 on device.  dets [D,7], gts [G,7] rows [img,cx,cy,w,h,score,cls] (fp32, CUDA).
+    Returns (order, tp_sorted, cls_sorted, score_sorted): detections in the reference's evaluation
+    order (class ascending, then stable descending score, utils.py:210,229) with their TP flags."""
+    dev = dets.device
+    D, G = dets.shape[0], gts.shape[0]
+    dets = dets.to(torch.float32).contiguous()
+    gts = gts.to(device=dev, dtype=torch.float32).contiguous()
+    # evaluation order: stable sort by score desc, then stable by class  == per-class stable score order
+    o1 = torch.sort(dets[:, 5], descending=True, stable=True).indices
+    o2 = torch.sort(dets[o1, 6], stable=True).indices
+    order = o1[o2]
+    rank = torch.empty(D, dtype=torch.int32, device=dev)
+    rank[order] = torch.arange(D, dtype=torch.int32, device=dev)
+    # group ground truths by image, keeping their original relative order (utils.py:236-238)
+    gorder = torch.sort(gts[:, 0], stable=True).indices if G else torch.zeros(0, dtype=torch.long, device=dev)
+    gsorted = gts[gorder].contiguous()
+    gimg = gsorted[:, 0].contiguous()
+    lo = torch.searchsorted(gimg, dets[:, 0].contiguous(), right=False).to(torch.int32)
+    hi = torch.searchsorted(gimg, dets[:, 0].contiguous(), right=True).to(torch.int32)
+    tp = torch.zeros(D, dtype=torch.float32, device=dev)
+    best_iou = torch.zeros(D, dtype=torch.float32, device=dev)
+    best_gt = torch.full((D,), -1, dtype=torch.int32, device=dev)
+    claim = torch.empty(max(G, 1), dtype=torch.int32, device=dev)
+    thr32 = float(torch.tensor(iou_threshold, dtype=torch.float32))
+    with torch.cuda.device(dev):
+        lib.yolo_map_match(ptr(dets), D, ptr(gsorted), G, ptr(lo), ptr(hi), ptr(rank), thr32, _fmt(box_format), ptr(tp),
+                           ptr(best_iou), ptr(best_gt), ptr(claim), stream_ptr(dev))
+    return order, tp[order], dets[order, 6], dets[order, 5], tp
+
+
+def calc_mAP(pred_boxes, true_boxes, iou_threshold=0.5, box_format="center", num_classes=20):
+    """utils.py:193-274.  Rows [img, cx, cy, w, h, score, cls]; returns a 0-dim fp32 tensor.
+    The O(D*G) matching runs on device (K7); the per-class cumsum / trapz tail is a handful of
+    torch ops on the device-resident TP flags."""
+    dev = pred_boxes.device if torch.is_tensor(pred_boxes) and pred_boxes.is_cuda else _device()
+    dets = torch.as_tensor(pred_boxes, dtype=torch.float32).reshape(-1, 7).to(dev)
+    gts = torch.as_tensor(true_boxes, dtype=torch.float32).reshape(-1, 7).to(dev)
+    classes = torch.arange(num_classes, dtype=torch.float32, device=dev)
+    n_gt = (gts[:, 6].unsqueeze(0) == classes.unsqueeze(1)).sum(1)  # utils.py:211-213
+    valid = n_gt > 0
+    n_valid = int(valid.sum())
+    if n_valid == 0:
+        raise ZeroDivisionError("division by zero")  # utils.py:274 with no ground truth at all
+    if dets.shape[0] == 0:
+        return torch.zeros((), dtype=torch.float32)
+    order, tp_s, cls_s, _, _ = map_match(dets, gts, iou_threshold, box_format)
+    # segmented cumulative sums per class over the evaluation order
+    ctp = torch.cumsum(tp_s, 0)
+    pos = torch.arange(1, tp_s.numel() + 1, dtype=torch.float32, device=dev)
+    start = torch.searchsorted(cls_s.contiguous(), classes, right=False)  # first det of each class
+    end = torch.searchsorted(cls_s.contiguous(), classes, right=True)
+    base_tp = torch.cat([torch.zeros(1, device=dev), ctp])[start]         # TP count before the class
+    aps = []
+    for c in torch.nonzero(valid).flatten().tolist():
+        s, e = int(start[c]), int(end[c])
+        if e == s:  # ground truth but no detections: AP 0 (utils.py:262-272 on empty tensors)
+            aps.append(torch.zeros((), device=dev))
+            continue
+        tp_c = ctp[s:e] - base_tp[c]
+        n_c = pos[s:e] - float(s)
+        prec = torch.cat([torch.ones(1, device=dev), tp_c / n_c])          # cumTP / (cumTP + cumFP)
+        rec = torch.cat([torch.zeros(1, device=dev), tp_c / float(n_gt[c])])
+        aps.append(torch.trapz(prec, rec))
+    return (sum(aps) / len(aps)).cpu()
+
+
+# ------------------------------------------------------------------- fused detection pipeline
+def _scaled_anchors(anchors, i: int, grid_size: int) -> torch.Tensor:
+    """utils.py:303 / demo.py:33-35: fp32 anchors times the grid size, rounded in fp32."""
+    a = anchors[i] if torch.is_tensor(anchors) else torch.tensor([*anchors[i]])
+    return a.detach().to(device="cpu", dtype=torch.float32) * grid_size
+
+
+class Detector:
+    """forward -> decode x3 -> batched NMS with every intermediate resident in HBM and static per
+    (batch, H, W): the device pipeline behind get_eval_boxes (utils.py:276-332) and demo.predict
+    (demo.py:30-55).  No host sync happens until results are read."""
+
+    def __init__(self, model, anchors=None, iou_threshold=config.NMS_IOU_THRESHOLD,
+                 obj_threshold=config.CONF_THRESHOLD, box_format="center"):
+        self.model = model
+        self.anchors = config.ANCHORS if anchors is None else anchors
+        self.iou_threshold, self.obj_threshold, self.box_format = iou_threshold, obj_threshold, box_format
+        self._state = {}
+
+    def _get_state(self, B, grids, device):
+        key = (B, tuple(grids), str(device))
+        st = self._state.get(key)
+        if st is None:
+            n = sum(3 * s * s for s in grids)
+            st = dict(n=n, cand=torch.empty(B, n, 6, dtype=torch.float32, device=device),
+                      off=(torch.arange(B + 1, dtype=torch.int32, device=device) * n).contiguous(),
+                      ws=NmsWorkspace(B * n, B, device))
+            self._state[key] = st
+        return st
+
+    def __call__(self, x: torch.Tensor):
+        """Returns (NmsResult, plan); plan.check_status() reports NaN inputs/layers after the fact."""
+        plan, heads = self.model.forward_async(x)
+        B = x.shape[0]
+        grids = [h.shape[2] for h in heads]
+        st = self._get_state(B, grids, x.device)
+        off = 0
+        for i, h in enumerate(heads):
+            s = grids[i]
+            anc = _scaled_anchors(self.anchors, i, s)
+            decode_boxes(h, anc, s, True, out=st["cand"], out_offset=off)
+            off += 3 * s * s
+        res = batched_nms(st["cand"].view(-1, 6), st["off"], self.iou_threshold, self.obj_threshold, self.box_format,
+                          workspace=st["ws"])
+        return res, plan
+
+
+def detect(model, x, anchors=None, iou_threshold=config.NMS_IOU_THRESHOLD, obj_threshold=config.CONF_THRESHOLD,
+           box_format="center") -> List[list]:
+    """One call for demo.predict's body (demo.py:41-55): per image, the NMS survivors as lists."""
+    det = model.__dict__.get("_yb_detector")
+    if det is None or (det.iou_threshold, det.obj_threshold, det.box_format) != (iou_threshold, obj_threshold, box_format) \
+            or (anchors is not None and det.anchors is not anchors):
+        det = Detector(model, anchors, iou_threshold, obj_threshold, box_format)
+        model.__dict__["_yb_detector"] = det
+    res, plan = det(x)
+    out = res.to_lists()
+    plan.check_status()
+    return out
+
+
+def get_eval_boxes(loader, model, iou_threshold, anchors, obj_threshold, box_format="center", device=None):
+    """utils.py:276-332 on the fused device pipeline: returns (all_box_predictions, all_true_boxes)
+    as lists of [image_idx, cx, cy, w, h, obj, cls], image indices counted across batches."""
+    device = _device(device)
+    was_training = model.training
+    model.eval()
+    det = Detector(model, anchors, iou_threshold, obj_threshold, box_format)
+    preds, trues, data_idx = [], [], 0
+    for x, targets in loader:
+        x = x.to(device)
+        res, plan = det(x)
+        t2 = targets[2].to(device=device, dtype=torch.float32)
+        s = t2.shape[2]
+        anc = _scaled_anchors(anchors, 2, s)
+        true_rows = decode_boxes(t2, anc, s, is_pred=False)  # utils.py:313-315
+        kept = res.kept_rows()
+        plan.check_status()
+        for b in range(x.shape[0]):
+            for row in kept[b].tolist():
+                preds.append([data_idx] + row)
+            tb = true_rows[b]
+            for row in tb[(tb[:, 4].double() > obj_threshold)].tolist():  # utils.py:326-328
+                trues.append([data_idx] + row)
+            data_idx += 1
+    if was_training:
+        model.train()
+    return preds, trues
+
+
+# names used by BASELINE.json's north_star (upstream Aladdin-Persson spelling)
+cells_to_bboxes = cells_to_boxes
+intersection_over_union = calc_iou
+mean_average_precision = calc_mAP
