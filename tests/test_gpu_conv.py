@@ -1,0 +1,167 @@
+"""GPU parity: K1/K2 (tcgen05 implicit-GEMM conv + folded BN + activation + residual + upsample store)
+through the C-ABI, against (a) torch-CPU fp32 conv2d on the same bf16-rounded operands (the oracle
+arithmetic) and (b) the test-only SIMT kernel of the same library.
+
+Tolerance (stated, bf16 path): outputs are bf16, accumulation fp32.  |err| <= 2^-7 * max(1, |ref|)
+(one bf16 ulp is 2^-8 relative) and cosine similarity >= 0.99999."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+REL = 2.0 ** -7
+
+
+def _run_case(B, H, cin, cout, k, stride, act="leaky_relu", residual=False, upsample=False, fp32=False,
+              a_mode=0, block_n=0, stages=0, in_pitch=None, out_pitch=None, seed=0, also_simt=True):
+    from yolo_for_turbines_b200._lib import ACT_CODES, ConvDesc, lib, ptr, stream_ptr
+    from yolo_for_turbines_b200.engine import make_conv_plan
+
+    g = torch.Generator().manual_seed(seed)
+    pad = 1 if k == 3 else 0
+    cpad = (cout + 31) // 32 * 32
+    in_pitch = in_pitch or cin
+    out_pitch = out_pitch or cpad
+    x = torch.randn(B, H, H, in_pitch, generator=g).bfloat16()
+    w = (torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k)) ** 0.5)
+    scale = 0.5 + torch.rand(cout, generator=g)
+    bias = 0.2 * torch.randn(cout, generator=g)
+    Ho = (H + 2 * pad - k) // stride + 1
+    res = torch.randn(B, Ho, Ho, cpad, generator=g).bfloat16() if residual else None
+
+    # oracle arithmetic: fp32 conv on the bf16-rounded operands
+    xr = x[..., :cin].float().permute(0, 3, 1, 2)
+    wr = w.bfloat16().float()
+    y = F.conv2d(xr, wr, None, stride, pad) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    y = F.leaky_relu(y, 0.1) if act == "leaky_relu" else (F.mish(y) if act == "mish" else y)
+    if residual:
+        y = y + res[..., :cout].float().permute(0, 3, 1, 2)
+    if upsample:
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+    ref = y.permute(0, 2, 3, 1).contiguous()  # NHWC
+
+    dev = "cuda"
+    xd = x.to(dev).contiguous()
+    wpk = torch.zeros(cpad, k * k, cin, dtype=torch.bfloat16)
+    wpk[:cout] = w.permute(0, 2, 3, 1).reshape(cout, k * k, cin).bfloat16()
+    wd = wpk.to(dev).contiguous()
+    sc = torch.zeros(cpad); sc[:cout] = scale
+    bi = torch.zeros(cpad); bi[:cout] = bias
+    sd, bd = sc.to(dev), bi.to(dev)
+    rd = res.to(dev).contiguous() if residual else None
+    Hy = Ho * (2 if upsample else 1)
+    odt = torch.float32 if fp32 else torch.bfloat16
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    d = ConvDesc()
+    d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch = B, H, H, cin, in_pitch
+    d.c_out, d.c_out_pad, d.out_pitch = cout, cpad, out_pitch
+    d.ksize, d.stride, d.pad, d.act = k, stride, pad, ACT_CODES[act]
+    d.has_residual, d.res_pitch = int(residual), cpad
+    d.upsample2x, d.out_fp32, d.check_nan = int(upsample), int(fp32), 1
+    d.a_mode, d.block_n_hint, d.stages_hint = a_mode, block_n, stages
+
+    outs = {}
+    yd = torch.full((B, Hy, Hy, out_pitch), 7.0, dtype=odt, device=dev)
+    plan = make_conv_plan(d, ptr(xd), ptr(wd), ptr(sd), ptr(bd), ptr(rd), ptr(yd))
+    lib.yolo_conv_fwd(plan[1], ptr(status), stream_ptr())
+    torch.cuda.synchronize()
+    outs["tcgen05"] = yd.float().cpu()
+    if also_simt:
+        ys = torch.full((B, Hy, Hy, out_pitch), 7.0, dtype=odt, device=dev)
+        lib.yolo_conv_fwd_simt(C.byref(d), ptr(xd), ptr(wd), ptr(sd), ptr(bd), ptr(rd), ptr(ys), ptr(status), stream_ptr())
+        torch.cuda.synchronize()
+        outs["simt"] = ys.float().cpu()
+    assert int(status.item()) == 0
+    for name, o in outs.items():
+        got = o[..., :cout]
+        err = (got - ref).abs()
+        tol = REL * torch.clamp(ref.abs(), min=1.0)
+        bad = err > tol
+        cos = F.cosine_similarity(got.flatten(), ref.flatten(), dim=0)
+        if bool(bad.any()) or cos < 0.99999:
+            idx = torch.nonzero(bad)
+            rows = torch.unique(idx[:, 0] * Hy * Hy + idx[:, 1] * Hy + idx[:, 2]) if idx.numel() else idx
+            raise AssertionError(
+                f"{name}: max err {float(err.max()):.4g}, cos {float(cos):.6f}, bad {int(bad.sum())}/{bad.numel()}, "
+                f"first bad idx {idx[:5].tolist()}, bad pixel rows%128 {sorted(set((rows % 128).tolist()))[:16]}, "
+                f"bad channels {sorted(set(idx[:, 3].tolist()))[:16]}")
+        if out_pitch > cpad:  # the kernel must not touch the neighbouring channels of a concat buffer
+            assert bool((o[..., cpad:] == 7.0).all()), name + " wrote outside its channel range"
+    return outs
+
+
+def test_conv1x1_tiled_single_kblock():
+    _run_case(B=1, H=16, cin=64, cout=64, k=1, stride=1)          # M=256: 2 tiles, K=64: 1 k-block, N=64
+
+
+def test_conv1x1_tiled_multi_kblock_and_m_tail():
+    _run_case(B=2, H=13, cin=256, cout=128, k=1, stride=1)        # M=338 (tail), 4 k-blocks, 128-wide tile
+
+
+def test_conv1x1_kc32_swizzle64():
+    _run_case(B=1, H=16, cin=32, cout=32, k=1, stride=1)          # the stem GEMM shape (K=32, N=32)
+    _run_case(B=1, H=24, cin=96, cout=64, k=1, stride=1)          # K=96: 3 k-blocks of 32
+
+
+def test_conv1x1_im2col_mode_equals_tiled():
+    _run_case(B=2, H=13, cin=128, cout=64, k=1, stride=1, a_mode=2)
+
+
+def test_conv3x3_s1_im2col():
+    _run_case(B=2, H=13, cin=64, cout=128, k=3, stride=1)         # padding via TMA zero fill, tiles cross images
+    _run_case(B=1, H=26, cin=128, cout=256, k=3, stride=1, block_n=256)
+
+
+def test_conv3x3_s2_im2col():
+    _run_case(B=2, H=26, cin=64, cout=128, k=3, stride=2)
+    _run_case(B=1, H=32, cin=32, cout=64, k=3, stride=2)          # kc=32 path
+
+
+def test_conv_residual_mish_fp32_head():
+    _run_case(B=2, H=13, cin=64, cout=128, k=3, stride=1, residual=True)
+    _run_case(B=1, H=13, cin=64, cout=64, k=1, stride=1, act="mish")
+    _run_case(B=2, H=13, cin=256, cout=255, k=1, stride=1, act="none", fp32=True)   # head: N padded 255->256
+    _run_case(B=1, H=13, cin=128, cout=21, k=1, stride=1, act="none", fp32=True)    # nc=2 head: 21->32
+
+
+def test_conv_upsample_store_and_concat_pitch():
+    _run_case(B=2, H=13, cin=128, cout=64, k=1, stride=1, upsample=True, out_pitch=192)  # writes ch [0,64) of 192
+    _run_case(B=1, H=26, cin=64, cout=64, k=3, stride=1, in_pitch=160, out_pitch=96)     # reads a pitched slice
+
+
+def test_conv_pipeline_depths_and_tiles():
+    for bn, st in ((32, 2), (64, 3), (128, 1), (128, 6), (256, 4)):
+        _run_case(B=1, H=20, cin=128, cout=256, k=3, stride=1, block_n=bn, stages=st, also_simt=False)
+
+
+def test_conv_darknet_shapes_batch4():
+    """Every distinct (Cin, Cout, k, stride, H) of YOLOv3-416 at H/4 resolution to keep the CPU oracle fast."""
+    shapes = [(32, 64, 3, 2, 104), (64, 32, 1, 1, 52), (32, 64, 3, 1, 52), (64, 128, 3, 2, 52), (128, 64, 1, 1, 26),
+              (64, 128, 3, 1, 26), (128, 256, 3, 2, 26), (256, 128, 1, 1, 13), (128, 256, 3, 1, 13), (256, 512, 3, 2, 14),
+              (512, 256, 1, 1, 7), (256, 512, 3, 1, 7), (512, 1024, 3, 2, 8), (1024, 512, 1, 1, 4), (512, 1024, 3, 1, 4),
+              (768, 256, 1, 1, 8), (384, 128, 1, 1, 13), (1024, 255, 1, 1, 4)]
+    for cin, cout, k, s, h in shapes:
+        _run_case(B=4, H=h, cin=cin, cout=cout, k=k, stride=s, act="none" if cout == 255 else "leaky_relu",
+                  fp32=(cout == 255), also_simt=False, seed=cin + cout)
+
+
+def test_nan_layer_flag():
+    from yolo_for_turbines_b200._lib import ConvDesc, lib, ptr, stream_ptr
+    from yolo_for_turbines_b200.engine import make_conv_plan
+
+    x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+    x[0, 3, 3, 5] = float("nan")
+    w = torch.ones(64, 1, 64, dtype=torch.bfloat16, device="cuda")
+    sc, bi = torch.ones(64, device="cuda"), torch.zeros(64, device="cuda")
+    y = torch.empty(1, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d = ConvDesc()
+    d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch, d.c_out, d.c_out_pad, d.out_pitch = 1, 8, 8, 64, 64, 64, 64, 64
+    d.ksize, d.stride, d.pad, d.act, d.check_nan = 1, 1, 0, 1, 1
+    plan = make_conv_plan(d, ptr(x), ptr(w), ptr(sc), ptr(bi), None, ptr(y))
+    lib.yolo_conv_fwd(plan[1], ptr(st), stream_ptr())
+    assert int(st.item()) == 2  # YB_STATUS_NAN_LAYER

@@ -1,0 +1,97 @@
+"""GPU parity: K3 decode, calc_iou / iou_aligned, K7 mAP matching, through the reference-shaped API."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle import yolo_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+DECODE_ATOL = 1e-5  # BASELINE.json north_star: decoded boxes within 1e-5 (fp32)
+
+
+def _close(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= DECODE_ATOL * np.maximum(1.0, np.abs(b)))
+
+
+def test_decode_golden(gold):
+    from yolo_for_turbines_b200.utils import cells_to_boxes
+
+    d = gold.decode
+    for name in ("zeros", "s13_nc80", "s26_nc2", "s8_nc5", "target"):
+        x = torch.from_numpy(d[name + "/in"]).clone()
+        out = np.asarray(cells_to_boxes(x, torch.from_numpy(d[name + "/anchors"]), x.shape[2], is_pred=(name != "target")),
+                         dtype=np.float32)
+        ref = d[name + "/out"]
+        assert out.shape == ref.shape, name
+        assert np.array_equal(out[..., 5], ref[..., 5]), name + ": class index (argmax, first on ties) must be exact"
+        assert _close(out[..., :5], ref[..., :5]), (name, float(np.abs(out - ref).max()))
+        if name + "/mutated" in d.files:  # the reference rewrites predictions[..., :4] in place
+            assert _close(x.numpy()[..., :4], d[name + "/mutated"][..., :4]), name
+            assert np.array_equal(x.numpy()[..., 4:], d[name + "/mutated"][..., 4:]), name
+
+
+def test_decode_strided_head_layout_vs_oracle():
+    """The model hands decode a non-contiguous (B,3,S,S,85) view of an NHWC buffer with pitch 256."""
+    from yolo_for_turbines_b200.utils import decode_boxes
+
+    B, S, nc = 3, 52, 80
+    g = torch.Generator().manual_seed(3)
+    buf = 1.5 * torch.randn(B, S, S, 256, generator=g)
+    view = torch.as_strided(buf, (B, 3, S, S, 85), (S * S * 256, 85, S * 256, 256, 1))
+    anchors = torch.tensor(orc.ANCHORS[2]) * S
+    ref = np.asarray(orc.cells_to_boxes(view.clone(), anchors, S), dtype=np.float32)
+    out = decode_boxes(torch.as_strided(buf.cuda(), view.shape, view.stride()), anchors, S).cpu().numpy()
+    assert np.array_equal(out[..., 5], ref[..., 5])
+    assert _close(out[..., :5], ref[..., :5])
+
+
+def test_iou_golden(gold):
+    from yolo_for_turbines_b200.utils import calc_iou, iou_aligned
+
+    a, b = torch.from_numpy(gold.iou["a"]), torch.from_numpy(gold.iou["b"])
+    assert np.array_equal(calc_iou(a, b, "center").cpu().numpy(), gold.iou["center"])  # bit-exact op order
+    assert np.array_equal(calc_iou(a, b, "corners").cpu().numpy(), gold.iou["corners"])
+    assert np.array_equal(calc_iou(a[0], b, "center").cpu().numpy(), gold.iou["bcast"])
+    assert np.array_equal(iou_aligned(a[:, 2:], b[:, 2:]).cpu().numpy(), gold.iou["aligned"])
+    kat = iou_aligned(torch.tensor([0.2, 0.3]), torch.tensor([[0.28, 0.22], [0.38, 0.48]]))
+    assert np.array_equal(kat.cpu().numpy(), gold.iou["aligned_kat"])
+
+
+def test_map_golden(gold):
+    from yolo_for_turbines_b200.utils import calc_mAP
+
+    for c in gold.map:
+        res = calc_mAP(c["preds"], c["trues"], c["iou_thr"], c["fmt"], c["num_classes"])
+        assert res.dim() == 0
+        assert abs(float(res) - c["mAP"]) <= 1e-6, (c["name"], float(res), c["mAP"])
+    with pytest.raises(ZeroDivisionError):
+        calc_mAP([[0, .5, .5, .1, .1, .9, 0]], [], 0.5, "center", 3)
+
+
+def test_map_tp_flags_match_oracle_exactly():
+    """The matching step (TP/FP per detection) is integer work: bit-exact against the oracle."""
+    from yolo_for_turbines_b200.utils import map_match
+
+    g = torch.Generator().manual_seed(77)
+    n_img, nc, n_gt, n_det = 6, 4, 80, 600
+    gts = torch.empty(n_gt, 7)
+    gts[:, 0] = torch.randint(0, n_img, (n_gt,), generator=g).float()
+    gts[:, 1:3] = 0.2 + 0.6 * torch.rand(n_gt, 2, generator=g)
+    gts[:, 3:5] = 0.1 + 0.3 * torch.rand(n_gt, 2, generator=g)
+    gts[:, 5] = 1.0
+    gts[:, 6] = torch.randint(0, nc, (n_gt,), generator=g).float()
+    dets = gts[torch.randint(0, n_gt, (n_det,), generator=g)].clone()
+    dets[:, 1:5] += 0.04 * torch.randn(n_det, 4, generator=g)
+    dets[:, 3:5] = dets[:, 3:5].abs() + 0.01
+    dets[:, 5] = torch.rand(n_det, generator=g)
+    dets[::11, 5] = dets[0, 5]
+    dets = dets[torch.argsort(dets[:, 0], stable=True)]
+    ref_map, tp_rows = orc.calc_mAP(dets.tolist(), gts.tolist(), 0.5, "center", nc, return_tp=True)
+    _, _, _, _, tp = map_match(dets.cuda(), gts.cuda(), 0.5, "center")
+    tp = tp.cpu().tolist()
+    assert all(tp[r] == v for r, v in tp_rows.items())
+    from yolo_for_turbines_b200.utils import calc_mAP
+    assert abs(float(calc_mAP(dets.tolist(), gts.tolist(), 0.5, "center", nc)) - float(ref_map)) <= 1e-6
