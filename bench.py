@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Headline benchmark: YOLOv3-416 images/sec (forward + anchor decode + NMS), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: BASELINE.json configs[1] = batch 64 synthetic
+416x416 images per GPU, 80 classes, random-init weights, conf 0.5 / IoU 0.45 (code/config.py:18-20).
+Images shard data-parallel over ranks with no collective on the data path (weak scaling).
+
+One JSON line on rank 0 with
+  value     images/s, inputs resident in HBM, CUDA-event timed, max over ranks;
+  e2e       images/s through the public API from PINNED HOST fp32 batches: H2D copy + forward + decode
+            + NMS + D2H of the survivors inside the timed region;
+  roofline  the conv kernels (tensor-bound): algorithmic FLOPs / CUDA-event time of the 75 conv launches;
+  cpu_baseline  the oracle port of the reference's CPU path on this box's host cores (bounded sample).
+`--impl reference` times that CPU port alone (the reference is pure Python/PyTorch and has no
+installable package).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GFLOP_PER_IMAGE = {(416, 80): 65.864, (608, 80): 140.692, (416, 2): 65.297, (320, 2): 38.637}
+
+
+def algorithmic_gflop(size: int, nc: int) -> float:
+    if (size, nc) in GFLOP_PER_IMAGE:
+        return GFLOP_PER_IMAGE[(size, nc)]
+    return GFLOP_PER_IMAGE[(416, nc if nc in (2, 80) else 80)] * (size / 416.0) ** 2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    hbm=d["hbm_gbs"], source="measured")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def nms_launch_count(batch: int) -> int:
+    img_passes = 0 if batch <= 1 else ((max(batch - 1, 1).bit_length() + 7) // 8)
+    sort = (4 + img_passes) * 3
+    return 3 + sort + 1 + sort + 1 + 1 + 4  # K4 | sort#1 | class keys | sort#2 | gather | nms | keep+offsets
+
+
+# ------------------------------------------------------------------------------------------ CPU
+def cpu_reference_step(sd, x, nc, conf, iou_thr, anchors):
+    """The reference's own path on host cores (oracle port of model.py:172, utils.py:86,150)."""
+    from oracle import yolo_oracle as orc
+
+    return orc.detect(sd, x, anchors, iou_thr, conf, nc, "leaky_relu", "center")
+
+
+def default_init_state_dict(nc: int, seed: int = 0):
+    """torch.manual_seed(0) + default nn init of the reference architecture."""
+    from yolo_for_turbines_b200.model import YOLOv3
+
+    torch.manual_seed(seed)
+    return YOLOv3(num_classes=nc).eval()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.manual_seed(0)
+    m = default_init_state_dict(args.classes)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    from yolo_for_turbines_b200 import config as cfg
+
+    sample = args.cpu_images
+    xs = [torch.rand(sample, 3, args.size, args.size, generator=torch.Generator().manual_seed(1234 + i)) for i in range(2)]
+    for i in range(args.warmup):
+        cpu_reference_step(sd, xs[i % 2][:1], args.classes, args.conf, args.iou, cfg.ANCHORS)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        cpu_reference_step(sd, xs[i % 2], args.classes, args.conf, args.iou, cfg.ANCHORS)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {"impl": "reference", "metric": "yolov3_416_images_per_sec_fwd_decode_nms", "value": val, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"YOLOv3-{args.size} nc{args.classes} conf {args.conf} iou {args.iou}: "
+                                   f"{sample}-image sample per step of the batch-{args.batch} workload, CPU"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{sample} images/step x {args.steps} steps, torch intra-op threads "
+                                       f"{torch.get_num_threads()} of {os.cpu_count()} cpus"},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=416)
+    ap.add_argument("--classes", type=int, default=80)
+    ap.add_argument("--conf", type=float, default=0.5)
+    ap.add_argument("--iou", type=float, default=0.45)
+    ap.add_argument("--cpu-images", type=int, default=2, help="images per CPU-baseline step")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--block-n", type=int, default=0)
+    ap.add_argument("--stages", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    from yolo_for_turbines_b200 import config as cfg
+    from yolo_for_turbines_b200.model import YOLOv3
+    from yolo_for_turbines_b200.utils import Detector
+
+    torch.manual_seed(0)  # identical weights on every rank
+    model = YOLOv3(num_classes=args.classes).eval().to(dev)
+    eng = model._engine(dev)
+    eng.block_n_hint, eng.stages_hint = args.block_n, args.stages
+    det = Detector(model, cfg.ANCHORS, args.iou, args.conf, "center")
+    B, S = args.batch, args.size
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    nbuf = 3
+    xs = [torch.rand(B, 3, S, S, generator=g, device=dev) for _ in range(nbuf)]
+    hx = [torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(77 + rank + i)).pin_memory() for i in range(2)]
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms: float) -> float:
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ---------------------------------------------------------
+    for i in range(args.warmup):
+        res, plan = det(xs[i % nbuf])
+    plan.check_status()
+    n_cand = res.boxes.shape[0] // B
+    kept_total = int(res.keep_off[-1].item())
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        res, plan = det(xs[i % nbuf])
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    plan.check_status()
+
+    # ---- conv-only time (roofline numerator): the plan's 75 conv launches, eager, event-timed ----
+    plan._launch_input(xs[0])
+    torch.cuda.synchronize(dev)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    conv_steps = max(3, min(args.steps, 10))
+    if plan.graph is not None:
+        plan.graph.replay()
+    torch.cuda.synchronize(dev)
+    c0.record()
+    for _ in range(conv_steps):
+        if plan.graph is not None:
+            plan.graph.replay()      # the captured graph holds exactly the conv launches
+        else:
+            plan._launch_convs()
+    c1.record()
+    torch.cuda.synchronize(dev)
+    ms_conv = c0.elapsed_time(c1) / conv_steps
+
+    # ---- end to end from pinned host memory through the public API ------------------------------
+    def e2e_step(i):
+        x = hx[i % 2].to(dev, non_blocking=True)          # H2D of this step's inputs
+        r, p = det(x)
+        off = r.keep_off.cpu()                              # D2H: per-image offsets ...
+        n = int(off[-1])
+        rows = r.boxes[r.keep_idx[:n].long()].cpu()        # ... and the surviving boxes
+        return off, rows
+    for i in range(3):
+        off, rows = e2e_step(i)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    d2h = 0
+    for i in range(args.steps):
+        off, rows = e2e_step(i)
+        d2h += off.numel() * 4 + rows.numel() * 4
+    t1.record()
+    barrier()
+    ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+    clocks = sampler.finish()
+
+    if rank == 0:
+        pk = peaks()
+        imgs = B * world * args.steps
+        value = imgs / (ms_dev / 1e3)
+        gflop = algorithmic_gflop(S, args.classes)
+        achieved = gflop * B / ms_conv  # GFLOP/ms == TFLOP/s
+        line = {
+            "metric": "yolov3_416_images_per_sec_fwd_decode_nms", "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"YOLOv3-{S} COCO-{args.classes}cls random-init, batch {B}/GPU, conf {args.conf} "
+                                   f"iou {args.iou} (BASELINE configs[1])", "global_batch": B * world,
+                       "parallelism": f"dp{world}", "candidates_per_image": n_cand, "kept_last_step": kept_total,
+                       "l2": f"{nbuf} rotating input batches of {B * 3 * S * S * 4 / 1e6:.0f} MB + "
+                             f"{plan.total_bytes / 1e9:.2f} GB of activations per step exceed the 126 MB L2"},
+            "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
+                    "d2h_bytes_per_step": d2h // args.steps},
+            "gpu_launches": (plan.launches_per_forward + 3 + nms_launch_count(B)) * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "k_conv_tcgen05 (75 launches per step)",
+                         "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["bf16_sustained"], "frac_of_burst_peak": achieved / pk["bf16"],
+                         "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                         "ms_per_step_conv": ms_conv, "conv_share_of_step": ms_conv / (ms_dev / args.steps),
+                         "traffic": None},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            m_cpu = default_init_state_dict(args.classes)
+            sd = {k: v.detach().clone() for k, v in m_cpu.state_dict().items()}
+            xc = torch.rand(args.cpu_images, 3, S, S, generator=torch.Generator().manual_seed(1234))
+            cpu_reference_step(sd, xc[:1], args.classes, args.conf, args.iou, cfg.ANCHORS)
+            tc = time.perf_counter()
+            for _ in range(args.cpu_steps):
+                cpu_reference_step(sd, xc, args.classes, args.conf, args.iou, cfg.ANCHORS)
+            dtc = time.perf_counter() - tc
+            line["cpu_baseline"] = {"value": args.cpu_images * args.cpu_steps / dtc, "unit": "images/s",
+                                    "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{args.cpu_images * args.cpu_steps} images of the same workload "
+                                              f"({dtc:.1f} s; torch threads {torch.get_num_threads()}, os.cpu_count {os.cpu_count()})"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
