@@ -165,3 +165,30 @@ def test_nan_layer_flag():
     plan = make_conv_plan(d, ptr(x), ptr(w), ptr(sc), ptr(bi), None, ptr(y))
     lib.yolo_conv_fwd(plan[1], ptr(st), stream_ptr())
     assert int(st.item()) == 2  # YB_STATUS_NAN_LAYER
+
+
+def test_conv_large_grid_matches_simt():
+    """The stem GEMM at the bench shape: M = 64*416*416 = 11 075 584 pixels = 86 528 M-tiles (> 65 535, so the
+    grid must be 1-D).  Too big for the CPU oracle: checked against the SIMT kernel on the same operands."""
+    from yolo_for_turbines_b200._lib import ConvDesc, lib, ptr, stream_ptr
+    from yolo_for_turbines_b200.engine import make_conv_plan
+
+    B, H, cin, cout = 64, 416, 32, 32
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, H, H, cin, generator=g, device="cuda").bfloat16()
+    w = (torch.randn(cout, 1, cin, generator=g, device="cuda") * cin ** -0.5).bfloat16()
+    sc, bi = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d = ConvDesc()
+    d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch, d.c_out, d.c_out_pad, d.out_pitch = B, H, H, cin, cin, cout, cout, cout
+    d.ksize, d.stride, d.pad, d.act, d.check_nan = 1, 1, 0, 1, 1
+    y1 = torch.empty(B, H, H, cout, dtype=torch.bfloat16, device="cuda")
+    y2 = torch.empty_like(y1)
+    plan = make_conv_plan(d, ptr(x), ptr(w), ptr(sc), ptr(bi), None, ptr(y1))
+    lib.yolo_conv_fwd(plan[1], ptr(st), stream_ptr())
+    lib.yolo_conv_fwd_simt(C.byref(d), ptr(x), ptr(w), ptr(sc), ptr(bi), None, ptr(y2), ptr(st), stream_ptr())
+    torch.cuda.synchronize()
+    assert int(st.item()) == 0
+    diff = (y1.float() - y2.float()).abs()
+    assert float(diff.max()) <= 2.0 ** -6 * max(1.0, float(y2.float().abs().max()))
+    assert float((diff > 0).float().mean()) < 0.02  # only accumulation-order ulps differ

@@ -41,7 +41,7 @@ struct ConvKParams {
   uint32_t* status;
   int M, h_out, w_out;
   int out_pitch, res_pitch;
-  int num_kb, cchunks, stages;
+  int num_kb, cchunks, stages, tiles_n;
   int ksize, stride, pad;
   int act, has_residual, upsample2x, out_fp32, check_nan, a_im2col;
 };
@@ -197,8 +197,10 @@ k_conv_tcgen05(const __grid_constant__ ConvKParams p) {
   const uint32_t tmem_full_bar = bar_base + 2 * stages * 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BLOCK_M;
-  const int n0 = blockIdx.x * BLOCK_N;
+  // 1-D grid (gridDim.y is limited to 65535): N-tiles of one M-tile are adjacent so that the CTAs
+  // sharing an A tile run together and hit it in L2.
+  const int m0 = int(blockIdx.x / p.tiles_n) * BLOCK_M;
+  const int n0 = int(blockIdx.x % p.tiles_n) * BLOCK_N;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -443,7 +445,7 @@ template <int BN, int KC>
 int launch_conv(const ConvPlan* pl, const ConvKParams& kp, cudaStream_t stream) {
   YB_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tcgen05<BN, KC>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes));
-  k_conv_tcgen05<BN, KC><<<dim3(pl->grid_x, pl->grid_y), CONV_THREADS, pl->smem_bytes, stream>>>(kp);
+  k_conv_tcgen05<BN, KC><<<dim3((unsigned)pl->grid_x * (unsigned)pl->grid_y), CONV_THREADS, pl->smem_bytes, stream>>>(kp);
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -476,8 +478,10 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
   ConvPlan* pl = new (plan_host) ConvPlan();
   pl->d = *d;
   const int kc = (d->c_in % 64 == 0) ? 64 : 32;
-  int bn = d->block_n_hint;
-  if (bn == 0) bn = d->c_out_pad >= 128 ? 128 : d->c_out_pad;
+  int bn = d->block_n_hint;  // a hint: ignored when it does not tile this layer
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) bn = 0;
+  if (bn != 0 && d->c_out_pad % bn != 0) bn = 0;
+  if (bn == 0) bn = d->c_out_pad % 128 == 0 ? 128 : (d->c_out_pad % 64 == 0 ? 64 : 32);
   YB_REQUIRE((bn == 32 || bn == 64 || bn == 128 || bn == 256) && d->c_out_pad % bn == 0,
              "conv plan: block_n %d does not tile c_out_pad %d", bn, d->c_out_pad);
   const int taps = d->ksize * d->ksize;
@@ -549,7 +553,7 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
   kp.scale = scale; kp.bias = bias; kp.residual = residual; kp.y = y; kp.status = nullptr;
   kp.M = (int)M; kp.h_out = h_out; kp.w_out = w_out;
   kp.out_pitch = d->out_pitch; kp.res_pitch = d->res_pitch;
-  kp.num_kb = num_kb; kp.cchunks = cchunks; kp.stages = stages;
+  kp.num_kb = num_kb; kp.cchunks = cchunks; kp.stages = stages; kp.tiles_n = d->c_out_pad / bn;
   kp.ksize = d->ksize; kp.stride = d->stride; kp.pad = d->pad;
   kp.act = d->act; kp.has_residual = d->has_residual; kp.upsample2x = d->upsample2x;
   kp.out_fp32 = d->out_fp32; kp.check_nan = d->check_nan; kp.a_im2col = im2col;

@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int NMS_THREADS = 512;
+constexpr int NMS_THREADS = 1024;
 
 __device__ __forceinline__ int find_image(const int32_t* __restrict__ off, int batch, int i) {
   int lo = 0, hi = batch;  // largest b with off[b] <= i
@@ -96,10 +96,37 @@ __global__ void k_gather_segments(const float* __restrict__ boxes, const uint64_
   const float* r = boxes + size_t(idx1[val2[q]]) * 6;
   const float w = r[2], h = r[3];
   const CBox c = yb_make_cbox(r[0], r[1], w, h, box_format);
-  cbox[q] = make_float4(c.x1, c.y1, c.x2, c.y2);
-  area[q] = __fmul_rn(w, h);  // utils.py:79-80
+  float a = __fmul_rn(w, h);  // utils.py:79-80
+  // torch.max/min propagate NaN (utils.py:70-73): a NaN corner makes every IoU with this box NaN, and
+  // so does a NaN area.  Fold both into area = NaN so that the hot loop can use plain fmaxf/fminf.
+  if (c.x1 != c.x1 || c.y1 != c.y1 || c.x2 != c.x2 || c.y2 != c.y2) {
+    cbox[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    a = __int_as_float(0x7fc00000);
+  } else {
+    cbox[q] = make_float4(c.x1, c.y1, c.x2, c.y2);
+  }
+  area[q] = a;
   suppressed[q] = 0;
   if (q == 0 || key2[q] != key2[q - 1]) seg_starts[atomicAdd(nseg, 1)] = q;
+}
+
+// `!(iou < thr)` of utils.py:175-179 for boxes prepared by k_gather_segments (no NaN corners; NaN
+// folded into the area).  Bit-identical to yb_iou, but: plain fmaxf/fminf, and pairs that do not
+// overlap skip the multiply/divide -- their intersection is exactly 0, so iou is +-0 (kept, as
+// 0 < thr) unless the denominator is 0 or NaN (iou NaN => suppressed).
+__device__ __forceinline__ bool nms_suppresses(const float4 e, const float ae, const float4 l,
+                                               const float al, const float thr, const bool thr_pos) {
+  const float xA = fmaxf(e.x, l.x), yA = fmaxf(e.y, l.y);
+  const float xB = fminf(e.z, l.z), yB = fminf(e.w, l.w);
+  const float dw = __fsub_rn(xB, xA), dh = __fsub_rn(yB, yA);
+  const float s = __fadd_rn(ae, al);
+  if (thr_pos && (dw <= 0.f || dh <= 0.f) && fabsf(dw) < INFINITY && fabsf(dh) < INFINITY) {
+    const float d = __fadd_rn(s, 1e-6f);  // union == s because the intersection is exactly 0
+    return !(d == d && d != 0.f);
+  }
+  const float inter = __fmul_rn(yb_clamp0(dw), yb_clamp0(dh));
+  const float iou = __fdiv_rn(inter, __fadd_rn(__fsub_rn(s, inter), 1e-6f));
+  return !(iou < thr);
 }
 
 // One CTA per (image, class) segment, boxes in descending-score order.  The
@@ -115,8 +142,10 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
                uint8_t* __restrict__ keep) {
   __shared__ float4 s_box[32];
   __shared__ float s_area[32];
+  __shared__ unsigned s_row[32];
   __shared__ int s_nkept;
   __shared__ int s_end;
+  const bool thr_pos = thr > 0.f;
   const int n = *n_dev, nseg = *nseg_dev;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
@@ -138,30 +167,23 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
       continue;
     }
     for (int c0 = s0; c0 < s1; c0 += 32) {
+      // (a) 32x32 suppression bits of the chunk, one pair per thread: warp i holds row i
+      {
+        const int qi = c0 + warp, qj = c0 + lane;
+        bool sup = false;
+        if (lane > warp && qj < s1) sup = nms_suppresses(cbox[qi], area[qi], cbox[qj], area[qj], thr, thr_pos);
+        const unsigned row = __ballot_sync(0xffffffffu, sup);
+        if (lane == 0) s_row[warp] = row;
+      }
+      __syncthreads();
+      // (b) warp 0 resolves the chunk serially (utils.py:170-187 restricted to these 32 boxes)
       if (warp == 0) {
         const int qi = c0 + lane;
         const bool valid = qi < s1;
-        float4 b = valid ? cbox[qi] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float a = valid ? area[qi] : 0.f;
-        const bool sup = valid ? (suppressed[qi] != 0) : true;
-        CBox me{b.x, b.y, b.z, b.w};
-        unsigned row = 0;  // bit j: I suppress chunk member j (j later than me)
-#pragma unroll 4
-        for (int j = 0; j < 32; ++j) {
-          CBox o;
-          o.x1 = __shfl_sync(0xffffffffu, b.x, j);
-          o.y1 = __shfl_sync(0xffffffffu, b.y, j);
-          o.x2 = __shfl_sync(0xffffffffu, b.z, j);
-          o.y2 = __shfl_sync(0xffffffffu, b.w, j);
-          const float ao = __shfl_sync(0xffffffffu, a, j);
-          if (j > lane && c0 + j < s1) {
-            const float iou = yb_iou(me, a, o, ao);
-            if (!(iou < thr)) row |= 1u << j;  // utils.py:179 keeps only iou < thr
-          }
-        }
-        unsigned alive = __ballot_sync(0xffffffffu, !sup);
+        const unsigned row = s_row[lane];
+        unsigned alive = __ballot_sync(0xffffffffu, valid && suppressed[qi] == 0);
         unsigned kept = 0;
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 0; i < 32; ++i) {
           const unsigned ri = __shfl_sync(0xffffffffu, row, i);
           if ((alive >> i) & 1u) { kept |= 1u << i; alive &= ~ri; }
@@ -169,23 +191,20 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
         if (valid) keep[val2[qi]] = (kept >> lane) & 1u;
         if ((kept >> lane) & 1u) {
           const int slot = __popc(kept & ((1u << lane) - 1u));
-          s_box[slot] = b;
-          s_area[slot] = a;
+          s_box[slot] = cbox[qi];
+          s_area[slot] = area[qi];
         }
         if (lane == 0) s_nkept = __popc(kept);
       }
       __syncthreads();
+      // (c) the chunk's survivors knock out later boxes of the segment, all threads
       const int nk = s_nkept;
       for (int q = c0 + 32 + tid; q < s1; q += NMS_THREADS) {
         if (suppressed[q]) continue;
         const float4 b = cbox[q];
-        const CBox later{b.x, b.y, b.z, b.w};
         const float al = area[q];
         for (int t = 0; t < nk; ++t) {
-          const float4 e = s_box[t];
-          const CBox early{e.x, e.y, e.z, e.w};
-          const float iou = yb_iou(early, s_area[t], later, al);
-          if (!(iou < thr)) { suppressed[q] = 1; break; }
+          if (nms_suppresses(s_box[t], s_area[t], b, al, thr, thr_pos)) { suppressed[q] = 1; break; }
         }
       }
       __syncthreads();
@@ -329,7 +348,7 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   int dev = 0, sms = 148;
   YB_CHECK_CUDA(cudaGetDevice(&dev));
   YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int grid = sms * 4;
+  int grid = sms * 2;
   if (grid > total) grid = total;
   k_nms_segments<<<grid, NMS_THREADS, 0, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts,
                                                    nseg, n_valid, iou_thr, w.suppressed, w.keep);
