@@ -81,6 +81,8 @@ typedef struct yolo_conv_desc {
   int32_t a_mode;                     /* 0 auto, 1 force tiled-2D, 2 im2col   */
   int32_t block_n_hint;               /* tuning: 0 auto | 32 | 64 | 128 | 256 */
   int32_t stages_hint;                /* tuning: 0 auto | smem pipeline depth */
+  int32_t impl_hint;                  /* 0 auto (persistent v2) | 1 one-tile-per-CTA v1 | 2 v2 */
+  int32_t cta_pair_hint;              /* 0 auto | 1 single CTA | 2 tcgen05 cta_group::2 pair  */
 } yolo_conv_desc;
 
 /* Size of the opaque, caller-owned plan blob (64-byte aligned storage).       */
@@ -91,8 +93,9 @@ int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yolo_conv_desc
                         const void* x, const void* w_packed, const float* scale,
                         const float* bias, const void* residual, void* y);
 int yolo_conv_fwd(const void* plan_host, uint32_t* status, yb_stream_t stream);
-/* tile configuration chosen by plan_init: block_n, block_k, stages, grid x/y */
-int yolo_conv_plan_info(const void* plan_host, int32_t* info5);
+/* tile configuration chosen by plan_init: info8 = block_n, block_k, stages, tiles_n, tiles_m,
+ * impl (1|2), CTAs per cluster, launched CTAs */
+int yolo_conv_plan_info(const void* plan_host, int32_t* info8);
 
 /* TEST-ONLY reference: the same math on CUDA cores (direct convolution, one
  * thread per output element).  Never called by the product path.              */

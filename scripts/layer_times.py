@@ -21,6 +21,8 @@ ap.add_argument("--classes", type=int, default=80)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--block-n", type=int, default=0)
 ap.add_argument("--stages", type=int, default=0)
+ap.add_argument("--impl", type=int, default=0)
+ap.add_argument("--pair", type=int, default=0)
 ap.add_argument("--conf", type=float, default=0.5)
 args = ap.parse_args()
 
@@ -29,6 +31,7 @@ torch.manual_seed(0)
 m = YOLOv3(num_classes=args.classes).eval().to(dev)
 eng = m._engine(dev)
 eng.block_n_hint, eng.stages_hint = args.block_n, args.stages
+eng.impl_hint, eng.cta_pair_hint = args.impl, args.pair
 x = torch.rand(args.batch, 3, args.size, args.size, device=dev)
 det = Detector(m, cfg.ANCHORS, 0.45, args.conf, "center")
 res, plan = det(x)
@@ -53,7 +56,7 @@ def timed(fn, reps=args.reps, do_flush=True):
 
 
 rows, tot_ms, tot_gf = [], 0.0, 0.0
-info = (C.c_int32 * 5)()
+info = (C.c_int32 * 8)()
 for op in plan.ops:
     pc = op.pc
     lib.yolo_conv_plan_info(op.plan_ptr, info)
@@ -62,7 +65,7 @@ for op in plan.ops:
     gf = 2.0 * M * pc.c_out * (pc.c_in if not pc.stem else 27) * (pc.ksize ** 2 if not pc.stem else 1) / 1e9
     tot_ms += ms
     tot_gf += gf
-    rows.append((op.name, pc.c_in, pc.c_out, pc.ksize, pc.stride, op.src.H, info[0], info[1], info[2], info[3] * info[4],
+    rows.append((op.name, pc.c_in, pc.c_out, pc.ksize, pc.stride, op.src.H, info[0], info[1], info[2], info[7],
                  ms, gf / ms))
 print(f"{'layer':34s} {'cin':>5s} {'cout':>5s} k s {'H':>4s} {'BN':>4s} {'KC':>3s} st {'ctas':>6s} {'ms':>8s} {'TFLOP/s':>8s}")
 for r in rows:

@@ -16,7 +16,7 @@ REL = 2.0 ** -7
 
 
 def _run_case(B, H, cin, cout, k, stride, act="leaky_relu", residual=False, upsample=False, fp32=False,
-              a_mode=0, block_n=0, stages=0, in_pitch=None, out_pitch=None, seed=0, also_simt=True):
+              a_mode=0, block_n=0, stages=0, in_pitch=None, out_pitch=None, seed=0, also_simt=True, impl=0, pair=0):
     from yolo_for_turbines_b200._lib import ACT_CODES, ConvDesc, lib, ptr, stream_ptr
     from yolo_for_turbines_b200.engine import make_conv_plan
 
@@ -63,6 +63,7 @@ def _run_case(B, H, cin, cout, k, stride, act="leaky_relu", residual=False, upsa
     d.has_residual, d.res_pitch = int(residual), cpad
     d.upsample2x, d.out_fp32, d.check_nan = int(upsample), int(fp32), 1
     d.a_mode, d.block_n_hint, d.stages_hint = a_mode, block_n, stages
+    d.impl_hint, d.cta_pair_hint = impl, pair
 
     outs = {}
     yd = torch.full((B, Hy, Hy, out_pitch), 7.0, dtype=odt, device=dev)
@@ -192,3 +193,33 @@ def test_conv_large_grid_matches_simt():
     diff = (y1.float() - y2.float()).abs()
     assert float(diff.max()) <= 2.0 ** -6 * max(1.0, float(y2.float().abs().max()))
     assert float((diff > 0).float().mean()) < 0.02  # only accumulation-order ulps differ
+
+
+# ---- the same cases on every kernel variant: v1 (one tile per CTA), v2 persistent, v2 with a CTA pair ----
+VARIANTS = [pytest.param(1, 0, id="v1"), pytest.param(2, 1, id="v2"), pytest.param(2, 2, id="v2pair")]
+
+
+@pytest.mark.parametrize("impl,pair", VARIANTS)
+def test_variants_1x1(impl, pair):
+    _run_case(B=2, H=13, cin=256, cout=128, k=1, stride=1, impl=impl, pair=pair, also_simt=False)       # M tail 338
+    _run_case(B=1, H=16, cin=32, cout=32, k=1, stride=1, impl=impl, pair=pair, also_simt=False)         # kc 32, N 32
+    _run_case(B=4, H=26, cin=512, cout=256, k=1, stride=1, impl=impl, pair=pair, also_simt=False)       # many tiles per CTA
+    _run_case(B=3, H=13, cin=128, cout=512, k=1, stride=1, impl=impl, pair=pair, also_simt=False, block_n=256)
+
+
+@pytest.mark.parametrize("impl,pair", VARIANTS)
+def test_variants_3x3(impl, pair):
+    _run_case(B=2, H=13, cin=64, cout=128, k=3, stride=1, residual=True, impl=impl, pair=pair, also_simt=False)
+    _run_case(B=2, H=26, cin=64, cout=128, k=3, stride=2, impl=impl, pair=pair, also_simt=False)
+    _run_case(B=1, H=32, cin=32, cout=64, k=3, stride=2, impl=impl, pair=pair, also_simt=False)
+    _run_case(B=5, H=13, cin=256, cout=512, k=3, stride=1, residual=True, impl=impl, pair=pair, also_simt=False)
+
+
+@pytest.mark.parametrize("impl,pair", VARIANTS)
+def test_variants_direct_store_paths(impl, pair):
+    _run_case(B=2, H=13, cin=256, cout=255, k=1, stride=1, act="none", fp32=True, impl=impl, pair=pair, also_simt=False)
+    _run_case(B=2, H=13, cin=128, cout=64, k=1, stride=1, upsample=True, out_pitch=192, impl=impl, pair=pair,
+              also_simt=False)
+    _run_case(B=1, H=26, cin=64, cout=64, k=3, stride=1, in_pitch=160, out_pitch=96, impl=impl, pair=pair,
+              also_simt=False)
+    _run_case(B=1, H=13, cin=64, cout=64, k=1, stride=1, act="mish", residual=True, impl=impl, pair=pair, also_simt=False)

@@ -19,161 +19,16 @@
 //   - 4 epilogue warps read TMEM with tcgen05.ld, apply folded BN + activation
 //     (+ residual), convert to bf16 and store.
 // Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue.
-#include <cuda.h>
-
 #include <new>
 
-#include "common.cuh"
+#include "conv_plan.cuh"
+#include "conv_ptx.cuh"
 
 namespace {
 
-constexpr int BLOCK_M = 128;
 constexpr int CONV_THREADS = 192;
-constexpr uint32_t PLAN_MAGIC = 0x59423230u;  // "YB20"
 
-struct ConvKParams {
-  alignas(64) CUtensorMap tmA;
-  alignas(64) CUtensorMap tmB;
-  const float* scale;
-  const float* bias;
-  const void* residual;
-  void* y;
-  uint32_t* status;
-  int M, h_out, w_out;
-  int out_pitch, res_pitch;
-  int num_kb, cchunks, stages, tiles_n;
-  int ksize, stride, pad;
-  int act, has_residual, upsample2x, out_fp32, check_nan, a_im2col;
-};
-
-struct ConvPlan {
-  ConvKParams kp;
-  yolo_conv_desc d;
-  int block_n, kc, grid_x, grid_y, smem_bytes;
-  uint32_t magic;
-};
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-// Bounded wait: a protocol bug must end in a trap, never in a hung GPU box.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar, uint32_t dst,
-                                            int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* tm, uint32_t bar, uint32_t dst,
-                                                   int c, int w, int h, int n, uint16_t off_w,
-                                                   uint16_t off_h) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n),
-        "h"(off_w), "h"(off_h)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
-               "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major smem operand descriptor (cute::UMMA::SmemDescriptor bit layout):
-//  [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle
-template <int ROW_BYTES>
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
-  constexpr uint64_t layout = (ROW_BYTES == 128) ? 2ull : 4ull;  // SWIZZLE_128B : SWIZZLE_64B
-  constexpr uint64_t sbo = (8 * ROW_BYTES) >> 4;                 // 8-row core-matrix group
-  return uint64_t((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | (sbo << 32) | (1ull << 46) |
-         (layout << 61);
-}
-
-// ---------------------------------------------------------------- epilogue math
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == YB_ACT_LEAKY) return v > 0.f ? v : 0.1f * v;  // nn.LeakyReLU(0.1), model.py:64
-  if (act == YB_ACT_MISH) {                                // nn.Mish(), model.py:66
-    const float sp = v > 20.f ? v : log1pf(expf(v));       // softplus, threshold 20
-    return v * tanhf(sp);
-  }
-  return v;
-}
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
+using namespace convptx;
 
 // ---------------------------------------------------------------- the kernel
 template <int BLOCK_N, int KC>
@@ -402,16 +257,6 @@ __global__ void k_conv_simt(const yolo_conv_desc d, const __nv_bfloat16* __restr
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                     const cuuint64_t*, const cuuint64_t*, const int*, const int*,
-                                     cuuint32_t, cuuint32_t, const cuuint32_t*,
-                                     CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 void* driver_fn(const char* name) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
@@ -560,6 +405,13 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
   pl->block_n = bn; pl->kc = kc;
   pl->grid_x = d->c_out_pad / bn;
   pl->grid_y = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  pl->w = w_packed;
+  pl->impl = d->impl_hint == 1 ? 1 : 2;
+  pl->ncta = 1;
+  if (pl->impl == 2) {
+    rc = conv2_plan_setup(pl, d, h_out, w_out, im2col, encTiled, residual, y);
+    if (rc) return rc;
+  }
   pl->magic = PLAN_MAGIC;
   return YB_OK;
 }
@@ -567,8 +419,9 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
 extern "C" int yolo_conv_plan_info(const void* plan_host, int32_t* info5) {
   const ConvPlan* pl = static_cast<const ConvPlan*>(plan_host);
   YB_REQUIRE(pl && pl->magic == PLAN_MAGIC && info5, "conv plan info: bad plan");
-  info5[0] = pl->block_n; info5[1] = pl->kc; info5[2] = pl->kp.stages;
+  info5[0] = pl->block_n; info5[1] = pl->kc; info5[2] = pl->impl == 2 ? pl->kp2.stages : pl->kp.stages;
   info5[3] = pl->grid_x; info5[4] = pl->grid_y;
+  info5[5] = pl->impl; info5[6] = pl->ncta; info5[7] = pl->impl == 2 ? pl->grid2 : pl->grid_x * pl->grid_y;
   return YB_OK;
 }
 
@@ -577,6 +430,7 @@ extern "C" int yolo_conv_fwd(const void* plan_host, uint32_t* status, yb_stream_
   YB_REQUIRE(pl && pl->magic == PLAN_MAGIC, "conv fwd: plan not initialised");
   YB_REQUIRE(status || !pl->kp.check_nan, "conv fwd: status word required when check_nan is set");
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (pl->impl == 2) return conv2_launch(pl, status, stream);
   ConvKParams kp = pl->kp;
   kp.status = status;
 #define YB_CONV_CASE(BN, KC) \

@@ -1,0 +1,442 @@
+// K1/K2 v2: persistent fused convolution.  Same math and boundary as conv.cu (see its header for
+// the reference call sites); what changes is how the SM is kept busy:
+//
+//   * persistent CTAs (one per SM, or one CTA PAIR per two SMs) loop over output tiles, so barrier
+//     init, tensor-map prefetch and the TMEM allocation are paid once per launch, not per tile;
+//   * the fp32 accumulator is double buffered in TMEM (2 x BLOCK_N columns): the epilogue of tile i
+//     overlaps the TMA/MMA main loop of tile i+1;
+//   * the epilogue stages bf16 output boxes (128 rows x 64 channels, 128B-swizzled) in shared memory
+//     and writes them with TMA bulk stores -- full 128-byte lines instead of 16-byte fragments per
+//     thread -- and the residual operand comes in through the same boxes with TMA loads;
+//   * NCTA == 2: tcgen05.mma.cta_group::2 pairs two SMs on one 256 x BLOCK_N tile.  Each CTA loads its
+//     own 128 rows of A and HALF of the weight tile, so per-CTA L2->smem traffic per FLOP halves.
+//
+// Warp roles (192 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer (leader CTA only issues),
+// 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+#include <new>
+
+#include "conv_plan.cuh"
+#include "conv_ptx.cuh"
+
+namespace {
+
+using namespace convptx;
+
+constexpr int CONV2_THREADS = 192;
+constexpr int NBOX = 4;  // ring of output/residual boxes in shared memory
+
+template <int BLOCK_N, int KC, int NCTA>
+struct Cfg {
+  static constexpr int ROW_BYTES = KC * 2;
+  static constexpr uint32_t A_BYTES = BLOCK_M * ROW_BYTES;
+  static constexpr int B_ROWS = BLOCK_N / NCTA;
+  static constexpr uint32_t B_BYTES = B_ROWS * ROW_BYTES;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BOXC = BLOCK_N < 64 ? BLOCK_N : 64;   // channels per epilogue box
+  static constexpr int BOX_ROW_BYTES = BOXC * 2;             // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  static constexpr uint32_t BOX_BYTES = BLOCK_M * BOX_ROW_BYTES;
+  static constexpr int NBOXES = BLOCK_N / BOXC;
+  static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) |
+                                    (uint32_t((BLOCK_M * NCTA) >> 4) << 24);
+  static int smem_bytes(int stages) {
+    return stages * STAGE_BYTES + NBOX * BOX_BYTES + (2 * stages + 4 + NBOX) * 8 + 16 + 1024;
+  }
+};
+
+template <int BLOCK_N, int KC, int NCTA>
+__global__ void __launch_bounds__(CONV2_THREADS, 1)
+k_conv_v2(const __grid_constant__ ConvKParams2 p) {
+  using C = Cfg<BLOCK_N, KC, NCTA>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stages = p.stages;
+  const uint32_t box_base = smem_base + stages * C::STAGE_BYTES;
+  const uint32_t bar_base = box_base + NBOX * C::BOX_BYTES;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (stages + s) * 8; };
+  auto tfull_bar = [&](int a) { return bar_base + (2 * stages + a) * 8; };
+  auto tempty_bar = [&](int a) { return bar_base + (2 * stages + 2 + a) * 8; };
+  auto res_bar = [&](int b) { return bar_base + (2 * stages + 4 + b) * 8; };
+  const uint32_t tmem_slot = bar_base + (2 * stages + 4 + NBOX) * 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x / NCTA;
+  const int num_clusters = gridDim.x / NCTA;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmY);
+    if (p.has_residual) tma_prefetch_desc(&p.tmR);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4 * NCTA);  // one arrive per epilogue warp of every CTA of the pair
+    }
+    for (int b = 0; b < NBOX; ++b) mbar_init(res_bar(b), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_n<NCTA>(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (every CTA loads its own A rows and its share of the weight tile) =====
+      uint32_t it = 0;
+      for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
+        const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+        int m0 = (mt * NCTA + (int)rank) * BLOCK_M;
+        if (m0 >= p.M) m0 = 0;  // peer CTA of a ragged last pair: load valid rows, results are discarded
+        const int nb0 = nt * BLOCK_N + (int)rank * C::B_ROWS;
+        int cw = 0, ch = 0, img = 0;
+        if (p.a_im2col) {
+          const int hw = p.h_out * p.w_out;
+          img = m0 / hw;
+          const int rem = m0 - img * hw;
+          const int po = rem / p.w_out, qo = rem - po * p.w_out;
+          cw = qo * p.stride - p.pad;
+          ch = po * p.stride - p.pad;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (leader) mbar_expect_tx(full_bar(s), C::STAGE_BYTES * NCTA);
+          const uint32_t sa = smem_base + s * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+          if constexpr (NCTA == 1) {
+            if (p.a_im2col) {
+              const int r = tap / p.ksize, q = tap - r * p.ksize;
+              tma_load_im2col_4d(&p.tmA, full_bar(s), sa, cc * KC, cw, ch, img, (uint16_t)q, (uint16_t)r);
+            } else {
+              tma_load_2d(&p.tmA, full_bar(s), sa, cc * KC, m0);
+            }
+            tma_load_2d(&p.tmB, full_bar(s), sb, kb * KC, nb0);
+          } else {
+            if (p.a_im2col) {
+              const int r = tap / p.ksize, q = tap - r * p.ksize;
+              tma_load_im2col_4d_2sm(&p.tmA, full_bar(s), sa, cc * KC, cw, ch, img, (uint16_t)q, (uint16_t)r);
+            } else {
+              tma_load_2d_2sm(&p.tmA, full_bar(s), sa, cc * KC, m0);
+            }
+            tma_load_2d_2sm(&p.tmB, full_bar(s), sb, kb * KC, nb0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer =====
+      uint32_t it = 0, tl = 0;
+      for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++tl) {
+        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), aph ^ 1u);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          const uint64_t adesc = make_kmajor_desc<C::ROW_BYTES>(sa);
+          const uint64_t bdesc = make_kmajor_desc<C::ROW_BYTES>(sb);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k)
+            umma_bf16_n<NCTA>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), C::IDESC,
+                              (kb | k) != 0 ? 1u : 0u);
+          umma_commit_n<NCTA>(empty_bar(s));
+        }
+        umma_commit_n<NCTA>(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int ep_tid = (warp - 2) * 32 + lane;
+    const bool direct = p.upsample2x || p.out_fp32;
+    uint32_t tl = 0, boxctr = 0;
+    bool saw_nan = false;
+    for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++tl) {
+      const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+      const int m0 = (mt * NCTA + (int)rank) * BLOCK_M;
+      const int n0 = nt * BLOCK_N;
+      const int m = m0 + row;
+      const bool valid = m < p.M;
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      size_t out_row[4];
+      int n_out_rows = 1;
+      out_row[0] = size_t(m);
+      if (p.upsample2x) {
+        const int hw = p.h_out * p.w_out;
+        const int img = m / hw;
+        const int rem = m - img * hw;
+        const int po = rem / p.w_out, qo = rem - po * p.w_out;
+        const int W2 = 2 * p.w_out;
+        const size_t r00 = (size_t(img) * (2 * p.h_out) + 2 * po) * W2 + 2 * qo;
+        out_row[0] = r00; out_row[1] = r00 + 1; out_row[2] = r00 + W2; out_row[3] = r00 + W2 + 1;
+        n_out_rows = 4;
+      }
+      bool acc_ready = false;
+#pragma unroll 1
+      for (int b = 0; b < C::NBOXES; ++b, ++boxctr) {
+        const uint32_t slot = boxctr % NBOX, sph = (boxctr / NBOX) & 1u;
+        const uint32_t slot_addr = box_base + slot * C::BOX_BYTES;
+        const int nb = n0 + b * C::BOXC;
+        if (!direct) {
+          if (ep_tid == 0) {
+            bulk_wait_group_read<NBOX - 1>();  // the TMA store that last used this slot has read it out
+            if (p.has_residual) {
+              mbar_expect_tx(res_bar(slot), C::BOX_BYTES);
+              tma_load_2d(&p.tmR, res_bar(slot), slot_addr, nb, m0);
+            }
+          }
+          named_bar_sync(1, 128);
+        }
+        if (!acc_ready) {
+          mbar_wait(tfull_bar(acc), aph);
+          tc_fence_after();
+          acc_ready = true;
+        }
+        if (!direct && p.has_residual) mbar_wait(res_bar(slot), sph);
+        const uint32_t row_addr = slot_addr + row * C::BOX_ROW_BYTES;
+        const uint32_t swz = (C::BOX_ROW_BYTES == 128) ? (row & 7) : ((row >> 1) & 3);
+#pragma unroll 1
+        for (int h = 0; h < C::BOXC / 32; ++h) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + b * C::BOXC + h * 32, v);
+          const int n = nb + h * 32;
+          float o[32];
+          const float4* sp = reinterpret_cast<const float4*>(p.scale + n);
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 s4 = __ldg(sp + j), b4 = __ldg(bp + j);
+            o[4 * j + 0] = apply_act(fmaf(__uint_as_float(v[4 * j + 0]), s4.x, b4.x), p.act);
+            o[4 * j + 1] = apply_act(fmaf(__uint_as_float(v[4 * j + 1]), s4.y, b4.y), p.act);
+            o[4 * j + 2] = apply_act(fmaf(__uint_as_float(v[4 * j + 2]), s4.z, b4.z), p.act);
+            o[4 * j + 3] = apply_act(fmaf(__uint_as_float(v[4 * j + 3]), s4.w, b4.w), p.act);
+          }
+          if (p.has_residual) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 r;
+              if (!direct) {
+                const uint32_t a = row_addr + (((h * 4 + j) ^ swz) << 4);
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+              } else {
+                r = valid ? __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) +
+                                                                 size_t(m) * p.res_pitch + n) + j)
+                          : make_uint4(0, 0, 0, 0);
+              }
+              o[8 * j + 0] += bf16_lo(r.x); o[8 * j + 1] += bf16_hi(r.x);
+              o[8 * j + 2] += bf16_lo(r.y); o[8 * j + 3] += bf16_hi(r.y);
+              o[8 * j + 4] += bf16_lo(r.z); o[8 * j + 5] += bf16_hi(r.z);
+              o[8 * j + 6] += bf16_lo(r.w); o[8 * j + 7] += bf16_hi(r.w);
+            }
+          }
+          if (p.check_nan && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) saw_nan |= (o[j] != o[j]);
+          }
+          if (!direct) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t a = row_addr + (((h * 4 + j) ^ swz) << 4);
+              const uint32_t w0 = pack_bf16(o[8 * j + 0], o[8 * j + 1]), w1 = pack_bf16(o[8 * j + 2], o[8 * j + 3]);
+              const uint32_t w2 = pack_bf16(o[8 * j + 4], o[8 * j + 5]), w3 = pack_bf16(o[8 * j + 6], o[8 * j + 7]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                           : "memory");
+            }
+          } else if (valid) {
+            if (p.out_fp32) {
+              for (int rr = 0; rr < n_out_rows; ++rr) {
+                float4* yp = reinterpret_cast<float4*>(static_cast<float*>(p.y) + out_row[rr] * p.out_pitch + n);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) yp[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              }
+            } else {
+              uint4 w4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                w4[j].x = pack_bf16(o[8 * j + 0], o[8 * j + 1]);
+                w4[j].y = pack_bf16(o[8 * j + 2], o[8 * j + 3]);
+                w4[j].z = pack_bf16(o[8 * j + 4], o[8 * j + 5]);
+                w4[j].w = pack_bf16(o[8 * j + 6], o[8 * j + 7]);
+              }
+              for (int rr = 0; rr < n_out_rows; ++rr) {
+                uint4* yp = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + out_row[rr] * p.out_pitch + n);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) yp[j] = w4[j];
+              }
+            }
+          }
+        }
+        if (b == C::NBOXES - 1) {
+          // all tcgen05.ld of this accumulator have completed (wait::ld): hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (NCTA == 1) mbar_arrive_local(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc));
+          }
+        }
+        if (!direct) {
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          named_bar_sync(1, 128);
+          if (ep_tid == 0) {
+            tma_store_2d(&p.tmY, slot_addr, nb, m0);  // rows >= M are clipped by the tensor map
+            bulk_commit_group();
+          }
+        }
+      }
+    }
+    if (saw_nan) atomicOr(p.status, YB_STATUS_NAN_LAYER);
+    if (ep_tid == 0) bulk_wait_group_all();
+  }
+
+  tc_fence_before();
+  if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) tmem_dealloc_n<NCTA>(tmem_base, C::TMEM_COLS);
+}
+
+template <int BN, int KC, int NCTA>
+int launch2(const ConvPlan* pl, const ConvKParams2& kp, cudaStream_t stream) {
+  auto kern = k_conv_v2<BN, KC, NCTA>;
+  YB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)pl->grid2);
+  cfg.blockDim = dim3(CONV2_THREADS);
+  cfg.dynamicSmemBytes = (size_t)pl->smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
+  return YB_OK;
+}
+
+template <int BN, int KC>
+int smem_for(int ncta, int stages) {
+  return ncta == 2 ? Cfg<BN, KC, 2>::smem_bytes(stages) : Cfg<BN, KC, 1>::smem_bytes(stages);
+}
+
+int smem_bytes_v2(int bn, int kc, int ncta, int stages) {
+#define YB_C2(BN, KC) if (bn == BN && kc == KC) return smem_for<BN, KC>(ncta, stages);
+  YB_C2(32, 32) YB_C2(64, 32) YB_C2(128, 32) YB_C2(256, 32) YB_C2(32, 64) YB_C2(64, 64) YB_C2(128, 64) YB_C2(256, 64)
+#undef YB_C2
+  return 1 << 30;
+}
+
+}  // namespace
+
+int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out, int im2col, PFN_encodeTiled encTiled,
+                     const void* residual, void* y) {
+  const int kc = pl->kc;
+  int ncta = d->cta_pair_hint == 2 ? 2 : 1;
+  int bn = pl->block_n;
+  if (ncta == 2 && d->block_n_hint == 0 && d->c_out_pad % 256 == 0) bn = 256;  // a pair splits the weight tile
+  if (ncta == 2 && bn < 64) ncta = 1;
+  const long long M = (long long)d->batch * h_out * w_out;
+  const int tiles_m = (int)((M + BLOCK_M * ncta - 1) / (BLOCK_M * ncta));
+  const int tiles_n = d->c_out_pad / bn;
+  const int taps = d->ksize * d->ksize;
+  const int num_kb = taps * (d->c_in / kc);
+  int stages = d->stages_hint;
+  if (stages <= 0) {
+    stages = 8;
+    while (stages > 1 && smem_bytes_v2(bn, kc, ncta, stages) > 227 * 1024) --stages;
+  }
+  if (stages > num_kb && num_kb >= 1) stages = num_kb > 1 ? num_kb : 1;
+  if (stages < 2 && num_kb >= 2) stages = 2;
+  const int smem = smem_bytes_v2(bn, kc, ncta, stages);
+  YB_REQUIRE(smem <= 227 * 1024, "conv v2: %d stages do not fit shared memory (block_n %d)", stages, bn);
+
+  ConvKParams2& kp = pl->kp2;
+  kp.tmA = pl->kp.tmA;  // same A geometry as v1 (128-row boxes of KC channels)
+  // weight tile: BLOCK_N / NCTA rows per CTA
+  {
+    const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    cuuint64_t dims[2] = {(cuuint64_t)taps * d->c_in, (cuuint64_t)d->c_out_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)taps * d->c_in * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(bn / ncta)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = encTiled(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(pl->w), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: tensor map B encode failed (%d)", (int)cr);
+  }
+  const int direct = d->upsample2x || d->out_fp32;
+  const int boxc = bn < 64 ? bn : 64;
+  const CUtensorMapSwizzle bswz = boxc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  if (!direct) {
+    cuuint64_t dims[2] = {(cuuint64_t)d->c_out_pad, (cuuint64_t)M};
+    cuuint32_t box[2] = {(cuuint32_t)boxc, (cuuint32_t)BLOCK_M};
+    cuuint32_t estr[2] = {1, 1};
+    cuuint64_t ystr[1] = {(cuuint64_t)d->out_pitch * 2};
+    CUresult cr = encTiled(&kp.tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y, dims, ystr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, bswz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: tensor map Y encode failed (%d)", (int)cr);
+    if (d->has_residual) {
+      cuuint64_t rstr[1] = {(cuuint64_t)d->res_pitch * 2};
+      cr = encTiled(&kp.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(residual), dims, rstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bswz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: tensor map R encode failed (%d)", (int)cr);
+    } else {
+      kp.tmR = kp.tmY;
+    }
+  } else {
+    kp.tmY = kp.tmA;
+    kp.tmR = kp.tmA;
+  }
+  kp.scale = pl->kp.scale; kp.bias = pl->kp.bias; kp.residual = residual; kp.y = y; kp.status = nullptr;
+  kp.M = (int)M; kp.h_out = h_out; kp.w_out = w_out;
+  kp.out_pitch = d->out_pitch; kp.res_pitch = d->res_pitch;
+  kp.num_kb = num_kb; kp.cchunks = d->c_in / kc; kp.stages = stages;
+  kp.tiles_n = tiles_n; kp.num_tiles = tiles_m * tiles_n;
+  kp.ksize = d->ksize; kp.stride = d->stride; kp.pad = d->pad;
+  kp.act = d->act; kp.has_residual = d->has_residual; kp.upsample2x = d->upsample2x;
+  kp.out_fp32 = d->out_fp32; kp.check_nan = d->check_nan; kp.a_im2col = im2col;
+
+  int dev = 0, sms = 148;
+  YB_CHECK_CUDA(cudaGetDevice(&dev));
+  YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int clusters = sms / ncta;
+  if (clusters > kp.num_tiles) clusters = kp.num_tiles;
+  pl->grid2 = clusters * ncta;
+  pl->ncta = ncta;
+  pl->block_n = bn;
+  pl->smem_bytes = smem;
+  pl->grid_x = tiles_n;
+  pl->grid_y = tiles_m;
+  return YB_OK;
+}
+
+int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream) {
+  ConvKParams2 kp = pl->kp2;
+  kp.status = status;
+#define YB_L2(BN, KC)                                                        \
+  if (pl->block_n == BN && pl->kc == KC)                                     \
+    return pl->ncta == 2 ? launch2<BN, KC, 2>(pl, kp, stream) : launch2<BN, KC, 1>(pl, kp, stream);
+  YB_L2(32, 32) YB_L2(64, 32) YB_L2(128, 32) YB_L2(256, 32) YB_L2(32, 64) YB_L2(64, 64) YB_L2(128, 64) YB_L2(256, 64)
+#undef YB_L2
+  yb_set_error("conv v2: no kernel for block_n %d kc %d", pl->block_n, pl->kc);
+  return YB_ERR_UNSUPPORTED;
+}

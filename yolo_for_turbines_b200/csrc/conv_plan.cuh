@@ -1,0 +1,66 @@
+// Plan blob shared by the conv kernels (opaque to the C-ABI caller).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+constexpr int BLOCK_M = 128;
+constexpr uint32_t PLAN_MAGIC = 0x59423230u;  // "YB20"
+
+// v1: one CTA per output tile (conv.cu)
+struct ConvKParams {
+  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmB;
+  const float* scale;
+  const float* bias;
+  const void* residual;
+  void* y;
+  uint32_t* status;
+  int M, h_out, w_out;
+  int out_pitch, res_pitch;
+  int num_kb, cchunks, stages, tiles_n;
+  int ksize, stride, pad;
+  int act, has_residual, upsample2x, out_fp32, check_nan, a_im2col;
+};
+
+// v2: persistent, TMEM double-buffered, TMA-store epilogue, optional CTA pair (conv2.cu)
+struct ConvKParams2 {
+  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmB;
+  alignas(64) CUtensorMap tmY;  // output boxes   [128 rows x min(64, BLOCK_N) cols]
+  alignas(64) CUtensorMap tmR;  // residual boxes, same geometry
+  const float* scale;
+  const float* bias;
+  const void* residual;
+  void* y;
+  uint32_t* status;
+  int M, h_out, w_out;
+  int out_pitch, res_pitch;
+  int num_kb, cchunks, stages, tiles_n, num_tiles;  // tiles of (128 * NCTA) x BLOCK_N
+  int ksize, stride, pad;
+  int act, has_residual, upsample2x, out_fp32, check_nan, a_im2col;
+};
+
+struct ConvPlan {
+  ConvKParams kp;
+  ConvKParams2 kp2;
+  int impl, ncta, grid2;
+  const void* w;
+  yolo_conv_desc d;
+  int block_n, kc, grid_x, grid_y, smem_bytes;
+  uint32_t magic;
+};
+
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// conv2.cu
+int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out, int im2col, PFN_encodeTiled encTiled,
+                     const void* residual, void* y);
+int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream);

@@ -235,6 +235,7 @@ class ForwardPlan:
             d.act = ACT_CODES[pc.act]
             d.upsample2x, d.out_fp32, d.check_nan = int(op.upsample), int(op.dst.fp32), int(op.check_nan)
             d.a_mode, d.block_n_hint, d.stages_hint = 0, engine.block_n_hint, engine.stages_hint
+            d.impl_hint, d.cta_pair_hint = engine.impl_hint, engine.cta_pair_hint
             x_ptr = sroot.buf.data_ptr() + soff * 2
             y_ptr = droot.buf.data_ptr() + doff * (4 if op.dst.fp32 else 2)
             r_ptr = None
@@ -309,6 +310,7 @@ class Engine:
 
         self.model, self.device = model, torch.device(device)
         self.block_n_hint, self.stages_hint = 0, 0
+        self.impl_hint, self.cta_pair_hint = 0, 0  # 0 = library defaults (include/yolo_b200.h)
         self.packed: Dict[int, PackedConv] = {}
         blocks = [m for m in model.modules() if isinstance(m, CNNBlock)]
         first = model.layers[0] if hasattr(model, "layers") and len(model.layers) else None
