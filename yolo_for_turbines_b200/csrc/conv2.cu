@@ -22,8 +22,9 @@ namespace {
 
 using namespace convptx;
 
-constexpr int CONV2_THREADS = 192;
-constexpr int NBOX = 4;  // ring of output/residual boxes in shared memory
+constexpr int CONV2_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 = two epilogue groups
+constexpr int WSLOTS = 2;           // per-warp ring of 32-row output/residual boxes in shared memory
+constexpr int EPI_WARPS = 8;
 
 template <int BLOCK_N, int KC, int NCTA>
 struct Cfg {
@@ -34,15 +35,52 @@ struct Cfg {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BOXC = BLOCK_N < 64 ? BLOCK_N : 64;   // channels per epilogue box
   static constexpr int BOX_ROW_BYTES = BOXC * 2;             // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
-  static constexpr uint32_t BOX_BYTES = BLOCK_M * BOX_ROW_BYTES;
+  static constexpr uint32_t WBOX_BYTES = 32 * BOX_ROW_BYTES; // one warp's 32 rows of a box
   static constexpr int NBOXES = BLOCK_N / BOXC;
+  static constexpr uint32_t EPI_BYTES = EPI_WARPS * WSLOTS * WBOX_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) |
                                     (uint32_t((BLOCK_M * NCTA) >> 4) << 24);
-  static int smem_bytes(int stages) {
-    return stages * STAGE_BYTES + NBOX * BOX_BYTES + (2 * stages + 4 + NBOX) * 8 + 16 + 1024;
-  }
+  __host__ __device__ static constexpr int NUM_BARS(int stages) { return 2 * stages + 4 + EPI_WARPS * WSLOTS; }
+  static int smem_bytes(int stages) { return stages * STAGE_BYTES + EPI_BYTES + NUM_BARS(stages) * 8 + 16 + 1024; }
 };
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// scale/bias + activation on 32 accumulator columns.  LeakyReLU(0.1) is branch-free: max(v, 0.1 v).
+__device__ __forceinline__ void bn_act32(const uint32_t (&v)[32], float (&o)[32], const float* __restrict__ scale,
+                                         const float* __restrict__ bias, int n, int act) {
+  const float4* sp = reinterpret_cast<const float4*>(scale + n);
+  const float4* bp = reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 s4 = __ldg(sp + j), b4 = __ldg(bp + j);
+    o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), s4.x, b4.x);
+    o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), s4.y, b4.y);
+    o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), s4.z, b4.z);
+    o[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), s4.w, b4.w);
+  }
+  if (act == YB_ACT_LEAKY) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.1f * o[j]);  // NaN stays NaN (both operands NaN)
+  } else if (act == YB_ACT_MISH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = apply_act(o[j], YB_ACT_MISH);
+  }
+}
 
 template <int BLOCK_N, int KC, int NCTA>
 __global__ void __launch_bounds__(CONV2_THREADS, 1)
@@ -51,14 +89,14 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int stages = p.stages;
-  const uint32_t box_base = smem_base + stages * C::STAGE_BYTES;
-  const uint32_t bar_base = box_base + NBOX * C::BOX_BYTES;
+  const uint32_t epi_base = smem_base + stages * C::STAGE_BYTES;
+  const uint32_t bar_base = epi_base + C::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (stages + s) * 8; };
   auto tfull_bar = [&](int a) { return bar_base + (2 * stages + a) * 8; };
   auto tempty_bar = [&](int a) { return bar_base + (2 * stages + 2 + a) * 8; };
-  auto res_bar = [&](int b) { return bar_base + (2 * stages + 4 + b) * 8; };
-  const uint32_t tmem_slot = bar_base + (2 * stages + 4 + NBOX) * 8;
+  auto res_bar = [&](int w, int sl) { return bar_base + (2 * stages + 4 + w * WSLOTS + sl) * 8; };
+  const uint32_t tmem_slot = bar_base + C::NUM_BARS(stages) * 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
@@ -77,9 +115,10 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4 * NCTA);  // one arrive per epilogue warp of every CTA of the pair
+      mbar_init(tempty_bar(a), 4 * NCTA);  // one arrive per warp of the owning epilogue group, per CTA
     }
-    for (int b = 0; b < NBOX; ++b) mbar_init(res_bar(b), 1);
+    for (int w = 0; w < EPI_WARPS; ++w)
+      for (int sl = 0; sl < WSLOTS; ++sl) mbar_init(res_bar(w, sl), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc_n<NCTA>(tmem_slot, C::TMEM_COLS);
@@ -107,13 +146,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           cw = qo * p.stride - p.pad;
           ch = po * p.stride - p.pad;
         }
+        int tap = 0, cc = 0;
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t ph = (it / stages) & 1;
           mbar_wait(empty_bar(s), ph ^ 1u);
           if (leader) mbar_expect_tx(full_bar(s), C::STAGE_BYTES * NCTA);
           const uint32_t sa = smem_base + s * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-          const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
           if constexpr (NCTA == 1) {
             if (p.a_im2col) {
               const int r = tap / p.ksize, q = tap - r * p.ksize;
@@ -131,6 +170,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             }
             tma_load_2d_2sm(&p.tmB, full_bar(s), sb, kb * KC, nb0);
           }
+          if (++cc == p.cchunks) { cc = 0; ++tap; }
         }
       }
     }
@@ -161,20 +201,25 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       }
     }
   } else {
-    // ===== epilogue =====
+    // ===== epilogue: group g = (warp-2)/4 owns TMEM accumulator g and every second tile; each warp works
+    // alone on its 32 rows (TMEM lane quadrant = warp % 4): own smem slots, own TMA loads/stores, no CTA barrier.
+    const int ew = warp - 2;
+    const uint32_t acc = uint32_t(ew >> 2);
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int ep_tid = (warp - 2) * 32 + lane;
     const bool direct = p.upsample2x || p.out_fp32;
-    uint32_t tl = 0, boxctr = 0;
+    const uint32_t wslot_base = epi_base + uint32_t(ew) * WSLOTS * C::WBOX_BYTES;
+    const uint32_t swz = (C::BOX_ROW_BYTES == 128) ? (lane & 7) : ((lane >> 1) & 3);
+    uint32_t tl = 0, wbox = 0;
     bool saw_nan = false;
     for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++tl) {
+      if ((tl & 1u) != acc) continue;
+      const uint32_t aph = (tl >> 1) & 1u;
       const int nt = t % p.tiles_n, mt = t / p.tiles_n;
-      const int m0 = (mt * NCTA + (int)rank) * BLOCK_M;
+      const int m0w = (mt * NCTA + (int)rank) * BLOCK_M + quad * 32;
       const int n0 = nt * BLOCK_N;
-      const int m = m0 + row;
+      const int m = m0w + lane;
       const bool valid = m < p.M;
-      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      const bool wvalid = m0w < p.M;
       size_t out_row[4];
       int n_out_rows = 1;
       out_row[0] = size_t(m);
@@ -188,46 +233,47 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         out_row[0] = r00; out_row[1] = r00 + 1; out_row[2] = r00 + W2; out_row[3] = r00 + W2 + 1;
         n_out_rows = 4;
       }
+      const bool staged = !direct && wvalid;
       bool acc_ready = false;
 #pragma unroll 1
-      for (int b = 0; b < C::NBOXES; ++b, ++boxctr) {
-        const uint32_t slot = boxctr % NBOX, sph = (boxctr / NBOX) & 1u;
-        const uint32_t slot_addr = box_base + slot * C::BOX_BYTES;
+      for (int b = 0; b < C::NBOXES; ++b) {
+        const uint32_t slot = wbox % WSLOTS, sph = (wbox / WSLOTS) & 1u;
+        const uint32_t slot_addr = wslot_base + slot * C::WBOX_BYTES;
         const int nb = n0 + b * C::BOXC;
-        if (!direct) {
-          if (ep_tid == 0) {
-            bulk_wait_group_read<NBOX - 1>();  // the TMA store that last used this slot has read it out
+        if (staged) {
+          if (lane == 0) {
+            bulk_wait_group_read<WSLOTS - 1>();  // the TMA store that last used this slot has read it out
             if (p.has_residual) {
-              mbar_expect_tx(res_bar(slot), C::BOX_BYTES);
-              tma_load_2d(&p.tmR, res_bar(slot), slot_addr, nb, m0);
+              mbar_expect_tx(res_bar(ew, slot), C::WBOX_BYTES);
+              tma_load_2d(&p.tmR, res_bar(ew, slot), slot_addr, nb, m0w);
             }
           }
-          named_bar_sync(1, 128);
+          __syncwarp();
         }
         if (!acc_ready) {
           mbar_wait(tfull_bar(acc), aph);
           tc_fence_after();
           acc_ready = true;
         }
-        if (!direct && p.has_residual) mbar_wait(res_bar(slot), sph);
-        const uint32_t row_addr = slot_addr + row * C::BOX_ROW_BYTES;
-        const uint32_t swz = (C::BOX_ROW_BYTES == 128) ? (row & 7) : ((row >> 1) & 3);
-#pragma unroll 1
-        for (int h = 0; h < C::BOXC / 32; ++h) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + b * C::BOXC + h * 32, v);
+        const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + b * C::BOXC;
+        uint32_t v0[32], v1[32];
+        tmem_ld32_nowait(taddr, v0);
+        if constexpr (C::BOXC == 64) tmem_ld32_nowait(taddr + 32, v1);
+        tmem_wait_ld();
+        if (b == C::NBOXES - 1) {
+          // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (NCTA == 1) mbar_arrive_local(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc));
+          }
+        }
+        if (staged && p.has_residual) mbar_wait(res_bar(ew, slot), sph);
+        const uint32_t row_addr = slot_addr + lane * C::BOX_ROW_BYTES;
+        auto process_half = [&](const uint32_t (&v)[32], const int h) {
           const int n = nb + h * 32;
           float o[32];
-          const float4* sp = reinterpret_cast<const float4*>(p.scale + n);
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 s4 = __ldg(sp + j), b4 = __ldg(bp + j);
-            o[4 * j + 0] = apply_act(fmaf(__uint_as_float(v[4 * j + 0]), s4.x, b4.x), p.act);
-            o[4 * j + 1] = apply_act(fmaf(__uint_as_float(v[4 * j + 1]), s4.y, b4.y), p.act);
-            o[4 * j + 2] = apply_act(fmaf(__uint_as_float(v[4 * j + 2]), s4.z, b4.z), p.act);
-            o[4 * j + 3] = apply_act(fmaf(__uint_as_float(v[4 * j + 3]), s4.w, b4.w), p.act);
-          }
+          bn_act32(v, o, p.scale, p.bias, n, p.act);
           if (p.has_residual) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -283,27 +329,22 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
               }
             }
           }
-        }
-        if (b == C::NBOXES - 1) {
-          // all tcgen05.ld of this accumulator have completed (wait::ld): hand it back to the MMA warp
-          tc_fence_before();
+        };
+        process_half(v0, 0);
+        if constexpr (C::BOXC == 64) process_half(v1, 1);
+        if (staged) {
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
-            if constexpr (NCTA == 1) mbar_arrive_local(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc));
-          }
-        }
-        if (!direct) {
-          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-          named_bar_sync(1, 128);
-          if (ep_tid == 0) {
-            tma_store_2d(&p.tmY, slot_addr, nb, m0);  // rows >= M are clipped by the tensor map
+            tma_store_2d(&p.tmY, slot_addr, nb, m0w);  // rows >= M are clipped by the tensor map
             bulk_commit_group();
           }
+          ++wbox;
         }
       }
     }
     if (saw_nan) atomicOr(p.status, YB_STATUS_NAN_LAYER);
-    if (ep_tid == 0) bulk_wait_group_all();
+    if (lane == 0) bulk_wait_group_all();
   }
 
   tc_fence_before();
@@ -362,8 +403,8 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
     stages = 8;
     while (stages > 1 && smem_bytes_v2(bn, kc, ncta, stages) > 227 * 1024) --stages;
   }
-  if (stages > num_kb && num_kb >= 1) stages = num_kb > 1 ? num_kb : 1;
-  if (stages < 2 && num_kb >= 2) stages = 2;
+  // the smem ring spans tiles in a persistent kernel: never clamp it to this layer's k-block count
+  while (stages > 1 && smem_bytes_v2(bn, kc, ncta, stages) > 227 * 1024) --stages;  // a hint is a ceiling
   const int smem = smem_bytes_v2(bn, kc, ncta, stages);
   YB_REQUIRE(smem <= 227 * 1024, "conv v2: %d stages do not fit shared memory (block_n %d)", stages, bn);
 
@@ -386,7 +427,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   const CUtensorMapSwizzle bswz = boxc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   if (!direct) {
     cuuint64_t dims[2] = {(cuuint64_t)d->c_out_pad, (cuuint64_t)M};
-    cuuint32_t box[2] = {(cuuint32_t)boxc, (cuuint32_t)BLOCK_M};
+    cuuint32_t box[2] = {(cuuint32_t)boxc, 32u};  // one epilogue warp's 32 rows
     cuuint32_t estr[2] = {1, 1};
     cuuint64_t ystr[1] = {(cuuint64_t)d->out_pitch * 2};
     CUresult cr = encTiled(&kp.tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y, dims, ystr, box, estr,

@@ -87,6 +87,52 @@ __global__ void __launch_bounds__(256) k_decode(const DecodeParams p) {
   }
 }
 
+// Fast path for the model's own head layout: a dense [B*S*S pixels][pitch] fp32 buffer whose (B,3,S,S,C)
+// view has strides (S*S*pitch, C, S*pitch, pitch, 1).  A CTA stages DEC_PIX whole pixel rows in shared
+// memory with coalesced loads (row pitch + 1 words => the per-cell scans below are bank-conflict free),
+// then one thread per (pixel, anchor) cell scans its logits from shared memory.  Same arithmetic as
+// k_decode; HBM traffic is exactly one read of the head and one 24-byte row per cell.
+constexpr int DEC_PIX = 32;
+constexpr int DEC_THREADS = 128;
+
+__global__ void __launch_bounds__(DEC_THREADS) k_decode_dense(const DecodeParams p, int pitch, long long total_pix) {
+  extern __shared__ float s_head[];
+  const int sp = pitch + 1;
+  const long long pix0 = (long long)blockIdx.x * DEC_PIX;
+  const int npix = (int)min((long long)DEC_PIX, total_pix - pix0);
+  const float* src = p.head + pix0 * pitch;
+  for (int i = threadIdx.x; i < npix * pitch; i += DEC_THREADS) {
+    const int r = i / pitch, c = i - r * pitch;
+    s_head[r * sp + c] = src[i];
+  }
+  __syncthreads();
+  const int C = 5 + p.nc;
+  const int ss = p.S * p.S;
+  for (int cell = threadIdx.x; cell < 3 * npix; cell += DEC_THREADS) {
+    const int a = cell / npix, r = cell - a * npix;  // consecutive threads -> consecutive output rows
+    const float* t = s_head + r * sp + a * C;
+    float best = t[5];
+    int best_i = 0;
+    bool best_nan = best != best;
+    for (int c = 1; c < p.nc; ++c) {  // utils.py:112: first maximal logit, NaN counts as maximal
+      const float v = t[5 + c];
+      const bool vn = v != v;
+      if (!best_nan && (vn || v > best)) { best = v; best_i = c; best_nan = vn; }
+    }
+    const long long pix = pix0 + r;
+    const int b = (int)(pix / ss);
+    const int rem = (int)(pix - (long long)b * ss);
+    const int i = rem / p.S, j = rem - i * p.S;
+    float* o = p.out + (size_t(b) * p.out_boxes_per_image + p.out_offset + size_t(a) * ss + rem) * 6;
+    const float sx = sigmoid_f32(t[0]), sy = sigmoid_f32(t[1]);
+    const float w = __fmul_rn(expf(t[2]), p.anchors[2 * a]), h = __fmul_rn(expf(t[3]), p.anchors[2 * a + 1]);
+    float2* o2 = reinterpret_cast<float2*>(o);
+    o2[0] = make_float2(__fmul_rn(p.inv_s, __fadd_rn(sx, float(j))), __fmul_rn(p.inv_s, __fadd_rn(sy, float(i))));
+    o2[1] = make_float2(__fmul_rn(p.inv_s, w), __fmul_rn(p.inv_s, h));
+    o2[2] = make_float2(sigmoid_f32(t[4]), float(best_i));
+  }
+}
+
 }  // namespace
 
 extern "C" int yolo_decode(const float* head, const int64_t* strides5_host, int batch, int S, int nc,
@@ -104,6 +150,18 @@ extern "C" int yolo_decode(const float* head, const int64_t* strides5_host, int 
   p.is_pred = is_pred; p.writeback = writeback;
   p.out = out; p.out_boxes_per_image = out_boxes_per_image; p.out_offset = out_offset;
   p.inv_s = (float)(1.0 / (double)S);
+  const long long pitch = p.st[3];
+  const int C = 5 + nc;
+  if (is_pred && !writeback && p.st[4] == 1 && p.st[1] == C && pitch >= 3 * C && pitch <= 384 &&
+      p.st[2] == (long long)S * pitch && p.st[0] == (long long)S * S * pitch &&
+      (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+    const long long total_pix = (long long)batch * S * S;
+    const size_t smem = size_t(DEC_PIX) * (pitch + 1) * sizeof(float);
+    k_decode_dense<<<(unsigned)((total_pix + DEC_PIX - 1) / DEC_PIX), DEC_THREADS, smem, (cudaStream_t)stream>>>(
+        p, (int)pitch, total_pix);
+    YB_CHECK_LAUNCH();
+    return YB_OK;
+  }
   const long long cells = 3ll * S * S * batch;
   const int wpb = 8;
   k_decode<<<(unsigned)((cells + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(p);

@@ -106,7 +106,11 @@ __global__ void k_gather_segments(const float* __restrict__ boxes, const uint64_
     cbox[q] = make_float4(c.x1, c.y1, c.x2, c.y2);
   }
   area[q] = a;
-  suppressed[q] = 0;
+  // bit 1 = "special": anything for which the 4-compare disjointness test below would not be the exact
+  // answer (non-finite corner or area, empty or inverted extent, negative area).  Bit 0 = suppressed.
+  const bool ordinary = fabsf(c.x1) < INFINITY && fabsf(c.y1) < INFINITY && fabsf(c.x2) < INFINITY &&
+                        fabsf(c.y2) < INFINITY && c.x2 > c.x1 && c.y2 > c.y1 && a >= 0.f && a < INFINITY;
+  suppressed[q] = ordinary ? 0 : 2;
   if (q == 0 || key2[q] != key2[q - 1]) seg_starts[atomicAdd(nseg, 1)] = q;
 }
 
@@ -129,6 +133,20 @@ __device__ __forceinline__ bool nms_suppresses(const float4 e, const float ae, c
   return !(iou < thr);
 }
 
+// Hot-loop form: two ordinary boxes (see k_gather_segments) whose extents are disjoint have an exactly
+// zero intersection and a positive finite denominator, so iou == 0 < thr: four compares settle it.
+__device__ __forceinline__ bool nms_pair(const float4 e, const float ae, const float4 l, const float al,
+                                         const bool general, const float thr, const bool thr_pos) {
+  if (!general) {
+    if (e.z <= l.x || l.z <= e.x || e.w <= l.y || l.w <= e.y) return false;
+    const float iw = __fsub_rn(fminf(e.z, l.z), fmaxf(e.x, l.x)), ih = __fsub_rn(fminf(e.w, l.w), fmaxf(e.y, l.y));
+    const float inter = __fmul_rn(iw, ih);
+    const float iou = __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(ae, al), inter), 1e-6f));
+    return !(iou < thr);
+  }
+  return nms_suppresses(e, ae, l, al, thr, thr_pos);
+}
+
 // One CTA per (image, class) segment, boxes in descending-score order.  The
 // segment is walked in chunks of 32: warp 0 resolves the chunk serially from a
 // 32x32 IoU bit matrix held in registers (one row per lane, shuffled out), the
@@ -142,6 +160,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
                uint8_t* __restrict__ keep) {
   __shared__ float4 s_box[32];
   __shared__ float s_area[32];
+  __shared__ int s_general[32];
   __shared__ unsigned s_row[32];
   __shared__ int s_nkept;
   __shared__ int s_end;
@@ -171,7 +190,9 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
       {
         const int qi = c0 + warp, qj = c0 + lane;
         bool sup = false;
-        if (lane > warp && qj < s1) sup = nms_suppresses(cbox[qi], area[qi], cbox[qj], area[qj], thr, thr_pos);
+        if (lane > warp && qj < s1)
+          sup = nms_pair(cbox[qi], area[qi], cbox[qj], area[qj], !thr_pos || ((suppressed[qi] | suppressed[qj]) & 2),
+                         thr, thr_pos);
         const unsigned row = __ballot_sync(0xffffffffu, sup);
         if (lane == 0) s_row[warp] = row;
       }
@@ -181,7 +202,8 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
         const int qi = c0 + lane;
         const bool valid = qi < s1;
         const unsigned row = s_row[lane];
-        unsigned alive = __ballot_sync(0xffffffffu, valid && suppressed[qi] == 0);
+        const int my_state = valid ? suppressed[qi] : 1;
+        unsigned alive = __ballot_sync(0xffffffffu, (my_state & 1) == 0);
         unsigned kept = 0;
 #pragma unroll 8
         for (int i = 0; i < 32; ++i) {
@@ -193,6 +215,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
           const int slot = __popc(kept & ((1u << lane) - 1u));
           s_box[slot] = cbox[qi];
           s_area[slot] = area[qi];
+          s_general[slot] = !thr_pos || (my_state & 2);
         }
         if (lane == 0) s_nkept = __popc(kept);
       }
@@ -200,11 +223,16 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
       // (c) the chunk's survivors knock out later boxes of the segment, all threads
       const int nk = s_nkept;
       for (int q = c0 + 32 + tid; q < s1; q += NMS_THREADS) {
-        if (suppressed[q]) continue;
+        const int state = suppressed[q];
+        if (state & 1) continue;
         const float4 b = cbox[q];
         const float al = area[q];
+        const bool lgen = (state & 2) != 0;
         for (int t = 0; t < nk; ++t) {
-          if (nms_suppresses(s_box[t], s_area[t], b, al, thr, thr_pos)) { suppressed[q] = 1; break; }
+          if (nms_pair(s_box[t], s_area[t], b, al, lgen || s_general[t], thr, thr_pos)) {
+            suppressed[q] = state | 1;
+            break;
+          }
         }
       }
       __syncthreads();
@@ -222,14 +250,16 @@ k_keep_count(const uint8_t* __restrict__ keep, const int32_t* __restrict__ n_dev
   for (int k = 0; k < COMPACT_ITEMS; ++k) c += (base + k < n && keep[base + k]) ? 1 : 0;
   int tot;
   block_exclusive_scan<COMPACT_THREADS>(c, &tot);
-  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot;
+  if (threadIdx.x == 0) {
+    tile_cnt[blockIdx.x] = tot;
+    if (blockIdx.x == 0) tile_cnt[gridDim.x] = 0;  // sentinel: after the scan it holds the grand total
+  }
 }
 
 __global__ void __launch_bounds__(COMPACT_THREADS)
 k_keep_write(const uint8_t* __restrict__ keep, const uint64_t* __restrict__ key1,
              const int32_t* __restrict__ idx1, const int32_t* __restrict__ n_dev,
-             const int32_t* __restrict__ tile_off, int32_t* __restrict__ keep_idx,
-             int32_t* __restrict__ keep_off) {
+             const int32_t* __restrict__ tile_off, int32_t* __restrict__ keep_idx) {
   const int n = *n_dev;
   const int base = blockIdx.x * COMPACT_TILE + threadIdx.x * COMPACT_ITEMS;
   unsigned flags = 0;
@@ -241,11 +271,30 @@ k_keep_write(const uint8_t* __restrict__ keep, const uint64_t* __restrict__ key1
 #pragma unroll
   for (int k = 0; k < COMPACT_ITEMS; ++k) {
     if (flags & (1u << k)) {
-      const int p = base + k;
-      keep_idx[pos++] = idx1[p];
-      atomicAdd(&keep_off[int(key1[p] >> 32)], 1);  // per-image counts, scanned afterwards
+      keep_idx[pos++] = idx1[base + k];
     }
   }
+}
+
+// keep_off[b] = number of survivors in images < b = survivors at positions p < (first p of image >= b):
+// one warp per entry; binary search on the image-sorted keys, then tile prefix + partial-tile count.
+__global__ void k_keep_offsets(const uint8_t* __restrict__ keep, const uint64_t* __restrict__ key1,
+                               const int32_t* __restrict__ n_dev, const int32_t* __restrict__ tile_off, int batch,
+                               int32_t* __restrict__ keep_off) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b > batch) return;
+  const int n = *n_dev;
+  int lo = 0, hi = n;  // first p with image(p) >= b
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (int(key1[mid] >> 32) < b) lo = mid + 1; else hi = mid;
+  }
+  const int tile = lo / COMPACT_TILE;
+  int c = 0;
+  for (int p = tile * COMPACT_TILE + lane; p < lo; p += 32) c += keep[p] ? 1 : 0;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if (lane == 0) keep_off[b] = tile_off[tile] + c;
 }
 
 struct NmsWs {
@@ -357,12 +406,15 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   // survivors, in the reference's order, + per-image offsets
   k_keep_count<<<w.ctiles, COMPACT_THREADS, 0, stream>>>(w.keep, n_valid, w.tile_cnt);
   YB_CHECK_LAUNCH();
-  rc = exclusive_scan_small(w.tile_cnt, w.ctiles, nullptr, stream);
+  rc = exclusive_scan_small(w.tile_cnt, w.ctiles + 1, nullptr, stream);
   if (rc) return rc;
   k_keep_write<<<w.ctiles, COMPACT_THREADS, 0, stream>>>(w.keep, w.key1, w.idx1, n_valid,
-                                                         w.tile_cnt, keep_idx, keep_off);
+                                                         w.tile_cnt, keep_idx);
   YB_CHECK_LAUNCH();
-  return exclusive_scan_small(keep_off, batch + 1, nullptr, stream);
+  k_keep_offsets<<<yb_cdiv((batch + 1) * 32, 128), 128, 0, stream>>>(w.keep, w.key1, n_valid, w.tile_cnt, batch,
+                                                                     keep_off);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
 }
 
 // ---- element-wise IoU: utils.py:38-84 calc_iou / utils.py:22-36 iou_aligned --

@@ -37,6 +37,23 @@ k_exclusive_scan(int32_t* __restrict__ data, int n, int32_t* __restrict__ total_
   if (threadIdx.x == 0 && total_out) *total_out = total;
 }
 
+// One CTA per digit: exclusive scan of that digit's per-tile counts (contiguous, coalesced) and the
+// digit's total.  Replaces a single-CTA scan over all 256 x tiles entries.
+__global__ void __launch_bounds__(256)
+k_radix_scan_digits(int32_t* __restrict__ hist, int num_tiles, int32_t* __restrict__ digit_total) {
+  int32_t* row = hist + size_t(blockIdx.x) * num_tiles;
+  int carry = 0;
+  for (int base = 0; base < num_tiles; base += 256) {
+    const int i = base + threadIdx.x;
+    const int v = i < num_tiles ? row[i] : 0;
+    int tot;
+    const int ex = block_exclusive_scan<256>(v, &tot);
+    if (i < num_tiles) row[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) digit_total[blockIdx.x] = carry;
+}
+
 // Stable scatter: items are taken in index order (round-major, then thread id);
 // within a round the rank of an item among equal digits is
 //   [items of lower warps] + [lower lanes of the same warp]  (match_any ballot).
@@ -44,14 +61,17 @@ __global__ void __launch_bounds__(SORT_THREADS)
 k_radix_scatter(const uint64_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                 uint64_t* __restrict__ keys_out, int32_t* __restrict__ vals_out,
                 const int32_t* __restrict__ n_dev, int shift, const int32_t* __restrict__ hist,
-                int num_tiles) {
+                const int32_t* __restrict__ digit_total, int num_tiles) {
   __shared__ int digit_base[256];
   __shared__ int warp_cnt[SORT_THREADS / 32][256];
   const int n = *n_dev;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int base = blockIdx.x * SORT_TILE;
   if (base >= n) return;  // uniform: the whole tile is past the live count
-  digit_base[tid] = hist[tid * num_tiles + blockIdx.x];
+  {
+    const int doff = block_exclusive_scan<SORT_THREADS>(digit_total[tid], nullptr);  // keys with a smaller digit
+    digit_base[tid] = doff + hist[tid * num_tiles + blockIdx.x];                      // + same digit, earlier tiles
+  }
   for (int r = 0; r < SORT_ROUNDS; ++r) {
     const int round_base = base + r * SORT_THREADS;
     if (round_base >= n) break;  // uniform
@@ -106,10 +126,10 @@ int radix_sort_pairs(uint64_t* keys, int32_t* vals, const int32_t* n_dev, int ma
   for (int shift = bit_lo; shift < bit_hi; shift += 8) {
     k_radix_hist<<<tiles, SORT_THREADS, 0, stream>>>(kin, n_dev, shift, sb.hist, tiles);
     YB_CHECK_LAUNCH();
-    k_exclusive_scan<<<1, 1024, 0, stream>>>(sb.hist, 256 * tiles, nullptr);
+    k_radix_scan_digits<<<256, 256, 0, stream>>>(sb.hist, tiles, sb.digit_total);
     YB_CHECK_LAUNCH();
     k_radix_scatter<<<tiles, SORT_THREADS, 0, stream>>>(kin, vin, kout, vout, n_dev, shift, sb.hist,
-                                                        tiles);
+                                                        sb.digit_total, tiles);
     YB_CHECK_LAUNCH();
     uint64_t* tk = kin; kin = kout; kout = tk;
     int32_t* tv = vin; vin = vout; vout = tv;

@@ -6,13 +6,14 @@
 #include "common.cuh"
 
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ROUNDS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;  // 4096 keys per CTA
+constexpr int SORT_ROUNDS = 4;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;  // 1024 keys per CTA
 
 struct SortBuffers {  // carved from the caller's workspace
   uint64_t* keys_alt;
   int32_t* vals_alt;
-  int32_t* hist;  // [256][num_tiles]
+  int32_t* hist;         // [256][num_tiles], digit-major
+  int32_t* digit_total;  // [256]
   int num_tiles;
 };
 inline void sort_carve(WsCarver& ws, int max_n, SortBuffers* sb) {
@@ -20,6 +21,7 @@ inline void sort_carve(WsCarver& ws, int max_n, SortBuffers* sb) {
   sb->keys_alt = ws.take<uint64_t>(max_n);
   sb->vals_alt = ws.take<int32_t>(max_n);
   sb->hist = ws.take<int32_t>(size_t(256) * sb->num_tiles);
+  sb->digit_total = ws.take<int32_t>(256);
 }
 
 // Sorts ascending on key bits [bit_lo, bit_hi) (multiples of 8).  Result is in
