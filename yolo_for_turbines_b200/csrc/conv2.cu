@@ -389,7 +389,8 @@ int smem_bytes_v2(int bn, int kc, int ncta, int stages) {
 int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out, int im2col, PFN_encodeTiled encTiled,
                      const void* residual, void* y) {
   const int kc = pl->kc;
-  int ncta = d->cta_pair_hint == 2 ? 2 : 1;
+  // default: a cta_group::2 pair (measured faster or equal on every YOLOv3 layer); 1 forces single CTAs
+  int ncta = d->cta_pair_hint == 1 ? 1 : 2;
   int bn = pl->block_n;
   if (ncta == 2 && d->block_n_hint == 0 && d->c_out_pad % 256 == 0) bn = 256;  // a pair splits the weight tile
   if (ncta == 2 && bn < 64) ncta = 1;
