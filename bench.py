@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
-    ap.add_argument("--impl", type=int, default=0)
+    ap.add_argument("--conv-impl", type=int, default=0)
     ap.add_argument("--pair", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -184,7 +184,7 @@ def main():
     model = YOLOv3(num_classes=args.classes).eval().to(dev)
     eng = model._engine(dev)
     eng.block_n_hint, eng.stages_hint = args.block_n, args.stages
-    eng.impl_hint, eng.cta_pair_hint = args.impl, args.pair
+    eng.impl_hint, eng.cta_pair_hint = args.conv_impl, args.pair
     det = Detector(model, cfg.ANCHORS, args.iou, args.conf, "center")
     B, S = args.batch, args.size
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
