@@ -129,75 +129,71 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer (every CTA loads its own A rows and its share of the weight tile) =====
-      uint32_t it = 0;
-      for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
-        const int nt = t % p.tiles_n, mt = t / p.tiles_n;
-        int m0 = (mt * NCTA + (int)rank) * BLOCK_M;
-        if (m0 >= p.M) m0 = 0;  // peer CTA of a ragged last pair: load valid rows, results are discarded
-        const int nb0 = nt * BLOCK_N + (int)rank * C::B_ROWS;
-        int cw = 0, ch = 0, img = 0;
-        if (p.a_im2col) {
-          const int hw = p.h_out * p.w_out;
-          img = m0 / hw;
-          const int rem = m0 - img * hw;
-          const int po = rem / p.w_out, qo = rem - po * p.w_out;
-          cw = qo * p.stride - p.pad;
-          ch = po * p.stride - p.pad;
-        }
-        int tap = 0, cc = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1u);
+    // ===== TMA producer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
+      const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+      int m0 = (mt * NCTA + (int)rank) * BLOCK_M;
+      if (m0 >= p.M) m0 = 0;  // peer CTA of a ragged last pair: load valid rows, results are discarded
+      const int nb0 = nt * BLOCK_N + (int)rank * C::B_ROWS;
+      int cw = 0, ch = 0, img = 0;
+      if (p.a_im2col) {
+        const int hw = p.h_out * p.w_out;
+        img = m0 / hw;
+        const int rem = m0 - img * hw;
+        const int po = rem / p.w_out, qo = rem - po * p.w_out;
+        cw = qo * p.stride - p.pad;
+        ch = po * p.stride - p.pad;
+      }
+      int tr = 0, tq = 0, cc = 0;  // filter tap (row, col) and channel chunk of the current k-block
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (elect_one()) {
           if (leader) mbar_expect_tx(full_bar(s), C::STAGE_BYTES * NCTA);
           const uint32_t sa = smem_base + s * C::STAGE_BYTES, sb = sa + C::A_BYTES;
           if constexpr (NCTA == 1) {
-            if (p.a_im2col) {
-              const int r = tap / p.ksize, q = tap - r * p.ksize;
-              tma_load_im2col_4d(&p.tmA, full_bar(s), sa, cc * KC, cw, ch, img, (uint16_t)q, (uint16_t)r);
-            } else {
-              tma_load_2d(&p.tmA, full_bar(s), sa, cc * KC, m0);
-            }
+            if (p.a_im2col) tma_load_im2col_4d(&p.tmA, full_bar(s), sa, cc * KC, cw, ch, img, (uint16_t)tq, (uint16_t)tr);
+            else tma_load_2d(&p.tmA, full_bar(s), sa, cc * KC, m0);
             tma_load_2d(&p.tmB, full_bar(s), sb, kb * KC, nb0);
           } else {
-            if (p.a_im2col) {
-              const int r = tap / p.ksize, q = tap - r * p.ksize;
-              tma_load_im2col_4d_2sm(&p.tmA, full_bar(s), sa, cc * KC, cw, ch, img, (uint16_t)q, (uint16_t)r);
-            } else {
-              tma_load_2d_2sm(&p.tmA, full_bar(s), sa, cc * KC, m0);
-            }
+            if (p.a_im2col) tma_load_im2col_4d_2sm(&p.tmA, full_bar(s), sa, cc * KC, cw, ch, img, (uint16_t)tq, (uint16_t)tr);
+            else tma_load_2d_2sm(&p.tmA, full_bar(s), sa, cc * KC, m0);
             tma_load_2d_2sm(&p.tmB, full_bar(s), sb, kb * KC, nb0);
           }
-          if (++cc == p.cchunks) { cc = 0; ++tap; }
         }
+        __syncwarp();
+        if (++cc == p.cchunks) { cc = 0; if (++tq == p.ksize) { tq = 0; ++tr; } }
+        if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ===== MMA issuer =====
-      uint32_t it = 0, tl = 0;
+    if (leader) {
+      // ===== MMA issuer: warp-uniform loop, tcgen05.mma / commit from one elected lane =====
+      int s = 0;
+      uint32_t ph = 0, tl = 0;
+      const uint64_t adesc0 = make_kmajor_desc<C::ROW_BYTES>(smem_base);
+      const uint64_t bdesc0 = make_kmajor_desc<C::ROW_BYTES>(smem_base + C::A_BYTES);
       for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++tl) {
         const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
         mbar_wait(tempty_bar(acc), aph ^ 1u);  // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = (it / stages) & 1;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-          const uint64_t adesc = make_kmajor_desc<C::ROW_BYTES>(sa);
-          const uint64_t bdesc = make_kmajor_desc<C::ROW_BYTES>(sb);
+          if (elect_one()) {
+            const uint64_t soff = uint64_t((uint32_t(s) * C::STAGE_BYTES) >> 4);  // stage offset in descriptor units
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k)
-            umma_bf16_n<NCTA>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), C::IDESC,
-                              (kb | k) != 0 ? 1u : 0u);
-          umma_commit_n<NCTA>(empty_bar(s));
+            for (int k = 0; k < KC / 16; ++k)
+              umma_bf16_n<NCTA>(d_tmem, adesc0 + soff + uint64_t(2 * k), bdesc0 + soff + uint64_t(2 * k), C::IDESC,
+                                (kb | k) != 0 ? 1u : 0u);
+            umma_commit_n<NCTA>(empty_bar(s));
+            if (kb == p.num_kb - 1) umma_commit_n<NCTA>(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (++s == stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit_n<NCTA>(tfull_bar(acc));
       }
     }
   } else {

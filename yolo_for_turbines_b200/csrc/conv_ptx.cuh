@@ -16,8 +16,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
-// Bounded wait: a protocol bug must end in a trap, never in a hung GPU box.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// Bounded wait: a protocol bug must end in a trap, never in a hung GPU box.  The clock is only read
+// once the first probe has failed, so the common (already complete) case costs a single instruction.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   for (;;) {
     uint32_t done;
@@ -127,6 +142,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+
+// One lane of a converged warp; the predicate comes from elect.sync so that ptxas keeps the guarded
+// tcgen05 / TMA operands in uniform registers instead of emitting a per-lane R2UR waterfall.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ---- additions for the persistent / 2-CTA kernel ------------------------------------------------
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;           // clears the CTA-rank bit of a shared::cluster address
