@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int NMS_THREADS = 1024;
+constexpr int NMS_THREADS = 512;
 
 __device__ __forceinline__ int find_image(const int32_t* __restrict__ off, int batch, int i) {
   int lo = 0, hi = batch;  // largest b with off[b] <= i
@@ -147,22 +147,46 @@ __device__ __forceinline__ bool nms_pair(const float4 e, const float ae, const f
   return nms_suppresses(e, ae, l, al, thr, thr_pos);
 }
 
-// One CTA per (image, class) segment, boxes in descending-score order.  The
-// segment is walked in chunks of 32: warp 0 resolves the chunk serially from a
-// 32x32 IoU bit matrix held in registers (one row per lane, shuffled out), the
-// chunk's survivors are staged in shared memory, then the whole CTA applies
-// them to every later, still-alive box of the segment.
+// One CTA per (image, class) segment, boxes in descending-score order, walked in chunks of 32:
+//   (0) the chunk's boxes go to shared memory; the warp that owns them publishes their alive bits;
+//   (a) 32x32 suppression bit matrix, one pair per thread, plus per-chunk SPATIAL BIN MASKS: for each of
+//       32 x-bins and 32 y-bins of [0,1), which chunk boxes overlap the bin;
+//   (b) warp 0 resolves the chunk serially (the reference's greedy loop restricted to 32 boxes);
+//   (c) every thread applies the chunk's survivors to the later boxes it OWNS.  Owned boxes live in
+//       registers for the whole segment (<= 16 per thread, 8192 per segment; longer segments fall back to
+//       global memory).  A later box is only tested against survivors that share an x-bin AND a y-bin
+//       with it -- disjoint extents cannot suppress (iou == 0 < thr) -- so the usual cost per (box,
+//       chunk) is a few shared-memory words instead of up to 32 IoU tests.
+constexpr int NMS_WARPS = NMS_THREADS / 32;
+constexpr int NMS_QPT = 16;
+constexpr int NMS_REG_CAP = NMS_THREADS * NMS_QPT;
+
+__device__ __forceinline__ int nms_bin(float v) {  // monotone and clamped => overlapping extents share a bin
+  return (int)fminf(fmaxf(v * 32.f, 0.f), 31.f);
+}
+__device__ __forceinline__ uint32_t nms_pack_bins(const float4 b) {
+  return uint32_t(nms_bin(b.x)) | (uint32_t(nms_bin(b.z)) << 8) | (uint32_t(nms_bin(b.y)) << 16) |
+         (uint32_t(nms_bin(b.w)) << 24);
+}
+// survivors of the current chunk that could overlap a box with these bins (superset)
+__device__ __forceinline__ uint32_t nms_candidates(uint32_t bins, const uint32_t* s_binx, const uint32_t* s_biny) {
+  const int xl = bins & 31, xh = (bins >> 8) & 31, yl = (bins >> 16) & 31, yh = (bins >> 24) & 31;
+  uint32_t mx = 0, my = 0;
+  if (xh - xl > 3) mx = 0xffffffffu; else for (int b = xl; b <= xh; ++b) mx |= s_binx[b];
+  if (yh - yl > 3) my = 0xffffffffu; else for (int b = yl; b <= yh; ++b) my |= s_biny[b];
+  return mx & my;
+}
+
 __global__ void __launch_bounds__(NMS_THREADS)
 k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
                const uint64_t* __restrict__ key2, const int32_t* __restrict__ val2,
                const int32_t* __restrict__ seg_starts, const int32_t* __restrict__ nseg_dev,
                const int32_t* __restrict__ n_dev, float thr, uint8_t* __restrict__ suppressed,
                uint8_t* __restrict__ keep) {
-  __shared__ float4 s_box[32];
-  __shared__ float s_area[32];
-  __shared__ int s_general[32];
-  __shared__ unsigned s_row[32];
-  __shared__ int s_nkept;
+  __shared__ float4 s_cbox[32];
+  __shared__ float s_carea[32];
+  __shared__ uint32_t s_row[32], s_binx[32], s_biny[32];
+  __shared__ uint32_t s_alive, s_cgen, s_kept;
   __shared__ int s_end;
   const bool thr_pos = thr > 0.f;
   const int n = *n_dev, nseg = *nseg_dev;
@@ -185,53 +209,123 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
       __syncthreads();
       continue;
     }
-    for (int c0 = s0; c0 < s1; c0 += 32) {
-      // (a) 32x32 suppression bits of the chunk, one pair per thread: warp i holds row i
+    const int m = s1 - s0;
+    const bool regpath = m <= NMS_REG_CAP;
+    float4 bx[NMS_QPT];
+    uint32_t bins[NMS_QPT];
+    uint32_t supp = 0, gen = thr_pos ? 0u : 0xffffu;
+    if (regpath) {
+#pragma unroll
+      for (int j = 0; j < NMS_QPT; ++j) {
+        const int q = s0 + j * NMS_THREADS + tid;
+        if (q < s1) {
+          bx[j] = cbox[q];
+          if (suppressed[q] & 2) gen |= 1u << j;
+          bins[j] = nms_pack_bins(bx[j]);
+        } else {
+          bx[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          bins[j] = 0;
+          supp |= 1u << j;
+        }
+      }
+    }
+    for (int ci = 0; ci * 32 < m; ++ci) {
+      const int c0 = s0 + ci * 32;
+      const int own_warp = ci % NMS_WARPS, own_slot = ci / NMS_WARPS;
+      // (0) chunk boxes -> shared memory; alive / "general" bits
+      if (warp == 0) {
+        const int qi = c0 + lane;
+        const bool valid = qi < s1;
+        s_cbox[lane] = valid ? cbox[qi] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s_carea[lane] = valid ? area[qi] : 0.f;
+        const int st = valid ? suppressed[qi] : 1;
+        const uint32_t g = __ballot_sync(0xffffffffu, valid && (!thr_pos || (st & 2)));
+        const uint32_t al = __ballot_sync(0xffffffffu, (st & 1) == 0);
+        if (lane == 0) { s_cgen = g; if (!regpath) s_alive = al; }
+      }
+      if (regpath && warp == own_warp) {
+        const uint32_t al = __ballot_sync(0xffffffffu, ((supp >> own_slot) & 1u) == 0);
+        if (lane == 0) s_alive = al;
+      }
+      __syncthreads();
+      // (a) pair matrix (rows warp and warp+16) and spatial bin masks (bins warp and warp+16)
       {
-        const int qi = c0 + warp, qj = c0 + lane;
-        bool sup = false;
-        if (lane > warp && qj < s1)
-          sup = nms_pair(cbox[qi], area[qi], cbox[qj], area[qj], !thr_pos || ((suppressed[qi] | suppressed[qj]) & 2),
-                         thr, thr_pos);
-        const unsigned row = __ballot_sync(0xffffffffu, sup);
-        if (lane == 0) s_row[warp] = row;
+        const float4 bj = s_cbox[lane];
+        const float aj = s_carea[lane];
+        const uint32_t cgen = s_cgen;
+        const bool vj = c0 + lane < s1;
+        const uint32_t pb = nms_pack_bins(bj);
+        const int xl = pb & 31, xh = (pb >> 8) & 31, yl = (pb >> 16) & 31, yh = (pb >> 24) & 31;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = warp + h * NMS_WARPS;
+          bool sup = false;
+          if (lane > i && vj)
+            sup = nms_pair(s_cbox[i], s_carea[i], bj, aj, ((cgen >> i) | (cgen >> lane)) & 1u, thr, thr_pos);
+          const uint32_t row = __ballot_sync(0xffffffffu, sup);
+          const uint32_t mxb = __ballot_sync(0xffffffffu, vj && xl <= i && i <= xh);
+          const uint32_t myb = __ballot_sync(0xffffffffu, vj && yl <= i && i <= yh);
+          if (lane == 0) { s_row[i] = row; s_binx[i] = mxb; s_biny[i] = myb; }
+        }
       }
       __syncthreads();
       // (b) warp 0 resolves the chunk serially (utils.py:170-187 restricted to these 32 boxes)
       if (warp == 0) {
         const int qi = c0 + lane;
         const bool valid = qi < s1;
-        const unsigned row = s_row[lane];
-        const int my_state = valid ? suppressed[qi] : 1;
-        unsigned alive = __ballot_sync(0xffffffffu, (my_state & 1) == 0);
-        unsigned kept = 0;
+        const uint32_t row = s_row[lane];
+        uint32_t alive = s_alive & __ballot_sync(0xffffffffu, valid);
+        uint32_t kept = 0;
 #pragma unroll 8
         for (int i = 0; i < 32; ++i) {
-          const unsigned ri = __shfl_sync(0xffffffffu, row, i);
+          const uint32_t ri = __shfl_sync(0xffffffffu, row, i);
           if ((alive >> i) & 1u) { kept |= 1u << i; alive &= ~ri; }
         }
         if (valid) keep[val2[qi]] = (kept >> lane) & 1u;
-        if ((kept >> lane) & 1u) {
-          const int slot = __popc(kept & ((1u << lane) - 1u));
-          s_box[slot] = cbox[qi];
-          s_area[slot] = area[qi];
-          s_general[slot] = !thr_pos || (my_state & 2);
-        }
-        if (lane == 0) s_nkept = __popc(kept);
+        if (lane == 0) s_kept = kept;
       }
       __syncthreads();
-      // (c) the chunk's survivors knock out later boxes of the segment, all threads
-      const int nk = s_nkept;
-      for (int q = c0 + 32 + tid; q < s1; q += NMS_THREADS) {
-        const int state = suppressed[q];
-        if (state & 1) continue;
-        const float4 b = cbox[q];
-        const float al = area[q];
-        const bool lgen = (state & 2) != 0;
-        for (int t = 0; t < nk; ++t) {
-          if (nms_pair(s_box[t], s_area[t], b, al, lgen || s_general[t], thr, thr_pos)) {
-            suppressed[q] = state | 1;
-            break;
+      // (c) the chunk's survivors knock out later boxes of the segment
+      const uint32_t kept = s_kept;
+      if (kept != 0) {
+        const uint32_t kgen = kept & s_cgen;  // survivors that need the general path: always candidates
+        if (regpath) {
+#pragma unroll
+          for (int j = 0; j < NMS_QPT; ++j) {
+            const bool later = (j > own_slot) || (j == own_slot && warp > own_warp);
+            if (later && !((supp >> j) & 1u)) {
+              const bool qgen = (gen >> j) & 1u;
+              uint32_t cand = qgen ? kept : ((nms_candidates(bins[j], s_binx, s_biny) & kept) | kgen);
+              if (cand) {
+                const float al = area[s0 + j * NMS_THREADS + tid];
+                while (cand) {
+                  const int t = __ffs(cand) - 1;
+                  cand &= cand - 1;
+                  if (nms_pair(s_cbox[t], s_carea[t], bx[j], al, qgen || ((kgen >> t) & 1u), thr, thr_pos)) {
+                    supp |= 1u << j;
+                    break;
+                  }
+                }
+              }
+            }
+          }
+        } else {
+          for (int q = c0 + 32 + tid; q < s1; q += NMS_THREADS) {
+            const int state = suppressed[q];
+            if (state & 1) continue;
+            const float4 b = cbox[q];
+            const bool qgen = !thr_pos || (state & 2);
+            uint32_t cand = qgen ? kept : ((nms_candidates(nms_pack_bins(b), s_binx, s_biny) & kept) | kgen);
+            if (!cand) continue;
+            const float al = area[q];
+            while (cand) {
+              const int t = __ffs(cand) - 1;
+              cand &= cand - 1;
+              if (nms_pair(s_cbox[t], s_carea[t], b, al, qgen || ((kgen >> t) & 1u), thr, thr_pos)) {
+                suppressed[q] = state | 1;
+                break;
+              }
+            }
           }
         }
       }
@@ -397,7 +491,7 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   int dev = 0, sms = 148;
   YB_CHECK_CUDA(cudaGetDevice(&dev));
   YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int grid = sms * 2;
+  int grid = sms * 3;
   if (grid > total) grid = total;
   k_nms_segments<<<grid, NMS_THREADS, 0, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts,
                                                    nseg, n_valid, iou_thr, w.suppressed, w.keep);
