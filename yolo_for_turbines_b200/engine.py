@@ -10,6 +10,7 @@ Buffers, packed weights and TMA tensor maps are static per plan; torch owns all 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -38,7 +39,7 @@ class PackedConv:
     """bf16 K-major weights + folded-BN scale/bias of one CNNBlock, refreshed in place so that
     plans and CUDA graphs that hold their addresses stay valid across weight updates."""
 
-    def __init__(self, block, device, as_stem: bool = False):
+    def __init__(self, block, device, as_stem: bool = False, allow_fold: bool = False):
         conv = block.conv
         k, s, p = conv.kernel_size, conv.stride, conv.padding
         if k[0] != k[1] or s[0] != s[1] or p[0] != p[1] or k[0] not in (1, 3) or s[0] not in (1, 2) \
@@ -56,9 +57,42 @@ class PackedConv:
         else:
             self.k_eff, self.stride_eff, self.pad_eff = self.ksize, self.stride, self.pad
             self.c_in_eff = _round_up(self.c_in, 32)
-        self.w = torch.empty(self.c_out_pad * self.k_eff * self.k_eff * self.c_in_eff, dtype=torch.bfloat16, device=device)
-        self.scale = torch.empty(self.c_out_pad, dtype=torch.float32, device=device)
-        self.bias = torch.empty(self.c_out_pad, dtype=torch.float32, device=device)
+        # Pixel-pair folding: a 32-channel NHWC pixel is a 64-byte row, which wastes half of every TMA/L2
+        # request.  Two horizontally adjacent pixels are contiguous, so (B,H,W,32) IS (B,H,W/2,64): a stride-1
+        # conv over pixel pairs with block-structured weights (half of them zero) computes the same outputs
+        # from 128-byte rows.  Tensor-core work doubles, which is irrelevant for these HBM/TMA-bound layers.
+        self.fold = bool(allow_fold and self.stride_eff == 1 and (self.c_in_eff == 32 or self.c_out == 32)
+                         and self.c_out % 32 == 0 and block.batch_norm_act)
+        self.c_in_run = self.c_in_eff * (2 if self.fold else 1)       # what the kernel sees
+        self.c_out_run = self.c_out * (2 if self.fold else 1)
+        self.c_out_pad_run = self.c_out_pad * (2 if self.fold else 1)
+        self.w = torch.empty(self.c_out_pad_run * self.k_eff * self.k_eff * self.c_in_run, dtype=torch.bfloat16,
+                             device=device)
+        self.scale = torch.empty(self.c_out_pad_run, dtype=torch.float32, device=device)
+        self.bias = torch.empty(self.c_out_pad_run, dtype=torch.float32, device=device)
+
+    def _refresh_folded(self, w, st):
+        b, dev = self.block, self.w.device
+        if self.stem:  # K index of the patch matrix is (kh*3+kw)*C + c, zero padded to 32 (yolo_input_patchify)
+            wk = torch.zeros(self.c_out, 32, 1, 1, device=dev)
+            wk[:, : 9 * self.c_in, 0, 0] = w.permute(0, 2, 3, 1).reshape(self.c_out, 9 * self.c_in)
+        else:
+            wk = w
+            if self.c_in_eff != self.c_in:
+                wk = torch.zeros(self.c_out, self.c_in_eff, self.ksize, self.ksize, device=dev)
+                wk[:, : self.c_in] = w
+        w2 = _fold_weight_pairs(wk).contiguous()
+        lib.yolo_pack_weights(ptr(w2), w2.shape[0], w2.shape[1], self.k_eff, self.c_out_pad_run, self.c_in_run,
+                              ptr(self.w), st)
+        bn = b.batch_norm
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        g, be, mu, var = f32(bn.weight), f32(bn.bias), f32(bn.running_mean), f32(bn.running_var)
+        sc = torch.empty(self.c_out_pad, dtype=torch.float32, device=dev)
+        bi = torch.empty(self.c_out_pad, dtype=torch.float32, device=dev)
+        lib.yolo_fold_bn(ptr(g), ptr(be), ptr(mu), ptr(var), None, float(bn.eps), self.c_out, self.c_out_pad, ptr(sc),
+                         ptr(bi), st)
+        self.scale.copy_(sc.repeat(2))
+        self.bias.copy_(bi.repeat(2))
 
     def tensors(self):
         b = self.block
@@ -74,6 +108,9 @@ class PackedConv:
         st = stream_ptr(self.w.device)
         f32 = lambda t: t.detach().to(device=self.w.device, dtype=torch.float32).contiguous()  # noqa: E731
         w = f32(b.conv.weight)
+        if self.fold:
+            self._refresh_folded(w, st)
+            return
         if self.stem:
             lib.yolo_pack_stem_weights(ptr(w), self.c_out, self.c_in, self.c_out_pad, ptr(self.w), st)
         else:
@@ -87,6 +124,22 @@ class PackedConv:
             cb = f32(b.conv.bias) if b.conv.bias is not None else None
             lib.yolo_fold_bn(None, None, None, None, ptr(cb), 0.0, self.c_out, self.c_out_pad, ptr(self.scale),
                              ptr(self.bias), st)
+
+
+def _fold_weight_pairs(w: torch.Tensor) -> torch.Tensor:
+    """(O, I, k, k) weights of a stride-1 'same' conv -> (2O, 2I, k, k) weights of the equivalent conv over
+    horizontally adjacent pixel PAIRS: output half oh / input half ih of pair-tap s' touch input column offset
+    2*(s' - k//2) + ih - oh, which is original tap s = offset + k//2 when that lies inside the filter."""
+    O, I, k, _ = w.shape
+    c = k // 2
+    w2 = torch.zeros(2 * O, 2 * I, k, k, dtype=w.dtype, device=w.device)
+    for oh in range(2):
+        for ih in range(2):
+            for sp in range(k):
+                s = 2 * (sp - c) + ih - oh + c
+                if 0 <= s < k:
+                    w2[oh * O:(oh + 1) * O, ih * I:(ih + 1) * I, :, sp] = w[:, :, :, s]
+    return w2
 
 
 class _Act:
@@ -236,8 +289,15 @@ class ForwardPlan:
             sroot, soff = op.src.resolve()
             droot, doff = op.dst.resolve()
             d = ConvDesc()
-            d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch = B, op.src.H, op.src.W, pc.c_in_eff, sroot.C
-            d.c_out, d.c_out_pad, d.out_pitch = pc.c_out, pc.c_out_pad, droot.C
+            f = 1
+            if pc.fold:  # run on pixel pairs: needs dense tensors (a pair must be one contiguous row)
+                ok = (op.src.W % 2 == 0 and sroot.C == op.src.C and droot.C == op.dst.C and not op.upsample
+                      and not op.dst.fp32 and (op.res is None or op.res.resolve()[0].C == op.res.C))
+                if not ok:
+                    raise YoloB200Error(f"{op.name}: pixel-pair folding needs dense, even-width tensors")
+                f = 2
+            d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch = B, op.src.H, op.src.W // f, pc.c_in_run, sroot.C * f
+            d.c_out, d.c_out_pad, d.out_pitch = pc.c_out_run, pc.c_out_pad_run, droot.C * f
             d.ksize, d.stride, d.pad = pc.k_eff, pc.stride_eff, pc.pad_eff
             d.act = ACT_CODES[pc.act]
             d.upsample2x, d.out_fp32, d.check_nan = int(op.upsample), int(op.dst.fp32), int(op.check_nan)
@@ -248,7 +308,7 @@ class ForwardPlan:
             r_ptr = None
             if op.res is not None:
                 rroot, roff = op.res.resolve()
-                d.has_residual, d.res_pitch = 1, rroot.C
+                d.has_residual, d.res_pitch = 1, rroot.C * f
                 r_ptr = C.c_void_p(rroot.buf.data_ptr() + roff * 2)
             op.plan, op.plan_ptr = make_conv_plan(d, C.c_void_p(x_ptr), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), r_ptr,
                                                   C.c_void_p(y_ptr))
@@ -318,13 +378,14 @@ class Engine:
         self.model, self.device = model, torch.device(device)
         self.block_n_hint, self.stages_hint = 0, 0
         self.impl_hint, self.cta_pair_hint = 0, 0  # 0 = library defaults (include/yolo_b200.h)
+        self.allow_fold = hasattr(model, "layers") and hasattr(model, "num_classes") and os.environ.get("YOLO_B200_NO_FOLD") != "1"
         self.packed: Dict[int, PackedConv] = {}
         blocks = [m for m in model.modules() if isinstance(m, CNNBlock)]
         first = model.layers[0] if hasattr(model, "layers") and len(model.layers) else None
         with torch.cuda.device(self.device):
             for b in blocks:
                 stem = b is first and b.conv.kernel_size == (3, 3) and b.conv.stride == (1, 1) and 9 * b.conv.in_channels <= 32
-                self.packed[id(b)] = PackedConv(b, self.device, as_stem=stem)
+                self.packed[id(b)] = PackedConv(b, self.device, as_stem=stem, allow_fold=self.allow_fold)
         self.plans: Dict[tuple, ForwardPlan] = {}
         self._sig = None
 
