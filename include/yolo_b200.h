@@ -83,6 +83,10 @@ typedef struct yolo_conv_desc {
   int32_t stages_hint;                /* tuning: 0 auto | smem pipeline depth */
   int32_t impl_hint;                  /* 0 auto (persistent v2) | 1 one-tile-per-CTA v1 | 2 v2 */
   int32_t cta_pair_hint;              /* 0 auto | 1 single CTA | 2 tcgen05 cta_group::2 pair  */
+  /* optional rectangular geometry along W (0 = same as the square fields): used by the engine's
+   * pixel-pair folding of stride-2 layers, where a 3x3/s2/p1 conv becomes 3x2, stride (2,1), pad (1|0)  */
+  int32_t ksize_w, stride_w;          /* filter width / stride along W                         */
+  int32_t pad_w_hi_plus1;             /* 0: right pad = pad; else right pad = value - 1        */
 } yolo_conv_desc;
 
 /* Size of the opaque, caller-owned plan blob (64-byte aligned storage).       */

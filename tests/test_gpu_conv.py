@@ -223,3 +223,35 @@ def test_variants_direct_store_paths(impl, pair):
     _run_case(B=1, H=26, cin=64, cout=64, k=3, stride=1, in_pitch=160, out_pitch=96, impl=impl, pair=pair,
               also_simt=False)
     _run_case(B=1, H=13, cin=64, cout=64, k=1, stride=1, act="mish", residual=True, impl=impl, pair=pair, also_simt=False)
+
+
+def test_rectangular_geometry_pair_folded_stride2():
+    """The engine runs the 32->64 3x3/s2 layer on input pixel PAIRS: a 3x2 filter, stride (2,1), left pad 1, right
+    pad 0, Cin' = 64.  Checked against the plain 3x3/s2/p1 convolution on the unfolded tensor."""
+    from yolo_for_turbines_b200._lib import ConvDesc, lib, ptr, stream_ptr
+    from yolo_for_turbines_b200.engine import make_conv_plan
+
+    g = torch.Generator().manual_seed(5)
+    B, H, W, I, O = 2, 16, 24, 32, 64
+    x = torch.randn(B, H, W, I, generator=g).bfloat16()
+    w = (torch.randn(O, I, 3, 3, generator=g) * (I * 9) ** -0.5).bfloat16().float()
+    ref = F.leaky_relu(F.conv2d(x.float().permute(0, 3, 1, 2), w, None, 2, 1), 0.1).permute(0, 2, 3, 1)
+    w2 = torch.zeros(O, 2 * I, 3, 2)
+    w2[:, I:, :, 0] = w[:, :, :, 0]
+    w2[:, :I, :, 1] = w[:, :, :, 1]
+    w2[:, I:, :, 1] = w[:, :, :, 2]
+    wd = w2.permute(0, 2, 3, 1).contiguous().bfloat16().cuda()
+    xd = x.cuda()
+    sc, bi = torch.ones(O, device="cuda"), torch.zeros(O, device="cuda")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for impl in (1, 2):
+        y = torch.zeros(B, H // 2, W // 2, O, dtype=torch.bfloat16, device="cuda")
+        d = ConvDesc()
+        d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch, d.c_out, d.c_out_pad, d.out_pitch = B, H, W // 2, 2 * I, 2 * I, O, O, O
+        d.ksize, d.stride, d.pad, d.act, d.impl_hint = 3, 2, 1, 1, impl
+        d.ksize_w, d.stride_w, d.pad_w_hi_plus1 = 2, 1, 1
+        plan = make_conv_plan(d, ptr(xd), ptr(wd), ptr(sc), ptr(bi), None, ptr(y))
+        lib.yolo_conv_fwd(plan[1], ptr(st), stream_ptr())
+        torch.cuda.synchronize()
+        err = (y.float().cpu() - ref).abs()
+        assert float(err.max()) <= REL * max(1.0, float(ref.abs().max())), (impl, float(err.max()))

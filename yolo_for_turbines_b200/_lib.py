@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "h_in", "w_in", "c_in", "in_pitch", "c_out", "c_out_pad", "out_pitch", "ksize", "stride", "pad",
         "act", "has_residual", "res_pitch", "upsample2x", "out_fp32", "check_nan", "a_mode", "block_n_hint",
-        "stages_hint", "impl_hint", "cta_pair_hint")]
+        "stages_hint", "impl_hint", "cta_pair_hint", "ksize_w", "stride_w", "pad_w_hi_plus1")]
 
 
 _P, _I, _F, _D, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t

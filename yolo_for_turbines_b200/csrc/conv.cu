@@ -83,7 +83,7 @@ k_conv_tcgen05(const __grid_constant__ ConvKParams p) {
         img = m0 / hw;
         const int rem = m0 - img * hw;
         const int po = rem / p.w_out, qo = rem - po * p.w_out;
-        cw = qo * p.stride - p.pad;  // top-left tap of the first output pixel, input coords
+        cw = qo * p.stride_w - p.pad;  // top-left tap of the first output pixel, input coords
         ch = po * p.stride - p.pad;
       }
       for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -94,7 +94,7 @@ k_conv_tcgen05(const __grid_constant__ ConvKParams p) {
         const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
         const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
         if (p.a_im2col) {
-          const int r = tap / p.ksize, t = tap - r * p.ksize;
+          const int r = tap / p.ksize_w, t = tap - r * p.ksize_w;
           tma_load_im2col_4d(&p.tmA, full_bar(s), sa, cc * KC, cw, ch, img, (uint16_t)t, (uint16_t)r);
         } else {
           tma_load_2d(&p.tmA, full_bar(s), sa, cc * KC, m0);
@@ -226,14 +226,15 @@ __global__ void k_conv_simt(const yolo_conv_desc d, const __nv_bfloat16* __restr
   const int rem = int(m - (long long)img * h_out * w_out);
   const int po = rem / w_out, qo = rem - po * w_out;
   float acc = 0.f;
+  const int kw = d.ksize_w > 0 ? d.ksize_w : d.ksize, sw = d.stride_w > 0 ? d.stride_w : d.stride;
   for (int r = 0; r < d.ksize; ++r) {
     const int hi = po * d.stride - d.pad + r;
     if (hi < 0 || hi >= d.h_in) continue;
-    for (int t = 0; t < d.ksize; ++t) {
-      const int wi = qo * d.stride - d.pad + t;
+    for (int t = 0; t < kw; ++t) {
+      const int wi = qo * sw - d.pad + t;
       if (wi < 0 || wi >= d.w_in) continue;
       const __nv_bfloat16* xp = x + ((size_t(img) * d.h_in + hi) * d.w_in + wi) * d.in_pitch;
-      const __nv_bfloat16* wp = w + (size_t(n) * d.ksize * d.ksize + r * d.ksize + t) * d.c_in;
+      const __nv_bfloat16* wp = w + (size_t(n) * d.ksize * kw + r * kw + t) * d.c_in;
       for (int c = 0; c < d.c_in; ++c) acc += __bfloat162float(xp[c]) * __bfloat162float(wp[c]);
     }
   }
@@ -277,12 +278,14 @@ int validate_desc(const yolo_conv_desc* d, int* h_out, int* w_out) {
   YB_REQUIRE((d->ksize == 1 && d->pad == 0) || (d->ksize == 3 && d->pad == 1),
              "conv: only 1x1/pad0 and 3x3/pad1 (model.py:201)");
   YB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
+  YB_REQUIRE(yb_kw(d) >= 1 && yb_kw(d) <= 3 && (yb_sw(d) == 1 || yb_sw(d) == 2) && yb_pad_hi(d) >= 0 && yb_pad_hi(d) <= 1,
+             "conv: bad rectangular geometry (ksize_w %d stride_w %d)", d->ksize_w, d->stride_w);
   YB_REQUIRE(d->act >= YB_ACT_NONE && d->act <= YB_ACT_MISH, "conv: bad activation code %d", d->act);
   YB_REQUIRE(!d->has_residual || (d->res_pitch >= d->c_out_pad && d->res_pitch % 8 == 0),
              "conv: bad res_pitch");
   YB_REQUIRE(!(d->has_residual && d->out_fp32), "conv: residual with fp32 output unsupported");
   *h_out = (d->h_in + 2 * d->pad - d->ksize) / d->stride + 1;
-  *w_out = (d->w_in + 2 * d->pad - d->ksize) / d->stride + 1;
+  *w_out = (d->w_in + d->pad + yb_pad_hi(d) - yb_kw(d)) / yb_sw(d) + 1;
   return YB_OK;
 }
 
@@ -329,7 +332,7 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
   if (bn == 0) bn = d->c_out_pad % 128 == 0 ? 128 : (d->c_out_pad % 64 == 0 ? 64 : 32);
   YB_REQUIRE((bn == 32 || bn == 64 || bn == 128 || bn == 256) && d->c_out_pad % bn == 0,
              "conv plan: block_n %d does not tile c_out_pad %d", bn, d->c_out_pad);
-  const int taps = d->ksize * d->ksize;
+  const int taps = d->ksize * yb_kw(d);
   const int cchunks = d->c_in / kc;
   const int num_kb = taps * cchunks;
   const int im2col = (d->a_mode == 2) || (d->a_mode == 0 && !(d->ksize == 1 && d->stride == 1));
@@ -355,9 +358,9 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
     cuuint64_t dims[4] = {(cuuint64_t)d->c_in, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->w_in * d->in_pitch * 2,
                              (cuuint64_t)d->h_in * d->w_in * d->in_pitch * 2};
-    int lower[2] = {-d->pad, -d->pad};
-    int upper[2] = {d->pad - (d->ksize - 1), d->pad - (d->ksize - 1)};
-    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    int lower[2] = {-d->pad, -d->pad};  // {W, H}
+    int upper[2] = {yb_pad_hi(d) - (yb_kw(d) - 1), d->pad - (d->ksize - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)yb_sw(d), (cuuint32_t)d->stride, 1};
     cr = encIm2col(&pl->kp.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides,
                    lower, upper, (cuuint32_t)kc, (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -399,7 +402,7 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
   kp.M = (int)M; kp.h_out = h_out; kp.w_out = w_out;
   kp.out_pitch = d->out_pitch; kp.res_pitch = d->res_pitch;
   kp.num_kb = num_kb; kp.cchunks = cchunks; kp.stages = stages; kp.tiles_n = d->c_out_pad / bn;
-  kp.ksize = d->ksize; kp.stride = d->stride; kp.pad = d->pad;
+  kp.ksize = d->ksize; kp.stride = d->stride; kp.pad = d->pad; kp.ksize_w = yb_kw(d); kp.stride_w = yb_sw(d);
   kp.act = d->act; kp.has_residual = d->has_residual; kp.upsample2x = d->upsample2x;
   kp.out_fp32 = d->out_fp32; kp.check_nan = d->check_nan; kp.a_im2col = im2col;
   pl->block_n = bn; pl->kc = kc;

@@ -143,7 +143,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         img = m0 / hw;
         const int rem = m0 - img * hw;
         const int po = rem / p.w_out, qo = rem - po * p.w_out;
-        cw = qo * p.stride - p.pad;
+        cw = qo * p.stride_w - p.pad;
         ch = po * p.stride - p.pad;
       }
       int tr = 0, tq = 0, cc = 0;  // filter tap (row, col) and channel chunk of the current k-block
@@ -163,7 +163,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           }
         }
         __syncwarp();
-        if (++cc == p.cchunks) { cc = 0; if (++tq == p.ksize) { tq = 0; ++tr; } }
+        if (++cc == p.cchunks) { cc = 0; if (++tq == p.ksize_w) { tq = 0; ++tr; } }
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -393,7 +393,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   const long long M = (long long)d->batch * h_out * w_out;
   const int tiles_m = (int)((M + BLOCK_M * ncta - 1) / (BLOCK_M * ncta));
   const int tiles_n = d->c_out_pad / bn;
-  const int taps = d->ksize * d->ksize;
+  const int taps = d->ksize * yb_kw(d);
   const int num_kb = taps * (d->c_in / kc);
   int stages = d->stages_hint;
   if (stages <= 0) {
@@ -449,7 +449,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   kp.out_pitch = d->out_pitch; kp.res_pitch = d->res_pitch;
   kp.num_kb = num_kb; kp.cchunks = d->c_in / kc; kp.stages = stages;
   kp.tiles_n = tiles_n; kp.num_tiles = tiles_m * tiles_n;
-  kp.ksize = d->ksize; kp.stride = d->stride; kp.pad = d->pad;
+  kp.ksize = d->ksize; kp.stride = d->stride; kp.pad = d->pad; kp.ksize_w = yb_kw(d); kp.stride_w = yb_sw(d);
   kp.act = d->act; kp.has_residual = d->has_residual; kp.upsample2x = d->upsample2x;
   kp.out_fp32 = d->out_fp32; kp.check_nan = d->check_nan; kp.a_im2col = im2col;
 

@@ -7,6 +7,10 @@
 constexpr int BLOCK_M = 128;
 constexpr uint32_t PLAN_MAGIC = 0x59423230u;  // "YB20"
 
+inline int yb_kw(const yolo_conv_desc* d) { return d->ksize_w > 0 ? d->ksize_w : d->ksize; }
+inline int yb_sw(const yolo_conv_desc* d) { return d->stride_w > 0 ? d->stride_w : d->stride; }
+inline int yb_pad_hi(const yolo_conv_desc* d) { return d->pad_w_hi_plus1 > 0 ? d->pad_w_hi_plus1 - 1 : d->pad; }
+
 // v1: one CTA per output tile (conv.cu)
 struct ConvKParams {
   alignas(64) CUtensorMap tmA;
@@ -20,6 +24,7 @@ struct ConvKParams {
   int out_pitch, res_pitch;
   int num_kb, cchunks, stages, tiles_n;
   int ksize, stride, pad;
+  int ksize_w, stride_w;
   int act, has_residual, upsample2x, out_fp32, check_nan, a_im2col;
 };
 
@@ -38,6 +43,7 @@ struct ConvKParams2 {
   int out_pitch, res_pitch;
   int num_kb, cchunks, stages, tiles_n, num_tiles;  // tiles of (128 * NCTA) x BLOCK_N
   int ksize, stride, pad;
+  int ksize_w, stride_w;
   int act, has_residual, upsample2x, out_fp32, check_nan, a_im2col;
 };
 

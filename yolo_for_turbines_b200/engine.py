@@ -63,10 +63,16 @@ class PackedConv:
         # from 128-byte rows.  Tensor-core work doubles, which is irrelevant for these HBM/TMA-bound layers.
         self.fold = bool(allow_fold and self.stride_eff == 1 and (self.c_in_eff == 32 or self.c_out == 32)
                          and self.c_out % 32 == 0 and block.batch_norm_act)
-        self.c_in_run = self.c_in_eff * (2 if self.fold else 1)       # what the kernel sees
+        # Stride-2 variant (the 32->64 down-sampling conv): pairs on the INPUT side only.  Output column q reads
+        # input columns 2q-1, 2q, 2q+1 = second half of pair q-1 and both halves of pair q: a 3x2 filter over
+        # pairs with stride (2, 1) and padding one pair on the left, none on the right.
+        self.fold_s2 = bool(allow_fold and not self.fold and self.ksize == 3 and self.stride == 2
+                            and self.c_in_eff == 32 and block.batch_norm_act and not self.stem)
+        self.c_in_run = self.c_in_eff * (2 if (self.fold or self.fold_s2) else 1)       # what the kernel sees
         self.c_out_run = self.c_out * (2 if self.fold else 1)
         self.c_out_pad_run = self.c_out_pad * (2 if self.fold else 1)
-        self.w = torch.empty(self.c_out_pad_run * self.k_eff * self.k_eff * self.c_in_run, dtype=torch.bfloat16,
+        self.kw_run = 2 if self.fold_s2 else self.k_eff
+        self.w = torch.empty(self.c_out_pad_run * self.k_eff * self.kw_run * self.c_in_run, dtype=torch.bfloat16,
                              device=device)
         self.scale = torch.empty(self.c_out_pad_run, dtype=torch.float32, device=device)
         self.bias = torch.empty(self.c_out_pad_run, dtype=torch.float32, device=device)
@@ -110,6 +116,20 @@ class PackedConv:
         w = f32(b.conv.weight)
         if self.fold:
             self._refresh_folded(w, st)
+            return
+        if self.fold_s2:
+            O, I = self.c_out, self.c_in_eff
+            wk = torch.zeros(O, I, 3, 3, device=self.w.device)
+            wk[:, : self.c_in] = w
+            w2 = torch.zeros(self.c_out_pad, 2 * I, 3, 2, device=self.w.device)
+            w2[:O, I:, :, 0] = wk[:, :, :, 0]   # pair q-1, second half  <- tap s = 0 (column 2q-1)
+            w2[:O, :I, :, 1] = wk[:, :, :, 1]   # pair q,   first half   <- tap s = 1 (column 2q)
+            w2[:O, I:, :, 1] = wk[:, :, :, 2]   # pair q,   second half  <- tap s = 2 (column 2q+1)
+            self.w.copy_(w2.permute(0, 2, 3, 1).reshape(-1).to(torch.bfloat16))  # [Cout][kh][kw][Cin']
+            bn = b.batch_norm
+            g, be, mu, var = f32(bn.weight), f32(bn.bias), f32(bn.running_mean), f32(bn.running_var)
+            lib.yolo_fold_bn(ptr(g), ptr(be), ptr(mu), ptr(var), None, float(bn.eps), self.c_out, self.c_out_pad,
+                             ptr(self.scale), ptr(self.bias), st)
             return
         if self.stem:
             lib.yolo_pack_stem_weights(ptr(w), self.c_out, self.c_in, self.c_out_pad, ptr(self.w), st)
@@ -296,7 +316,13 @@ class ForwardPlan:
                 if not ok:
                     raise YoloB200Error(f"{op.name}: pixel-pair folding needs dense, even-width tensors")
                 f = 2
-            d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch = B, op.src.H, op.src.W // f, pc.c_in_run, sroot.C * f
+            fi = f
+            if pc.fold_s2:
+                if op.src.W % 2 or sroot.C != op.src.C:
+                    raise YoloB200Error(f"{op.name}: pixel-pair folding needs a dense, even-width input")
+                fi = 2
+                d.ksize_w, d.stride_w, d.pad_w_hi_plus1 = 2, 1, 1  # 3x2 filter, stride (2,1), no right padding
+            d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch = B, op.src.H, op.src.W // fi, pc.c_in_run, sroot.C * fi
             d.c_out, d.c_out_pad, d.out_pitch = pc.c_out_run, pc.c_out_pad_run, droot.C * f
             d.ksize, d.stride, d.pad = pc.k_eff, pc.stride_eff, pc.pad_eff
             d.act = ACT_CODES[pc.act]
