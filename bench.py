@@ -111,6 +111,10 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    try:  # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     torch.manual_seed(0)
     m = default_init_state_dict(args.classes)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
@@ -174,7 +178,19 @@ def main():
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created; stdout must carry exactly
+        # one JSON line, so fd 1 points at stderr until the first collective has run.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     from yolo_for_turbines_b200 import config as cfg
     from yolo_for_turbines_b200.model import YOLOv3
@@ -206,14 +222,16 @@ def main():
         return float(t.item())
 
     # ---- device-resident throughput ---------------------------------------------------------
-    for i in range(args.warmup):
+    sampler = ClockSampler(local)
+    sampler.start()  # samples through warm-up, the timed loops and the e2e loop: all under load
+    for i in range(max(args.warmup, 3)):
         res, plan = det(xs[i % nbuf])
     plan.check_status()
     n_cand = res.boxes.shape[0] // B
     kept_total = int(res.keep_off[-1].item())
-    sampler = ClockSampler(local)
+    for i in range(40):  # a second of steady load so that clocks / power state are the sustained ones
+        res, plan = det(xs[i % nbuf])
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
