@@ -186,7 +186,8 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
   __shared__ float4 s_cbox[32];
   __shared__ float s_carea[32];
   __shared__ uint32_t s_row[32], s_binx[32], s_biny[32];
-  __shared__ uint32_t s_alive, s_cgen, s_kept;
+  __shared__ uint32_t s_alive, s_cgen, s_kept, s_win[4];
+  __shared__ int s_cpos[32];
   __shared__ int s_end;
   const bool thr_pos = thr > 0.f;
   const int n = *n_dev, nseg = *nseg_dev;
@@ -229,10 +230,120 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
         }
       }
     }
+    if (regpath) {
+      // ---- register path: chunks are the next 32 boxes that are still ALIVE (dead boxes are skipped, which
+      // cuts the number of serial rounds from m/32 to ~(#survivors)/32), taken from a 128-position window.
+      int f = 0;  // frontier: first position (relative to s0) not yet consumed
+      while (f < m) {
+        const int wb = f >> 5;
+        // every warp publishes the blocks it owns that fall into the window
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const int blk = wb + d;
+          if ((blk % NMS_WARPS) == warp) {
+            uint32_t al = 0;
+            if (blk * 32 < m) al = __ballot_sync(0xffffffffu, ((supp >> (blk / NMS_WARPS)) & 1u) == 0);
+            if (d == 0) al &= ~((1u << (f & 31)) - 1u);
+            if (lane == 0) s_win[d] = al;
+          }
+        }
+        __syncthreads();
+        // (0b) every warp selects the members redundantly: lane l takes the (l+1)-th alive position
+        const uint32_t w0 = s_win[0], w1 = s_win[1], w2 = s_win[2], w3 = s_win[3];
+        const int c0n = __popc(w0), c1n = __popc(w1), c2n = __popc(w2), c3n = __popc(w3);
+        const int total = c0n + c1n + c2n + c3n;
+        if (total == 0) {  // uniform
+          f = (wb + 4) << 5;
+          __syncthreads();  // s_win is rewritten by the next round
+          continue;
+        }
+        const int nmem = total < 32 ? total : 32;
+        int mypos = -1;
+        if (lane < nmem) {
+          int r = lane, d = 0;
+          uint32_t wsel = w0;
+          if (r >= c0n) { r -= c0n; d = 1; wsel = w1;
+            if (r >= c1n) { r -= c1n; d = 2; wsel = w2;
+              if (r >= c2n) { r -= c2n; d = 3; wsel = w3; } } }
+          mypos = ((wb + d) << 5) + (int)__fns(wsel, 0, r + 1);
+        }
+        const int lastpos = __shfl_sync(0xffffffffu, mypos, nmem - 1);
+        const int f_new = (total <= 32) ? ((wb + 4) << 5) : (lastpos + 1);
+        // (0c) member boxes -> shared memory
+        if (warp == 0) {
+          const bool valid = lane < nmem;
+          const int qi = s0 + (valid ? mypos : 0);
+          s_cbox[lane] = valid ? cbox[qi] : make_float4(0.f, 0.f, 0.f, 0.f);
+          s_carea[lane] = valid ? area[qi] : 0.f;
+          const int st = valid ? suppressed[qi] : 0;
+          const uint32_t g = __ballot_sync(0xffffffffu, valid && (!thr_pos || (st & 2)));
+          if (lane == 0) s_cgen = g;
+          s_cpos[lane] = valid ? qi : -1;
+        }
+        __syncthreads();
+        // (a) pair matrix (rows warp and warp+16) and spatial bin masks (bins warp and warp+16)
+        {
+          const float4 bj = s_cbox[lane];
+          const float aj = s_carea[lane];
+          const uint32_t cgen = s_cgen;
+          const bool vj = lane < nmem;
+          const uint32_t pb = nms_pack_bins(bj);
+          const int xl = pb & 31, xh = (pb >> 8) & 31, yl = (pb >> 16) & 31, yh = (pb >> 24) & 31;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int i = warp + h * NMS_WARPS;
+            bool sup = false;
+            if (lane > i && vj)
+              sup = nms_pair(s_cbox[i], s_carea[i], bj, aj, ((cgen >> i) | (cgen >> lane)) & 1u, thr, thr_pos);
+            const uint32_t row = __ballot_sync(0xffffffffu, sup);
+            const uint32_t mxb = __ballot_sync(0xffffffffu, vj && xl <= i && i <= xh);
+            const uint32_t myb = __ballot_sync(0xffffffffu, vj && yl <= i && i <= yh);
+            if (lane == 0) { s_row[i] = row; s_binx[i] = mxb; s_biny[i] = myb; }
+          }
+        }
+        __syncthreads();
+        // (b) warp 0 resolves the chunk serially; rows are read up front so the dependent chain is pure ALU
+        if (warp == 0) {
+          uint32_t alive = nmem == 32 ? 0xffffffffu : ((1u << nmem) - 1u);
+          uint32_t kept = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t ri = s_row[i];
+            if ((alive >> i) & 1u) { kept |= 1u << i; alive &= ~ri; }
+          }
+          if ((kept >> lane) & 1u) keep[val2[s_cpos[lane]]] = 1;  // keep[] is zero-initialised
+          if (lane == 0) s_kept = kept;
+        }
+        __syncthreads();
+        // (c) the chunk's survivors knock out the later boxes this thread owns
+        const uint32_t kept = s_kept;
+        const uint32_t kgen = kept & s_cgen;
+#pragma unroll
+        for (int j = 0; j < NMS_QPT; ++j) {
+          if (j * NMS_THREADS + tid >= f_new && !((supp >> j) & 1u)) {
+            const bool qgen = (gen >> j) & 1u;
+            uint32_t cand = qgen ? kept : ((nms_candidates(bins[j], s_binx, s_biny) & kept) | kgen);
+            if (cand) {
+              const float al = area[s0 + j * NMS_THREADS + tid];
+              while (cand) {
+                const int t = __ffs(cand) - 1;
+                cand &= cand - 1;
+                if (nms_pair(s_cbox[t], s_carea[t], bx[j], al, qgen || ((kgen >> t) & 1u), thr, thr_pos)) {
+                  supp |= 1u << j;
+                  break;
+                }
+              }
+            }
+          }
+        }
+        f = f_new;
+      }
+      __syncthreads();
+      continue;
+    }
+    // ---- long segments (> 8192 boxes): consecutive 32-box chunks, state in global memory
     for (int ci = 0; ci * 32 < m; ++ci) {
       const int c0 = s0 + ci * 32;
-      const int own_warp = ci % NMS_WARPS, own_slot = ci / NMS_WARPS;
-      // (0) chunk boxes -> shared memory; alive / "general" bits
       if (warp == 0) {
         const int qi = c0 + lane;
         const bool valid = qi < s1;
@@ -241,14 +352,9 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
         const int st = valid ? suppressed[qi] : 1;
         const uint32_t g = __ballot_sync(0xffffffffu, valid && (!thr_pos || (st & 2)));
         const uint32_t al = __ballot_sync(0xffffffffu, (st & 1) == 0);
-        if (lane == 0) { s_cgen = g; if (!regpath) s_alive = al; }
-      }
-      if (regpath && warp == own_warp) {
-        const uint32_t al = __ballot_sync(0xffffffffu, ((supp >> own_slot) & 1u) == 0);
-        if (lane == 0) s_alive = al;
+        if (lane == 0) { s_cgen = g; s_alive = al; }
       }
       __syncthreads();
-      // (a) pair matrix (rows warp and warp+16) and spatial bin masks (bins warp and warp+16)
       {
         const float4 bj = s_cbox[lane];
         const float aj = s_carea[lane];
@@ -269,62 +375,37 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
         }
       }
       __syncthreads();
-      // (b) warp 0 resolves the chunk serially (utils.py:170-187 restricted to these 32 boxes)
       if (warp == 0) {
         const int qi = c0 + lane;
         const bool valid = qi < s1;
-        const uint32_t row = s_row[lane];
         uint32_t alive = s_alive & __ballot_sync(0xffffffffu, valid);
         uint32_t kept = 0;
-#pragma unroll 8
+#pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const uint32_t ri = __shfl_sync(0xffffffffu, row, i);
+          const uint32_t ri = s_row[i];
           if ((alive >> i) & 1u) { kept |= 1u << i; alive &= ~ri; }
         }
-        if (valid) keep[val2[qi]] = (kept >> lane) & 1u;
+        if (valid && ((kept >> lane) & 1u)) keep[val2[qi]] = 1;
         if (lane == 0) s_kept = kept;
       }
       __syncthreads();
-      // (c) the chunk's survivors knock out later boxes of the segment
       const uint32_t kept = s_kept;
       if (kept != 0) {
-        const uint32_t kgen = kept & s_cgen;  // survivors that need the general path: always candidates
-        if (regpath) {
-#pragma unroll
-          for (int j = 0; j < NMS_QPT; ++j) {
-            const bool later = (j > own_slot) || (j == own_slot && warp > own_warp);
-            if (later && !((supp >> j) & 1u)) {
-              const bool qgen = (gen >> j) & 1u;
-              uint32_t cand = qgen ? kept : ((nms_candidates(bins[j], s_binx, s_biny) & kept) | kgen);
-              if (cand) {
-                const float al = area[s0 + j * NMS_THREADS + tid];
-                while (cand) {
-                  const int t = __ffs(cand) - 1;
-                  cand &= cand - 1;
-                  if (nms_pair(s_cbox[t], s_carea[t], bx[j], al, qgen || ((kgen >> t) & 1u), thr, thr_pos)) {
-                    supp |= 1u << j;
-                    break;
-                  }
-                }
-              }
-            }
-          }
-        } else {
-          for (int q = c0 + 32 + tid; q < s1; q += NMS_THREADS) {
-            const int state = suppressed[q];
-            if (state & 1) continue;
-            const float4 b = cbox[q];
-            const bool qgen = !thr_pos || (state & 2);
-            uint32_t cand = qgen ? kept : ((nms_candidates(nms_pack_bins(b), s_binx, s_biny) & kept) | kgen);
-            if (!cand) continue;
-            const float al = area[q];
-            while (cand) {
-              const int t = __ffs(cand) - 1;
-              cand &= cand - 1;
-              if (nms_pair(s_cbox[t], s_carea[t], b, al, qgen || ((kgen >> t) & 1u), thr, thr_pos)) {
-                suppressed[q] = state | 1;
-                break;
-              }
+        const uint32_t kgen = kept & s_cgen;
+        for (int q = c0 + 32 + tid; q < s1; q += NMS_THREADS) {
+          const int state = suppressed[q];
+          if (state & 1) continue;
+          const float4 b = cbox[q];
+          const bool qgen = !thr_pos || (state & 2);
+          uint32_t cand = qgen ? kept : ((nms_candidates(nms_pack_bins(b), s_binx, s_biny) & kept) | kgen);
+          if (!cand) continue;
+          const float al = area[q];
+          while (cand) {
+            const int t = __ffs(cand) - 1;
+            cand &= cand - 1;
+            if (nms_pair(s_cbox[t], s_carea[t], b, al, qgen || ((kgen >> t) & 1u), thr, thr_pos)) {
+              suppressed[q] = state | 1;
+              break;
             }
           }
         }
@@ -458,6 +539,7 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   int32_t* n_valid = w.scalars;
   int32_t* nseg = w.scalars + 1;
   YB_CHECK_CUDA(cudaMemsetAsync(w.scalars, 0, sizeof(int32_t) * 8, stream));
+  YB_CHECK_CUDA(cudaMemsetAsync(w.keep, 0, size_t(total), stream));  // k_nms_segments only writes the 1s
 
   // K4: ordered threshold compaction -> (key, row index) pairs
   k_thr_count<<<w.ctiles, COMPACT_THREADS, 0, stream>>>(boxes, total, obj_thr, w.tile_cnt);
