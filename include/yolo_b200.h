@@ -156,8 +156,11 @@ int yolo_decode(const float* head, const int64_t* strides5_host, int batch, int 
  * in the reference's order (descending score, ties by original position).
  * ------------------------------------------------------------------------- */
 size_t yolo_nms_workspace_bytes(int total, int batch);
+/* class_bits: 0 = labels are arbitrary floats (grouped by float equality, NaN != NaN, as utils.py:178);
+ * 8 | 16 = the caller guarantees integer labels in [0, 2^class_bits) (true for cells_to_boxes output), which
+ * shortens the grouping sort from 4 radix passes to 1 | 2; violations are counted in workspace int32 #2.    */
 int yolo_nms(const float* boxes, const int32_t* img_offsets, int batch, int total,
-             float iou_thr, double obj_thr, int box_format, int32_t* keep_idx,
+             float iou_thr, double obj_thr, int box_format, int class_bits, int32_t* keep_idx,
              int32_t* keep_off, void* workspace, size_t workspace_bytes, yb_stream_t stream);
 
 /* Element-wise IoU -- replaces utils.py:38-84 calc_iou (n1 or n2 may be 1 to

@@ -54,7 +54,7 @@ SIGNATURES = {
     "yolo_input_patchify": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "yolo_decode": (_I, [_P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _I, _I, _P, _I, _I, _P]),
     "yolo_nms_workspace_bytes": (_SZ, [_I, _I]),
-    "yolo_nms": (_I, [_P, _P, _I, _I, _F, _D, _I, _P, _P, _P, _SZ, _P]),
+    "yolo_nms": (_I, [_P, _P, _I, _I, _F, _D, _I, _I, _P, _P, _P, _SZ, _P]),
     "yolo_iou": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
     "yolo_map_match": (_I, [_P, _I, _P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P]),
     "yolo_sort_workspace_bytes": (_SZ, [_I]),

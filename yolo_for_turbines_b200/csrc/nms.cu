@@ -74,13 +74,18 @@ k_thr_write(const float* __restrict__ boxes, const int32_t* __restrict__ img_off
 __global__ void k_class_keys(const float* __restrict__ boxes, const uint64_t* __restrict__ key1,
                              const int32_t* __restrict__ val1, const int32_t* __restrict__ n_dev,
                              uint64_t* __restrict__ key2, int32_t* __restrict__ val2,
-                             int32_t* __restrict__ idx1) {
+                             int32_t* __restrict__ idx1, int class_bits, int32_t* __restrict__ violations) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= *n_dev) return;
   const int idx = val1[p];
   idx1[p] = idx;
   float cls = __fadd_rn(boxes[size_t(idx) * 6 + 5], 0.0f);  // -0.0 == 0.0 in utils.py:178
   uint32_t cb = (cls != cls) ? 0x7fc00000u : __float_as_uint(cls);
+  if (class_bits > 0) {  // caller promises integer labels in [0, 2^class_bits): a 1-pass grouping key
+    const float lim = float(1 << class_bits);
+    if (cls >= 0.f && cls < lim && cls == floorf(cls)) cb = uint32_t(cls);
+    else { cb = 0; atomicAdd(violations, 1); }
+  }
   key2[p] = (key1[p] & 0xffffffff00000000ull) | cb;
   val2[p] = p;
 }
@@ -182,7 +187,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
                const uint64_t* __restrict__ key2, const int32_t* __restrict__ val2,
                const int32_t* __restrict__ seg_starts, const int32_t* __restrict__ nseg_dev,
                const int32_t* __restrict__ n_dev, float thr, uint8_t* __restrict__ suppressed,
-               uint8_t* __restrict__ keep) {
+               uint8_t* __restrict__ keep, const bool int_classes) {
   __shared__ float4 s_cbox[32];
   __shared__ float s_carea[32];
   __shared__ uint32_t s_row[32], s_binx[32], s_biny[32];
@@ -205,7 +210,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
     }
     __syncthreads();
     const int s1 = s_end;
-    if (uint32_t(k) == 0x7fc00000u) {  // NaN class: != is always true (utils.py:178) => all kept
+    if (!int_classes && uint32_t(k) == 0x7fc00000u) {  // NaN class: != is always true (utils.py:178) => all kept
       for (int q = s0 + tid; q < s1; q += NMS_THREADS) keep[val2[q]] = 1;
       __syncthreads();
       continue;
@@ -518,13 +523,14 @@ extern "C" size_t yolo_nms_workspace_bytes(int total, int batch) {
 }
 
 extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batch, int total,
-                        float iou_thr, double obj_thr, int box_format, int32_t* keep_idx,
+                        float iou_thr, double obj_thr, int box_format, int class_bits, int32_t* keep_idx,
                         int32_t* keep_off, void* workspace, size_t workspace_bytes,
                         yb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   YB_REQUIRE(batch >= 1 && total >= 0, "yolo_nms: batch must be >= 1 and total >= 0");
   YB_REQUIRE(box_format == YB_BOX_CENTER || box_format == YB_BOX_CORNERS, "yolo_nms: bad box_format");
   YB_REQUIRE(keep_off != nullptr, "yolo_nms: keep_off is null");
+  YB_REQUIRE(class_bits == 0 || class_bits == 8 || class_bits == 16, "yolo_nms: class_bits must be 0, 8 or 16");
   if (workspace_bytes < yolo_nms_workspace_bytes(total, batch)) {
     yb_set_error("yolo_nms: workspace too small (%zu < %zu)", workspace_bytes,
                  yolo_nms_workspace_bytes(total, batch));
@@ -559,9 +565,10 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   rc = radix_sort_pairs(w.key1, w.val1, n_valid, total, 32, img_hi, w.sb, stream);
   if (rc) return rc;
   const int eb = 256, eg = yb_cdiv(total, eb);
-  k_class_keys<<<eg, eb, 0, stream>>>(boxes, w.key1, w.val1, n_valid, w.key2, w.val2, w.idx1);
+  k_class_keys<<<eg, eb, 0, stream>>>(boxes, w.key1, w.val1, n_valid, w.key2, w.val2, w.idx1, class_bits,
+                                      w.scalars + 2);
   YB_CHECK_LAUNCH();
-  rc = radix_sort_pairs(w.key2, w.val2, n_valid, total, 0, 32, w.sb, stream);
+  rc = radix_sort_pairs(w.key2, w.val2, n_valid, total, 0, class_bits > 0 ? class_bits : 32, w.sb, stream);
   if (rc) return rc;
   rc = radix_sort_pairs(w.key2, w.val2, n_valid, total, 32, img_hi, w.sb, stream);
   if (rc) return rc;
@@ -576,7 +583,7 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   int grid = sms * 3;
   if (grid > total) grid = total;
   k_nms_segments<<<grid, NMS_THREADS, 0, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts,
-                                                   nseg, n_valid, iou_thr, w.suppressed, w.keep);
+                                                   nseg, n_valid, iou_thr, w.suppressed, w.keep, class_bits > 0);
   YB_CHECK_LAUNCH();
 
   // survivors, in the reference's order, + per-image offsets

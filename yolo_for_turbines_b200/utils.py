@@ -158,7 +158,8 @@ class NmsWorkspace:
 
 
 def batched_nms(boxes: torch.Tensor, img_offsets: torch.Tensor, iou_threshold: float, obj_threshold: float,
-                box_format: str = "corners", workspace: Optional[NmsWorkspace] = None) -> NmsResult:
+                box_format: str = "corners", workspace: Optional[NmsWorkspace] = None,
+                class_bits: int = 0) -> NmsResult:
     """Class-aware greedy NMS of a whole batch in one pipeline (K4 compaction, K5 sort, K6 NMS).
     boxes [total,6] fp32 CUDA rows [x,y,w,h,score,cls]; img_offsets [B+1] int32 CUDA."""
     if not boxes.is_cuda:
@@ -172,7 +173,7 @@ def batched_nms(boxes: torch.Tensor, img_offsets: torch.Tensor, iou_threshold: f
     thr32 = float(torch.tensor(iou_threshold, dtype=torch.float32))  # utils.py:179 compares in fp32
     with torch.cuda.device(boxes.device):
         lib.yolo_nms(ptr(boxes), ptr(img_offsets), B, total, thr32, float(obj_threshold), _fmt(box_format),
-                     ptr(ws.keep_idx), ptr(ws.keep_off), ptr(ws.buf), ws.nbytes, stream_ptr(boxes.device))
+                     int(class_bits), ptr(ws.keep_idx), ptr(ws.keep_off), ptr(ws.buf), ws.nbytes, stream_ptr(boxes.device))
     return NmsResult(boxes, ws.keep_idx, ws.keep_off)
 
 
@@ -301,8 +302,10 @@ class Detector:
             anc = _scaled_anchors(self.anchors, i, s)
             decode_boxes(h, anc, s, True, out=st["cand"], out_offset=off)
             off += 3 * s * s
+        # classes come from the decode's argmax: integers < num_classes, so the grouping sort needs one pass
+        nc = max(h.shape[-1] - 5 for h in heads)
         res = batched_nms(st["cand"].view(-1, 6), st["off"], self.iou_threshold, self.obj_threshold, self.box_format,
-                          workspace=st["ws"])
+                          workspace=st["ws"], class_bits=8 if nc <= 256 else (16 if nc <= 65536 else 0))
         return res, plan
 
 
