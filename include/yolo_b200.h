@@ -181,6 +181,13 @@ int yolo_map_match(const float* dets, int D, const float* gts, int G, const int3
                    int box_format, float* tp, float* best_iou, int32_t* best_gt,
                    int32_t* gt_claim /* [G] scratch */, yb_stream_t stream);
 
+/* Accuracy reductions -- replaces the per-scale body of utils.py:356-371 (check_model_accuracy).
+ * head (B,3,S,S,5+nc) / target (B,3,S,S,6) fp32 with element strides; counts6 (device u64, accumulated):
+ * correct_class, total_class, correct_obj, total_obj, correct_noobj, total_noobj.                          */
+int yolo_accuracy_counts(const float* head, const int64_t* hstrides5_host, const float* target,
+                         const int64_t* tstrides5_host, int batch, int S, int nc, float obj_thr,
+                         unsigned long long* counts6, yb_stream_t stream);
+
 /* Stable LSD radix sort of (u64 key, i32 value) pairs on bits [0,end_bit)
  * (end_bit multiple of 8); K5's building block, exported for tests and for
  * the mAP score ordering.  n_dev: device int32 holding the live count (<=max_n).

@@ -150,6 +150,47 @@ def main():
         print("mAP", c["name"], c["mAP"])
     json.dump(mp, open(os.path.join(GOLD, "map.json"), "w"))
 
+    # ---- check_model_accuracy (utils.py:334-381) -------------------------------------------------
+    class _FakeModel:  # the reference only needs eval()/train() and __call__
+        def __init__(self, outs):
+            self.outs = outs
+
+        def eval(self):
+            pass
+
+        def train(self):
+            pass
+
+        def __call__(self, x):
+            return [o.clone() for o in self.outs]
+
+    acc = {}
+    g = torch.Generator().manual_seed(321)
+    nc, thr = 4, 0.6
+    outs, tgts = [], []
+    for s in (2, 4, 8):
+        o = 2.0 * torch.randn(3, 3, s, s, 5 + nc, generator=g)
+        # keep objectness logits away from the threshold so that 1-ulp sigmoid differences cannot flip a count
+        lim = float(torch.logit(torch.tensor(thr)))
+        near = (o[..., 4] - lim).abs() < 0.05
+        o[..., 4][near] += 0.2
+        t = torch.zeros(3, 3, s, s, 6)
+        u = torch.rand(3, 3, s, s, generator=g)
+        t[..., 4] = torch.where(u < 0.2, torch.tensor(1.0), torch.where(u < 0.3, torch.tensor(-1.0), torch.tensor(0.0)))
+        t[..., 5] = torch.randint(0, nc, (3, 3, s, s), generator=g).float()
+        agree = torch.rand(3, 3, s, s, generator=g) < 0.5  # make half of the labels agree with the argmax
+        t[..., 5][agree] = torch.argmax(o[..., 5:], dim=-1).float()[agree]
+        outs.append(o)
+        tgts.append(t)
+    res = rutils.check_model_accuracy(_FakeModel(outs), [(torch.zeros(3, 3, 64, 64), [t.clone() for t in tgts])], thr)
+    for i in range(3):
+        acc[f"out{i}"] = outs[i].numpy()
+        acc[f"tgt{i}"] = tgts[i].numpy()
+    acc["thr"] = np.float64(thr)
+    acc["result"] = np.asarray([float(r) for r in res], dtype=np.float64)  # class, noobj, obj
+    np.savez_compressed(os.path.join(GOLD, "accuracy.npz"), **acc)
+    print("accuracy", acc["result"])
+
     # ---- forward --------------------------------------------------------------------------
     fwd = {}
     for name, (nc, act, size, seed) in {"nc80_leaky_64": (80, "leaky_relu", 64, 0), "nc2_mish_96": (2, "mish", 96, 1)}.items():

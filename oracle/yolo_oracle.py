@@ -8,6 +8,7 @@ reference (GabeTsai/YOLO-For-Turbines, paths relative to its checkout):
   calc_iou / iou_aligned    code/utils.py:38-84 / :22-36
   non_max_suppression(...)  code/utils.py:150-191
   calc_mAP(...)             code/utils.py:193-274
+  check_model_accuracy(...) code/utils.py:334-381 (the per-batch reductions)
   read_darknet_weights(...) code/model.py:162-170, 227-337
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
@@ -245,6 +246,22 @@ def calc_mAP(pred_boxes: list, true_boxes: list, iou_threshold: float = 0.5,
         aps.append(torch.trapz(prec, rec))
     result = sum(aps) / len(aps)  # ZeroDivisionError when no class has ground truth, as the reference
     return (result, tp_rows) if return_tp else result
+
+
+def check_model_accuracy(outs, targets, object_threshold):
+    """Reductions of utils.py:356-381 for one batch: returns (class_acc, noobj_acc, obj_acc) and the six counts."""
+    cc = tc = co = to = cn = tn = 0
+    for out, tgt in zip(outs, targets):
+        obj, noobj = tgt[..., 4] == 1, tgt[..., 4] == 0
+        cc += torch.sum(torch.argmax(out[..., 5:][obj], dim=-1) == tgt[..., 5][obj])
+        tc += torch.sum(obj)
+        pred = torch.sigmoid(out[..., 4]) > object_threshold
+        co += torch.sum(pred[obj] == tgt[..., 4][obj])
+        to += torch.sum(obj)
+        cn += torch.sum(pred[noobj] == tgt[..., 4][noobj])
+        tn += torch.sum(noobj)
+    counts = [int(v) for v in (cc, tc, co, to, cn, tn)]
+    return (cc / (tc + 1e-16), cn / (tn + 1e-16), co / (to + 1e-16)), counts
 
 
 # --- Darknet weight file (model.py:162-170, 227-337) ------------------------------

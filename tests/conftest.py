@@ -38,6 +38,7 @@ def gold():
         forward = np.load(os.path.join(GOLD, "forward.npz"))
         keys = json.load(open(os.path.join(GOLD, "state_dict_keys_nc80.json")))
         loader = json.load(open(os.path.join(GOLD, "loader.json")))
+        accuracy = np.load(os.path.join(GOLD, "accuracy.npz"))
     return G
 
 

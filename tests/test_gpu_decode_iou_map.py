@@ -95,3 +95,19 @@ def test_map_tp_flags_match_oracle_exactly():
     assert all(tp[r] == v for r, v in tp_rows.items())
     from yolo_for_turbines_b200.utils import calc_mAP
     assert abs(float(calc_mAP(dets.tolist(), gts.tolist(), 0.5, "center", nc)) - float(ref_map)) <= 1e-6
+
+
+def test_accuracy_counts_match_reference(gold):
+    """check_model_accuracy reductions (utils.py:334-381): integer counts exact, ratios equal to the reference's."""
+    from yolo_for_turbines_b200.utils import accuracy_counts
+
+    a = gold.accuracy
+    outs = [torch.from_numpy(a[f"out{i}"]) for i in range(3)]
+    tgts = [torch.from_numpy(a[f"tgt{i}"]) for i in range(3)]
+    _, ref_counts = orc.check_model_accuracy(outs, tgts, float(a["thr"]))
+    # heads as the model hands them over: non-contiguous (B,3,S,S,C) views of NHWC storage
+    dev_outs = [o.permute(0, 2, 3, 1, 4).contiguous().cuda().permute(0, 3, 1, 2, 4) for o in outs]
+    c = accuracy_counts(dev_outs, tgts, float(a["thr"])).cpu().tolist()
+    assert c == ref_counts
+    got = [c[0] / (c[1] + 1e-16), c[4] / (c[5] + 1e-16), c[2] / (c[3] + 1e-16)]
+    assert np.allclose(got, a["result"], rtol=1e-6)

@@ -120,3 +120,12 @@ def test_darknet_loader_matches_reference(gold):
                     assert float(sd[k].abs().sum()) == 0.0, (tag, k)  # untouched by the cutoff
             if tag == "cutoff74":
                 assert info["loaded_bn_convs"] == 37  # not 52/74
+
+
+def test_accuracy_reductions_match_reference(gold):
+    a = gold.accuracy
+    outs = [torch.from_numpy(a[f"out{i}"]) for i in range(3)]
+    tgts = [torch.from_numpy(a[f"tgt{i}"]) for i in range(3)]
+    (ca, na, oa), counts = orc.check_model_accuracy(outs, tgts, float(a["thr"]))
+    assert [float(ca), float(na), float(oa)] == list(a["result"])
+    assert counts[1] == counts[3] > 0 and counts[5] > 0

@@ -352,6 +352,48 @@ def get_eval_boxes(loader, model, iou_threshold, anchors, obj_threshold, box_for
     return preds, trues
 
 
+def accuracy_counts(outs, targets, object_threshold) -> torch.Tensor:
+    """Six int64 counts (correct_class, total_class, correct_obj, total_obj, correct_noobj, total_noobj) summed
+    over the three scales: the reductions of utils.py:356-371 on device."""
+    dev = outs[0].device
+    counts = torch.zeros(6, dtype=torch.int64, device=dev)
+    thr32 = float(torch.tensor(object_threshold, dtype=torch.float32))
+    with torch.cuda.device(dev):
+        for o, t in zip(outs, targets):
+            o = o if o.dtype == torch.float32 else o.float()
+            t = t.to(device=dev, dtype=torch.float32)
+            B, A, S, _, Cc = o.shape
+            if A != 3 or tuple(t.shape[:4]) != (B, 3, S, S):
+                raise YoloB200Error(f"head {tuple(o.shape)} and target {tuple(t.shape)} do not match")
+            lib.yolo_accuracy_counts(ptr(o), (C.c_int64 * 5)(*o.stride()), ptr(t), (C.c_int64 * 5)(*t.stride()), B, S,
+                                     Cc - 5, thr32, ptr(counts), stream_ptr(dev))
+            counts.record_stream(torch.cuda.current_stream(dev))
+    return counts
+
+
+def check_model_accuracy(model, loader, object_threshold):
+    """utils.py:334-381: class / no-object / object accuracy over a loader; same prints, same return order."""
+    was_training = model.training
+    model.eval()
+    dev = next(model.parameters()).device
+    total = torch.zeros(6, dtype=torch.int64, device=dev)
+    for x, target in loader:
+        x = x.to(dev)
+        plan, heads = model.forward_async(x)
+        total += accuracy_counts(heads, target, object_threshold)
+        plan.check_status()
+    c = total.to(torch.float32).cpu()
+    class_accuracy = c[0] / (c[1] + 1e-16)
+    noobj_accuracy = c[4] / (c[5] + 1e-16)
+    obj_accuracy = c[2] / (c[3] + 1e-16)
+    print(f"Class accuracy is: {(class_accuracy)*100:2f}%")
+    print(f"No obj accuracy is: {(noobj_accuracy)*100:2f}%")
+    print(f"Obj accuracy is: {(obj_accuracy)*100:2f}%")
+    if was_training:
+        model.train()
+    return class_accuracy, noobj_accuracy, obj_accuracy
+
+
 # names used by BASELINE.json's north_star (upstream Aladdin-Persson spelling)
 cells_to_bboxes = cells_to_boxes
 intersection_over_union = calc_iou
