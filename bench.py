@@ -259,6 +259,41 @@ def main():
     torch.cuda.synchronize(dev)
     ms_conv = c0.elapsed_time(c1) / conv_steps
 
+    # ---- stage timings that explain the step: decode (HBM roofline) and the NMS pipeline (boxes/s) -----
+    from yolo_for_turbines_b200.utils import batched_nms, decode_boxes, _scaled_anchors
+
+    heads = plan.head_views()
+    stt = det._get_state(B, [h.shape[2] for h in heads], dev)
+
+    def run_decode():
+        off = 0
+        for i, h in enumerate(heads):
+            s = h.shape[2]
+            decode_boxes(h, _scaled_anchors(cfg.ANCHORS, i, s), s, True, out=stt["cand"], out_offset=off)
+            off += 3 * s * s
+
+    def run_nms():
+        batched_nms(stt["cand"].view(-1, 6), stt["off"], args.iou, args.conf, "center", workspace=stt["ws"], class_bits=8)
+
+    def timed_graph(fn, reps=10):
+        fn()
+        torch.cuda.synchronize(dev)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        gr.replay()
+        torch.cuda.synchronize(dev)
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            gr.replay()
+        bb.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(bb) / reps
+
+    ms_decode = timed_graph(run_decode)
+    ms_nms = timed_graph(run_nms)
+
     # ---- end to end from pinned host memory through the public API ------------------------------
     # Every step: H2D copy of that step's pinned fp32 batch, model forward + decode + NMS through
     # utils.Detector, D2H of the survivors (per-image offsets + kept rows) into pinned host memory.
@@ -349,6 +384,13 @@ def main():
                          "ms_per_step_conv": ms_conv, "conv_share_of_step": ms_conv / (ms_dev / args.steps),
                          "traffic": None},
             "clocks": clocks,
+            "stages": {
+                "nms": {"ms_per_step": ms_nms, "candidates_per_sec": B * n_cand / (ms_nms / 1e3), "unit": "boxes/s",
+                        "note": "K4 threshold compaction + K5 sorts + K6 greedy NMS on the step's own candidates"},
+                "decode": {"ms_per_step": ms_decode, "achieved_gbs": B * n_cand * ((5 + args.classes) * 4 + 24) / ms_decode / 1e6,
+                           "peak_gbs": pk["hbm"], "frac": B * n_cand * ((5 + args.classes) * 4 + 24) / ms_decode / 1e6 / pk["hbm"],
+                           "bound": "hbm", "bytes_per_candidate": (5 + args.classes) * 4 + 24},
+            },
         }
         if world == 1 and not args.no_cpu_baseline:
             m_cpu = default_init_state_dict(args.classes)

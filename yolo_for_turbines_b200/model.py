@@ -232,10 +232,8 @@ class YOLOv3(_EngineHolder, nn.Module):
             self.__dict__["_yb_engine"] = eng
         return eng
 
-    def forward_async(self, x):
-        """Enqueues the whole forward on the current stream and returns (plan, head views) WITHOUT
-        the host sync; callers must eventually call plan.check_status().  Views alias static buffers
-        that the next forward of the same shape overwrites."""
+    def _prepare(self, x):
+        """Input checks + (cached) plan lookup shared by forward_async and utils.Detector."""
         require_cuda(x, "YOLOv3 input")
         if self.training:
             raise YoloB200Error("train-mode forward (batch-statistics BatchNorm + autograd) is not built on this "
@@ -246,7 +244,13 @@ class YOLOv3(_EngineHolder, nn.Module):
         eng.refresh_if_needed()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
-        plan = eng.plan(x.shape[0], x.shape[2], x.shape[3])
+        return eng.plan(x.shape[0], x.shape[2], x.shape[3]), x
+
+    def forward_async(self, x):
+        """Enqueues the whole forward on the current stream and returns (plan, head views) WITHOUT
+        the host sync; callers must eventually call plan.check_status().  Views alias static buffers
+        that the next forward of the same shape overwrites."""
+        plan, x = self._prepare(x)
         with torch.cuda.device(x.device):
             plan.run(x)
         return plan, plan.head_views()

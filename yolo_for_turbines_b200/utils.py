@@ -277,6 +277,7 @@ class Detector:
         self.model = model
         self.anchors = config.ANCHORS if anchors is None else anchors
         self.iou_threshold, self.obj_threshold, self.box_format = iou_threshold, obj_threshold, box_format
+        self.use_graph = True
         self._state = {}
 
     def _get_state(self, B, grids, device):
@@ -290,23 +291,45 @@ class Detector:
             self._state[key] = st
         return st
 
-    def __call__(self, x: torch.Tensor):
-        """Returns (NmsResult, plan); plan.check_status() reports NaN inputs/layers after the fact."""
-        plan, heads = self.model.forward_async(x)
-        B = x.shape[0]
-        grids = [h.shape[2] for h in heads]
-        st = self._get_state(B, grids, x.device)
+    def _post(self, plan, st):
+        """decode x3 + batched NMS on the plan's head buffers (all launches on the current stream)."""
+        heads = plan.head_views()
         off = 0
         for i, h in enumerate(heads):
-            s = grids[i]
-            anc = _scaled_anchors(self.anchors, i, s)
-            decode_boxes(h, anc, s, True, out=st["cand"], out_offset=off)
+            s = h.shape[2]
+            decode_boxes(h, _scaled_anchors(self.anchors, i, s), s, True, out=st["cand"], out_offset=off)
             off += 3 * s * s
         # classes come from the decode's argmax: integers < num_classes, so the grouping sort needs one pass
         nc = max(h.shape[-1] - 5 for h in heads)
-        res = batched_nms(st["cand"].view(-1, 6), st["off"], self.iou_threshold, self.obj_threshold, self.box_format,
-                          workspace=st["ws"], class_bits=8 if nc <= 256 else (16 if nc <= 65536 else 0))
-        return res, plan
+        return batched_nms(st["cand"].view(-1, 6), st["off"], self.iou_threshold, self.obj_threshold, self.box_format,
+                           workspace=st["ws"], class_bits=8 if nc <= 256 else (16 if nc <= 65536 else 0))
+
+    def __call__(self, x: torch.Tensor):
+        """Returns (NmsResult, plan); plan.check_status() reports NaN inputs/layers after the fact.
+        Call 1 of a shape runs eagerly (warm-up), call 2 captures convs + decode + NMS (~115 launches) in ONE
+        CUDA graph, later calls replay it; only the input conversion (its source pointer changes) stays eager."""
+        plan, x = self.model._prepare(x)
+        with torch.cuda.device(x.device):
+            st = self._get_state(plan.B, [h.H for h in plan.heads], x.device)
+            if st.get("plan") is not plan:  # the model re-planned (new engine): drop the stale graph
+                st.update(plan=plan, graph=None, calls=0, res=None)
+            if st["graph"] is not None:
+                plan._launch_input(x)
+                st["graph"].replay()
+            elif st["calls"] == 0 or not self.use_graph:
+                plan.run(x)
+                st["res"] = self._post(plan, st)
+            else:
+                plan._launch_input(x)
+                torch.cuda.current_stream(x.device).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    plan._launch_convs()
+                    st["res"] = self._post(plan, st)
+                st["graph"] = g
+                g.replay()
+            st["calls"] += 1
+        return st["res"], plan
 
 
 def detect(model, x, anchors=None, iou_threshold=config.NMS_IOU_THRESHOLD, obj_threshold=config.CONF_THRESHOLD,
