@@ -122,3 +122,35 @@ def test_nms_properties_at_full_size():
             i, j = torch.triu_indices(rc.shape[0], rc.shape[0], 1, device="cuda")
             iou = calc_iou(rc[i, :4], rc[j, :4], "center")
             assert bool((iou < torch.tensor(0.45, device="cuda")).all())
+
+
+@pytest.mark.parametrize("n,nc,conf,wh", [(7000, 1, 0.3, (0.02, 0.1)), (8192, 1, 0.0, (0.02, 0.08)), (8193, 1, 0.0, (0.02, 0.08)),
+                                          (23000, 1, 0.01, (0.02, 0.12)), (30000, 2, 0.2, (0.05, 0.4))])
+def test_long_single_class_segments_match_oracle(oracle_c, n, nc, conf, wh):
+    """One (image, class) segment holding thousands of boxes: the regime of a random-init model (argmax collapses
+    onto a few classes).  <= 8192 boxes take the register-resident path, longer ones the global-memory path."""
+    from yolo_for_turbines_b200.utils import batched_nms
+
+    b = synth.synth_boxes(n, nc, 4242 + n, tie_frac=0.02, wh=wh)
+    b[5, 2] = float("inf")      # a few special boxes inside a long segment
+    b[77, 0] = float("nan")
+    b[100, 2] = -0.05           # negative width
+    off = torch.tensor([0, n], dtype=torch.int32, device="cuda")
+    for fmt in ("center", "corners"):
+        res = batched_nms(b.cuda(), off, 0.45, conf, fmt)
+        k = int(res.keep_off[1])
+        assert res.keep_idx[:k].cpu().tolist() == oracle_c(b, 0.45, conf, fmt), (n, fmt)
+        # the integer-class fast path must give the same answer
+        res8 = batched_nms(b.cuda(), off, 0.45, conf, fmt, class_bits=8)
+        assert res8.keep_idx[: int(res8.keep_off[1])].cpu().tolist() == res.keep_idx[:k].cpu().tolist()
+
+
+def test_nms_zero_and_negative_iou_threshold(oracle_c):
+    """iou_threshold <= 0 disables the disjoint-boxes shortcut (0 < thr is false): everything of a class but the top box goes."""
+    from yolo_for_turbines_b200.utils import batched_nms
+
+    b = synth.synth_boxes(500, 3, 99, wh=(0.02, 0.2))
+    off = torch.tensor([0, 500], dtype=torch.int32, device="cuda")
+    for thr in (0.0, -1.0, 1e-30):
+        res = batched_nms(b.cuda(), off, thr, 0.1, "center")
+        assert res.keep_idx[: int(res.keep_off[1])].cpu().tolist() == oracle_c(b, thr, 0.1, "center"), thr

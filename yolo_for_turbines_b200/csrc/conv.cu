@@ -350,7 +350,8 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
   if (stages > num_kb) stages = num_kb;
   if (stages < 1) stages = 1;
   pl->smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
-  YB_REQUIRE(pl->smem_bytes <= 227 * 1024, "conv plan: %d stages of %d B exceed shared memory", stages, stage_bytes);
+  if (d->impl_hint == 1)
+    YB_REQUIRE(pl->smem_bytes <= 227 * 1024, "conv plan: %d stages of %d B exceed shared memory", stages, stage_bytes);
 
   const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult cr;
