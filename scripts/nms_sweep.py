@@ -1,0 +1,86 @@
+"""BASELINE config 5: standalone NMS (+ mAP matching) sweep, 10^4..10^6 candidate boxes per batch of 64 images.
+GPU: yolo_nms through utils.batched_nms (CUDA events).  CPU: the reference algorithm (oracle port, torch ops per kept box)
+timed per image on a subset and scaled to the batch (labelled extrapolated), plus the C restatement for context."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import yolo_oracle as orc  # noqa: E402  (CPU baseline leg only)
+from yolo_for_turbines_b200.utils import NmsWorkspace, batched_nms, map_match  # noqa: E402
+
+B = 64
+dev = torch.device("cuda", 0)
+
+
+def make(total, nc, seed=42):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    b = torch.rand(total, 6, generator=g, device=dev)
+    b[:, 2:4] = 0.02 + 0.28 * b[:, 2:4]
+    b[:, 5] = torch.floor(b[:, 5] * nc)
+    n_tie = total // 100
+    b[torch.randperm(total, generator=g, device=dev)[:n_tie], 4] = 0.7311  # 1 % tie-score subset
+    return b
+
+
+def gpu_time(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        c.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(c))
+    return sorted(ts)[len(ts) // 2]
+
+
+print(f"{'N/batch':>9s} {'nc':>3s} {'conf':>5s} {'kept':>8s} {'GPU ms':>8s} {'GPU Mbox/s':>11s} {'CPU ref s (extrap.)':>20s} {'CPU kbox/s':>10s} {'speedup':>9s}")
+for total in (10_000, 30_000, 100_000, 300_000, 1_000_000):
+    per = total // B
+    total = per * B
+    for nc in (80, 2):
+        boxes = make(total, nc)
+        off = (torch.arange(B + 1, dtype=torch.int32, device=dev) * per)
+        ws = NmsWorkspace(total, B, dev)
+        for conf in (0.5, 0.01):
+            ms = gpu_time(lambda: batched_nms(boxes, off, 0.45, conf, "center", workspace=ws, class_bits=8))
+            kept = int(ws.keep_off[-1])
+            # CPU: the reference's algorithm on image 0 (and 1 more when cheap), scaled to 64 images
+            n_img = 2 if per <= 2000 else 1
+            cpu = 0.0
+            if per <= 5000:
+                for i in range(n_img):
+                    rows = boxes[i * per:(i + 1) * per].cpu().tolist()
+                    t0 = time.perf_counter()
+                    orc.non_max_suppression(rows, 0.45, conf, "center")
+                    cpu += time.perf_counter() - t0
+                cpu = cpu / n_img * B
+                cpu_s = f"{cpu:20.2f}"
+                rate = f"{total / cpu / 1e3:10.1f}"
+                sp = f"{cpu * 1e3 / ms:9.0f}"
+            else:
+                cpu_s, rate, sp = f"{'(skipped: > minutes)':>20s}", f"{'-':>10s}", f"{'-':>9s}"
+            print(f"{total:9d} {nc:3d} {conf:5.2f} {kept:8d} {ms:8.3f} {total / ms / 1e3:11.1f} {cpu_s} {rate} {sp}", flush=True)
+
+# mAP matching at evaluation scale: D detections vs G ground truths
+print()
+print(f"{'D dets':>9s} {'G gts':>7s} {'images':>7s} {'GPU ms (map_match)':>20s}")
+for D, G, n_img in ((10_000, 1_000, 64), (100_000, 10_000, 640), (1_000_000, 35_000, 5000)):
+    g = torch.Generator(device=dev).manual_seed(7)
+    gts = torch.rand(G, 7, generator=g, device=dev)
+    gts[:, 0] = torch.floor(gts[:, 0] * n_img)
+    gts[:, 3:5] = 0.05 + 0.35 * gts[:, 3:5]
+    gts[:, 6] = torch.floor(gts[:, 6] * 80)
+    dets = gts[torch.randint(0, G, (D,), generator=g, device=dev)].clone()
+    dets[:, 1:5] += 0.03 * torch.randn(D, 4, generator=g, device=dev)
+    dets[:, 5] = torch.rand(D, generator=g, device=dev)
+    ms = gpu_time(lambda: map_match(dets, gts, 0.5, "center"), reps=3)
+    print(f"{D:9d} {G:7d} {n_img:7d} {ms:20.3f}")

@@ -33,10 +33,10 @@ struct Cfg {
   static constexpr int B_ROWS = BLOCK_N / NCTA;
   static constexpr uint32_t B_BYTES = B_ROWS * ROW_BYTES;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  // 32-channel epilogue boxes (64-byte rows, SWIZZLE_64B): the staging ring costs 32 KB instead of 64 KB, which
-  // buys one more 32 KB stage of the A/B ring -- the main loop is bound by bytes in flight, not by stores.
-  static constexpr int BOXC = 32;
-  static constexpr int BOX_ROW_BYTES = BOXC * 2;
+  // 64-channel boxes (128-byte rows).  Measured alternative: 32-channel boxes free 32 KB for a 6th stage of the
+  // A/B ring but double the per-box epilogue overhead -- net slower on the N=256, short-K layers.
+  static constexpr int BOXC = BLOCK_N < 64 ? BLOCK_N : 64;   // channels per epilogue box
+  static constexpr int BOX_ROW_BYTES = BOXC * 2;             // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   static constexpr uint32_t WBOX_BYTES = 32 * BOX_ROW_BYTES; // one warp's 32 rows of a box
   static constexpr int NBOXES = BLOCK_N / BOXC;
   static constexpr uint32_t EPI_BYTES = EPI_WARPS * WSLOTS * WBOX_BYTES;
@@ -254,8 +254,9 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           acc_ready = true;
         }
         const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + b * C::BOXC;
-        uint32_t v0[32];
+        uint32_t v0[32], v1[32];
         tmem_ld32_nowait(taddr, v0);
+        if constexpr (C::BOXC == 64) tmem_ld32_nowait(taddr + 32, v1);
         tmem_wait_ld();
         if (b == C::NBOXES - 1) {
           // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
@@ -328,6 +329,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           }
         };
         process_half(v0, 0);
+        if constexpr (C::BOXC == 64) process_half(v1, 1);
         if (staged) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
@@ -420,8 +422,8 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
     YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: tensor map B encode failed (%d)", (int)cr);
   }
   const int direct = d->upsample2x || d->out_fp32;
-  const int boxc = 32;
-  const CUtensorMapSwizzle bswz = CU_TENSOR_MAP_SWIZZLE_64B;
+  const int boxc = bn < 64 ? bn : 64;
+  const CUtensorMapSwizzle bswz = boxc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   if (!direct) {
     cuuint64_t dims[2] = {(cuuint64_t)d->c_out_pad, (cuuint64_t)M};
     cuuint32_t box[2] = {(cuuint32_t)boxc, 32u};  // one epilogue warp's 32 rows
