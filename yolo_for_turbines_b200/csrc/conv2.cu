@@ -5,9 +5,9 @@
 //     init, tensor-map prefetch and the TMEM allocation are paid once per launch, not per tile;
 //   * the fp32 accumulator is double buffered in TMEM (2 x BLOCK_N columns): the epilogue of tile i
 //     overlaps the TMA/MMA main loop of tile i+1;
-//   * every epilogue warp stages its 32-row x 64-channel bf16 box (128B-swizzled) in shared memory and copies it out
-//     with line-coalesced st.global (4 rows x 128 B per instruction) instead of 16-byte fragments per thread; the
-//     residual operand comes in through the same boxes with TMA loads;
+//   * the epilogue stages bf16 output boxes (128 rows x 64 channels, 128B-swizzled) in shared memory
+//     and writes them with TMA bulk stores -- full 128-byte lines instead of 16-byte fragments per
+//     thread -- and the residual operand comes in through the same boxes with TMA loads;
 //   * NCTA == 2: tcgen05.mma.cta_group::2 pairs two SMs on one 256 x BLOCK_N tile.  Each CTA loads its
 //     own 128 rows of A and HALF of the weight tile, so per-CTA L2->smem traffic per FLOP halves.
 //
@@ -239,9 +239,12 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         const uint32_t slot_addr = wslot_base + slot * C::WBOX_BYTES;
         const int nb = n0 + b * C::BOXC;
         if (staged) {
-          if (lane == 0 && p.has_residual) {
-            mbar_expect_tx(res_bar(ew, slot), C::WBOX_BYTES);
-            tma_load_2d(&p.tmR, res_bar(ew, slot), slot_addr, nb, m0w);
+          if (lane == 0) {
+            bulk_wait_group_read<WSLOTS - 1>();  // the TMA store that last used this slot has read it out
+            if (p.has_residual) {
+              mbar_expect_tx(res_bar(ew, slot), C::WBOX_BYTES);
+              tma_load_2d(&p.tmR, res_bar(ew, slot), slot_addr, nb, m0w);
+            }
           }
           __syncwarp();
         }
@@ -328,30 +331,18 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         process_half(v0, 0);
         if constexpr (C::BOXC == 64) process_half(v1, 1);
         if (staged) {
-          // copy-out: the warp re-reads its 32 x BOXC box from shared memory so that every store instruction
-          // writes whole 128-byte lines (4 rows x 128 B, or 8 rows x 64 B).  Plain st.global instead of a TMA
-          // bulk store: a store queued in the TMA unit behind the deep ring of prefetch loads came back
-          // microseconds later and throttled the short-K (1x1) layers through the slot ring.
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
-          constexpr int CPR = C::BOX_ROW_BYTES / 16;  // 16-byte chunks per row
-          constexpr int RPI = 32 / CPR;               // rows per warp instruction
-          const int crow = lane / CPR, cchunk = lane % CPR;
-          __nv_bfloat16* ybase = static_cast<__nv_bfloat16*>(p.y) + nb + cchunk * 8;
-#pragma unroll
-          for (int i = 0; i < CPR; ++i) {
-            const int r = i * RPI + crow;
-            const uint32_t rs = (C::BOX_ROW_BYTES == 128) ? (r & 7) : ((r >> 1) & 3);
-            const uint32_t a = slot_addr + r * C::BOX_ROW_BYTES + ((cchunk ^ rs) << 4);
-            uint4 v;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-            if (m0w + r < p.M) *reinterpret_cast<uint4*>(ybase + size_t(m0w + r) * p.out_pitch) = v;
+          if (lane == 0) {
+            tma_store_2d(&p.tmY, slot_addr, nb, m0w);  // rows >= M are clipped by the tensor map
+            bulk_commit_group();
           }
-          __syncwarp();  // the slot may now be refilled (residual TMA load / next box)
           ++wbox;
         }
       }
     }
     if (saw_nan) atomicOr(p.status, YB_STATUS_NAN_LAYER);
+    if (lane == 0) bulk_wait_group_all();
   }
 
   tc_fence_before();
