@@ -188,6 +188,15 @@ int yolo_accuracy_counts(const float* head, const int64_t* hstrides5_host, const
                          const int64_t* tstrides5_host, int batch, int S, int nc, float obj_thr,
                          unsigned long long* counts6, yb_stream_t stream);
 
+/* K8 (forward only) -- the four terms of YOLOLoss.forward (loss.py:29-81) for one scale.  pred (B,3,S,S,5+nc)
+ * and target (B,3,S,S,6) fp32 with element strides; anchors6 = the scale's 3 (w,h) anchors in grid units.
+ * sums6 (device double[6], MUST be zero on entry): sum softplus over no-obj cells, #no-obj, sum (logit-iou)^2
+ * over obj cells, sum of the 4 squared box terms, sum cross-entropy, #obj.  mutate=1 also applies loss.py:71-72's
+ * in-place updates of pred[...,1:3] and target[...,2:4] (only when an object cell exists).                    */
+int yolo_loss_fwd(float* pred, const int64_t* pstrides5_host, float* target, const int64_t* tstrides5_host,
+                  int batch, int S, int nc, const float* anchors6_host, int mutate, double* sums6,
+                  yb_stream_t stream);
+
 /* Stable LSD radix sort of (u64 key, i32 value) pairs on bits [0,end_bit)
  * (end_bit multiple of 8); K5's building block, exported for tests and for
  * the mAP score ordering.  n_dev: device int32 holding the live count (<=max_n).

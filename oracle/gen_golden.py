@@ -191,6 +191,31 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "accuracy.npz"), **acc)
     print("accuracy", acc["result"])
 
+    # ---- YOLOLoss.forward (loss.py:29-81) ------------------------------------------------------
+    lossd = {}
+    for name, (bsz, s, nc, scale_i, with_obj) in {"s13_nc2": (4, 13, 2, 0, True), "s16_nc80": (1, 16, 80, 1, True),
+                                                  "s8_noobj": (2, 8, 3, 2, False)}.items():
+        g = torch.Generator().manual_seed(700 + s)
+        pred = 1.5 * torch.randn(bsz, 3, s, s, 5 + nc, generator=g)
+        tgt = torch.zeros(bsz, 3, s, s, 6)
+        u = torch.rand(bsz, 3, s, s, generator=g)
+        if with_obj:
+            tgt[..., 4] = torch.where(u < 0.08, torch.tensor(1.0), torch.where(u < 0.12, torch.tensor(-1.0), torch.tensor(0.0)))
+        tgt[..., 0:2] = torch.rand(bsz, 3, s, s, 2, generator=g)
+        tgt[..., 2:4] = 0.5 + 3.5 * torch.rand(bsz, 3, s, s, 2, generator=g)     # grid units
+        tgt[..., 5] = torch.randint(0, nc, (bsz, 3, s, s), generator=g).float()
+        anchors = torch.tensor(orc.TURBINE_ANCHORS[scale_i]) * s
+        p_work, t_work = pred.clone(), tgt.clone()
+        out = rloss.YOLOLoss()(p_work, t_work, anchors)
+        lossd[name + "/pred"] = pred.numpy()
+        lossd[name + "/tgt"] = tgt.numpy()
+        lossd[name + "/anchors"] = anchors.numpy()
+        lossd[name + "/loss"] = np.asarray([float(v) for v in out], dtype=np.float64)
+        lossd[name + "/pred_after"] = p_work.numpy()   # in-place side effects (loss.py:71-72)
+        lossd[name + "/tgt_after"] = t_work.numpy()
+        print("loss", name, lossd[name + "/loss"])
+    np.savez_compressed(os.path.join(GOLD, "loss.npz"), **lossd)
+
     # ---- forward --------------------------------------------------------------------------
     fwd = {}
     for name, (nc, act, size, seed) in {"nc80_leaky_64": (80, "leaky_relu", 64, 0), "nc2_mish_96": (2, "mish", 96, 1)}.items():

@@ -9,6 +9,7 @@ reference (GabeTsai/YOLO-For-Turbines, paths relative to its checkout):
   non_max_suppression(...)  code/utils.py:150-191
   calc_mAP(...)             code/utils.py:193-274
   check_model_accuracy(...) code/utils.py:334-381 (the per-batch reductions)
+  yolo_loss(...)            code/loss.py:29-81
   read_darknet_weights(...) code/model.py:162-170, 227-337
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
@@ -262,6 +263,25 @@ def check_model_accuracy(outs, targets, object_threshold):
         tn += torch.sum(noobj)
     counts = [int(v) for v in (cc, tc, co, to, cn, tn)]
     return (cc / (tc + 1e-16), cn / (tn + 1e-16), co / (to + 1e-16)), counts
+
+
+def yolo_loss(predictions: torch.Tensor, targets: torch.Tensor, anchors: torch.Tensor) -> list:
+    """YOLOLoss.forward (loss.py:29-81) for one scale, including its in-place updates of predictions[..., 1:3]
+    and targets[..., 2:4] and the index quirk (sigmoid on entries 1:3, i.e. ty and tw)."""
+    obj, noobj = targets[..., 4] == 1, targets[..., 4] == 0
+    anchors = anchors.reshape(1, 3, 1, 1, 2)
+    zero = torch.tensor(0.0)
+    object_loss = box_loss = class_loss = zero
+    no_obj_loss = F.binary_cross_entropy_with_logits(predictions[..., 4][noobj], targets[..., 4][noobj])
+    if obj.any():
+        boxes = torch.cat([torch.sigmoid(predictions[..., :2]), torch.exp(predictions[..., 2:4]) * anchors], dim=-1)
+        ious = calc_iou(boxes[obj], targets[..., :4][obj]).unsqueeze(1).detach()
+        object_loss = F.mse_loss(predictions[..., 4:5][obj], ious * targets[..., 4:5][obj])
+        predictions[..., 1:3] = torch.sigmoid(predictions[..., 1:3])
+        targets[..., 2:4] = torch.log(1e-16 + targets[..., 2:4] / anchors)
+        box_loss = F.mse_loss(predictions[..., :4][obj], targets[..., :4][obj])
+        class_loss = F.cross_entropy(predictions[..., 5:][obj], targets[..., 5][obj].long())
+    return [5 * box_loss, 1 * object_loss, 0.5 * no_obj_loss, 1 * class_loss]
 
 
 # --- Darknet weight file (model.py:162-170, 227-337) ------------------------------

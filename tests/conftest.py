@@ -39,6 +39,7 @@ def gold():
         keys = json.load(open(os.path.join(GOLD, "state_dict_keys_nc80.json")))
         loader = json.load(open(os.path.join(GOLD, "loader.json")))
         accuracy = np.load(os.path.join(GOLD, "accuracy.npz"))
+        loss = np.load(os.path.join(GOLD, "loss.npz"))
     return G
 
 

@@ -111,3 +111,25 @@ def test_accuracy_counts_match_reference(gold):
     assert c == ref_counts
     got = [c[0] / (c[1] + 1e-16), c[4] / (c[5] + 1e-16), c[2] / (c[3] + 1e-16)]
     assert np.allclose(got, a["result"], rtol=1e-6)
+
+
+def test_yolo_loss_forward_matches_reference(gold):
+    """Fused YOLOLoss forward (loss.py:29-81).  Stated tolerance: 1e-5 relative per term (fp32 reference sums vs
+    fp64 device accumulation); in-place side effects within 1e-6."""
+    from yolo_for_turbines_b200.loss import YOLOLoss
+
+    d = gold.loss
+    for name in ("s13_nc2", "s16_nc80", "s8_noobj"):
+        p = torch.from_numpy(d[name + "/pred"]).cuda()
+        t = torch.from_numpy(d[name + "/tgt"]).cuda()
+        with torch.no_grad():
+            out = YOLOLoss()(p, t, torch.from_numpy(d[name + "/anchors"]))
+        got = np.asarray([float(v) for v in out])
+        ref = d[name + "/loss"]
+        assert len(out) == 4 and all(v.dim() == 0 and v.dtype == torch.float32 for v in out)
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-7), (name, got, ref)
+        assert np.allclose(p.cpu().numpy(), d[name + "/pred_after"], rtol=1e-6, atol=1e-6), name
+        assert np.allclose(t.cpu().numpy(), d[name + "/tgt_after"], rtol=1e-6, atol=1e-6), name
+    p = torch.zeros(1, 3, 4, 4, 7, device="cuda", requires_grad=True)
+    with pytest.raises(Exception, match="backward is not built"):
+        YOLOLoss()(p, torch.zeros(1, 3, 4, 4, 6, device="cuda"), [[1, 1]] * 3)

@@ -129,3 +129,12 @@ def test_accuracy_reductions_match_reference(gold):
     (ca, na, oa), counts = orc.check_model_accuracy(outs, tgts, float(a["thr"]))
     assert [float(ca), float(na), float(oa)] == list(a["result"])
     assert counts[1] == counts[3] > 0 and counts[5] > 0
+
+
+def test_yolo_loss_matches_reference(gold):
+    d = gold.loss
+    for name in ("s13_nc2", "s16_nc80", "s8_noobj"):
+        p, t = torch.from_numpy(d[name + "/pred"]).clone(), torch.from_numpy(d[name + "/tgt"]).clone()
+        out = orc.yolo_loss(p, t, torch.from_numpy(d[name + "/anchors"]))
+        assert [float(v) for v in out] == list(d[name + "/loss"]), name
+        assert np.array_equal(p.numpy(), d[name + "/pred_after"]) and np.array_equal(t.numpy(), d[name + "/tgt_after"]), name

@@ -58,6 +58,7 @@ SIGNATURES = {
     "yolo_iou": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
     "yolo_map_match": (_I, [_P, _I, _P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P]),
     "yolo_accuracy_counts": (_I, [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64), _I, _I, _I, _F, _P, _P]),
+    "yolo_loss_fwd": (_I, [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _I, _P, _P]),
     "yolo_sort_workspace_bytes": (_SZ, [_I]),
     "yolo_sort_pairs": (_I, [_P, _P, _P, _I, _I, _P, _SZ, _P]),
 }
