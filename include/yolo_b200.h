@@ -87,6 +87,10 @@ typedef struct yolo_conv_desc {
    * pixel-pair folding of stride-2 layers, where a 3x3/s2/p1 conv becomes 3x2, stride (2,1), pad (1|0)  */
   int32_t ksize_w, stride_w;          /* filter width / stride along W                         */
   int32_t pad_w_hi_plus1;             /* 0: right pad = pad; else right pad = value - 1        */
+  /* fused stem: > 0 marks the network's first conv (model.py:21) run straight from the NCHW fp32 image;
+   * the desc then describes the pair-folded GEMM (ksize 1, c_in 64 = 2 x 32 taps, c_out 64, w_in = W/2),
+   * x is not needed at plan time and the plan is launched with yolo_conv_fwd_stem.                      */
+  int32_t stem_c;                     /* image channels (3), 0 = ordinary layer                */
 } yolo_conv_desc;
 
 /* Size of the opaque, caller-owned plan blob (64-byte aligned storage).       */
@@ -97,6 +101,8 @@ int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yolo_conv_desc
                         const void* x, const void* w_packed, const float* scale,
                         const float* bias, const void* residual, void* y);
 int yolo_conv_fwd(const void* plan_host, uint32_t* status, yb_stream_t stream);
+/* Fused stem launch: x_nchw = (B,3,H,W) fp32; also ORs YB_STATUS_NAN_INPUT (model.py:175).               */
+int yolo_conv_fwd_stem(const void* plan_host, const float* x_nchw, uint32_t* status, yb_stream_t stream);
 /* tile configuration chosen by plan_init: info8 = block_n, block_k, stages, tiles_n, tiles_m,
  * impl (1|2), CTAs per cluster, launched CTAs */
 int yolo_conv_plan_info(const void* plan_host, int32_t* info8);

@@ -65,15 +65,20 @@ for op in plan.ops:
     if args.warm:
         ts = []
         for _ in range(args.reps):
-            if prev is not None:
+            if prev is not None and not (plan.stem_direct and prev is plan.ops[0]):
                 lib.yolo_conv_fwd(prev.plan_ptr, sp, st)  # leaves this layer's input in L2 as the graph does
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            lib.yolo_conv_fwd(op.plan_ptr, sp, st)
+            if plan.stem_direct and op is plan.ops[0]:
+                lib.yolo_conv_fwd_stem(op.plan_ptr, ptr(x), sp, st)
+            else:
+                lib.yolo_conv_fwd(op.plan_ptr, sp, st)
             b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
         ms = sorted(ts)[len(ts) // 2]
+    elif plan.stem_direct and op is plan.ops[0]:
+        ms = timed(lambda: lib.yolo_conv_fwd_stem(op.plan_ptr, ptr(x), sp, st))
     else:
         ms = timed(lambda: lib.yolo_conv_fwd(op.plan_ptr, sp, st))
     prev = op
@@ -89,7 +94,7 @@ for r in rows:
 print(f"conv total (isolated, L2 flushed): {tot_ms:.3f} ms  {tot_gf:.1f} GFLOP  {tot_gf / tot_ms:.1f} TFLOP/s")
 ms_in = timed(lambda: plan._launch_input(x))
 print(f"input patchify: {ms_in:.4f} ms  ({x.numel() * 4 / 1e6:.0f} MB in, {args.batch * args.size ** 2 * 64 / 1e6:.0f} MB out)")
-ms_graph = timed(lambda: plan.graph.replay(), do_flush=False)
+ms_graph = timed(lambda: (plan._launch_input(x) if plan.stem_direct else None, plan.graph.replay()), do_flush=False)
 print(f"conv graph replay (back to back): {ms_graph:.3f} ms -> {tot_gf / ms_graph:.1f} TFLOP/s, {args.batch / ms_graph * 1e3:.0f} img/s conv-only")
 from yolo_for_turbines_b200.utils import batched_nms, decode_boxes  # noqa: E402
 heads = plan.head_views()

@@ -19,6 +19,8 @@
 //   - 4 epilogue warps read TMEM with tcgen05.ld, apply folded BN + activation
 //     (+ residual), convert to bf16 and store.
 // Warp roles: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue.
+#include <string.h>
+
 #include <new>
 
 #include "conv_plan.cuh"
@@ -310,7 +312,8 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
   int h_out, w_out;
   int rc = validate_desc(d, &h_out, &w_out);
   if (rc) return rc;
-  YB_REQUIRE(x && w_packed && scale && bias && y, "conv plan: null tensor pointer");
+  const bool stem = d->stem_c > 0;
+  YB_REQUIRE((x || stem) && w_packed && scale && bias && y, "conv plan: null tensor pointer");
   YB_REQUIRE(!d->has_residual || residual, "conv plan: residual pointer missing");
   YB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
@@ -355,7 +358,10 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
 
   const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult cr;
-  if (im2col) {
+  if (stem) {
+    cr = CUDA_SUCCESS;  // no A tensor map: the stem kernel gathers A from the NCHW image itself
+    memset(&pl->kp.tmA, 0, sizeof(pl->kp.tmA));
+  } else if (im2col) {
     cuuint64_t dims[4] = {(cuuint64_t)d->c_in, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
     cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->w_in * d->in_pitch * 2,
                              (cuuint64_t)d->h_in * d->w_in * d->in_pitch * 2};
@@ -410,7 +416,8 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
   pl->grid_x = d->c_out_pad / bn;
   pl->grid_y = (int)((M + BLOCK_M - 1) / BLOCK_M);
   pl->w = w_packed;
-  pl->impl = d->impl_hint == 1 ? 1 : 2;
+  pl->impl = (d->impl_hint == 1 && !stem) ? 1 : 2;
+  pl->stem_direct = 0;
   pl->ncta = 1;
   if (pl->impl == 2) {
     rc = conv2_plan_setup(pl, d, h_out, w_out, im2col, encTiled, residual, y);
@@ -444,6 +451,12 @@ extern "C" int yolo_conv_fwd(const void* plan_host, uint32_t* status, yb_stream_
 #undef YB_CONV_CASE
   yb_set_error("conv fwd: no kernel for block_n %d kc %d", pl->block_n, pl->kc);
   return YB_ERR_UNSUPPORTED;
+}
+
+extern "C" int yolo_conv_fwd_stem(const void* plan_host, const float* x_nchw, uint32_t* status, yb_stream_t stream) {
+  const ConvPlan* pl = static_cast<const ConvPlan*>(plan_host);
+  YB_REQUIRE(pl && pl->magic == PLAN_MAGIC, "conv stem: plan not initialised");
+  return conv2_launch_stem(pl, x_nchw, status, (cudaStream_t)stream);
 }
 
 extern "C" int yolo_conv_fwd_simt(const yolo_conv_desc* d, const void* x, const void* w_packed,

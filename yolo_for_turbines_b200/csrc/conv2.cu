@@ -84,8 +84,14 @@ __device__ __forceinline__ void bn_act32(const uint32_t (&v)[32], float (&o)[32]
   }
 }
 
-template <int BLOCK_N, int KC, int NCTA>
-__global__ void __launch_bounds__(CONV2_THREADS, 1)
+constexpr int STEM_GATHER_WARPS = 4;  // STEM mode: warps 10..13 build the A tile from the fp32 NCHW image
+
+// STEM = true: the network's first conv (Cin = 3, 3x3/s1/p1) without the patch-matrix round trip through HBM.
+// There is no A tensor map: four extra warps gather each output pixel PAIR's 2 x 27 taps straight from the
+// NCHW fp32 input, convert to bf16 and write the 128-byte K-major row (pair-folded layout, 128B swizzle) into
+// the ring; fence.proxy.async hands it to the tensor core.  The NaN-input flag (model.py:175) is raised here.
+template <int BLOCK_N, int KC, int NCTA, bool STEM = false>
+__global__ void __launch_bounds__(CONV2_THREADS + (STEM ? STEM_GATHER_WARPS * 32 : 0), 1)
 k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   using C = Cfg<BLOCK_N, KC, NCTA>;
   extern __shared__ uint8_t smem_raw[];
@@ -112,7 +118,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     tma_prefetch_desc(&p.tmY);
     if (p.has_residual) tma_prefetch_desc(&p.tmR);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), STEM ? 1 + STEM_GATHER_WARPS : 1);  // + one arrive per gather warp
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -152,9 +158,11 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         if (elect_one()) {
-          if (leader) mbar_expect_tx(full_bar(s), C::STAGE_BYTES * NCTA);
+          if (leader) mbar_expect_tx(full_bar(s), (STEM ? C::B_BYTES : C::STAGE_BYTES) * NCTA);
           const uint32_t sa = smem_base + s * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-          if constexpr (NCTA == 1) {
+          if constexpr (STEM) {
+            tma_load_2d(&p.tmB, full_bar(s), sb, kb * KC, nb0);
+          } else if constexpr (NCTA == 1) {
             if (p.a_im2col) tma_load_im2col_4d(&p.tmA, full_bar(s), sa, cc * KC, cw, ch, img, (uint16_t)tq, (uint16_t)tr);
             else tma_load_2d(&p.tmA, full_bar(s), sa, cc * KC, m0);
             tma_load_2d(&p.tmB, full_bar(s), sb, kb * KC, nb0);
@@ -197,6 +205,61 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
       }
+    }
+  } else if (STEM && warp >= 2 + EPI_WARPS) {
+    // ===== STEM gather warps: one thread per A row = one output pixel pair =====
+    if constexpr (STEM) {
+      const int gr = (warp - 2 - EPI_WARPS) * 32 + lane;
+      const int W = p.stem_w, H = p.stem_h, W2 = W >> 1;
+      const size_t plane = size_t(H) * W;
+      int s = 0;
+      uint32_t ph = 0;
+      bool saw_nan = false;
+      for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
+        const int m = (t / p.tiles_n) * BLOCK_M + gr;  // pixel-pair index (tiles_n == 1 for the stem)
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t row_addr = smem_base + s * C::STAGE_BYTES + gr * 128;
+        const bool valid = m < p.M;
+        const int b = valid ? m / (H * W2) : 0;
+        const int rem = valid ? m - b * (H * W2) : 0;
+        const int i = rem / W2, j0 = (rem - i * W2) * 2;
+        const float* xb = p.stem_x + size_t(b) * 3 * plane;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int j = j0 + half;
+          float v[32];
+#pragma unroll
+          for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const int ii = i + kh - 1;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const int jj = j + kw - 1;
+              const bool in = valid && ii >= 0 && ii < H && jj >= 0 && jj < W;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const float xv = in ? __ldg(xb + size_t(c) * plane + size_t(ii) * W + jj) : 0.f;
+                v[(kh * 3 + kw) * 3 + c] = xv;
+                if (kh == 1 && kw == 1) saw_nan |= (xv != xv);
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t chunk = uint32_t(half * 4 + q) ^ uint32_t(gr & 7);
+            const uint32_t w0 = pack_bf16(v[8 * q + 0], v[8 * q + 1]), w1 = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+            const uint32_t w2 = pack_bf16(v[8 * q + 4], v[8 * q + 5]), w3 = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + (chunk << 4)), "r"(w0), "r"(w1),
+                         "r"(w2), "r"(w3) : "memory");
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to tcgen05.mma's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(full_bar(s));
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+      if (saw_nan) atomicOr(p.status, YB_STATUS_NAN_INPUT);
     }
   } else {
     // ===== epilogue: group g = (warp-2)/4 owns TMEM accumulator g and every second tile; each warp works
@@ -350,13 +413,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   if (warp == 1) tmem_dealloc_n<NCTA>(tmem_base, C::TMEM_COLS);
 }
 
-template <int BN, int KC, int NCTA>
+template <int BN, int KC, int NCTA, bool STEM = false>
 int launch2(const ConvPlan* pl, const ConvKParams2& kp, cudaStream_t stream) {
-  auto kern = k_conv_v2<BN, KC, NCTA>;
+  auto kern = k_conv_v2<BN, KC, NCTA, STEM>;
   YB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)pl->grid2);
-  cfg.blockDim = dim3(CONV2_THREADS);
+  cfg.blockDim = dim3(CONV2_THREADS + (STEM ? STEM_GATHER_WARPS * 32 : 0));
   cfg.dynamicSmemBytes = (size_t)pl->smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -387,11 +450,13 @@ int smem_bytes_v2(int bn, int kc, int ncta, int stages) {
 int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out, int im2col, PFN_encodeTiled encTiled,
                      const void* residual, void* y) {
   const int kc = pl->kc;
+  const bool stem = d->stem_c > 0;
   // default: a cta_group::2 pair (measured faster or equal on every YOLOv3 layer); 1 forces single CTAs
   int ncta = d->cta_pair_hint == 1 ? 1 : 2;
   int bn = pl->block_n;
   if (ncta == 2 && d->block_n_hint == 0 && d->c_out_pad % 256 == 0) bn = 256;  // a pair splits the weight tile
   if (ncta == 2 && bn < 64) ncta = 1;
+  if (stem) ncta = 1;  // HBM-bound layer; keeps the gather warps' arrivals CTA-local
   const long long M = (long long)d->batch * h_out * w_out;
   const int tiles_m = (int)((M + BLOCK_M * ncta - 1) / (BLOCK_M * ncta));
   const int tiles_n = d->c_out_pad / bn;
@@ -408,7 +473,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   YB_REQUIRE(smem <= 227 * 1024, "conv v2: %d stages do not fit shared memory (block_n %d)", stages, bn);
 
   ConvKParams2& kp = pl->kp2;
-  kp.tmA = pl->kp.tmA;  // same A geometry as v1 (128-row boxes of KC channels)
+  kp.tmA = pl->kp.tmA;  // same A geometry as v1 (128-row boxes of KC channels); unused by the stem
   // weight tile: BLOCK_N / NCTA rows per CTA
   {
     const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -454,6 +519,14 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   kp.ksize = d->ksize; kp.stride = d->stride; kp.pad = d->pad; kp.ksize_w = yb_kw(d); kp.stride_w = yb_sw(d);
   kp.act = d->act; kp.has_residual = d->has_residual; kp.upsample2x = d->upsample2x;
   kp.out_fp32 = d->out_fp32; kp.check_nan = d->check_nan; kp.a_im2col = im2col;
+  kp.stem_x = nullptr; kp.stem_h = d->h_in; kp.stem_w = d->w_in * 2;
+  pl->stem_direct = stem ? 1 : 0;
+  if (stem) {
+    YB_REQUIRE(bn == 64 && kc == 64 && d->stem_c == 3 && d->ksize == 1 && tiles_n == 1 && !d->has_residual && !direct,
+               "conv stem: needs the pair-folded 3->32 stem geometry (c_in 64, c_out 64)");
+    stages = stages > 6 ? 6 : stages;
+    kp.stages = stages;
+  }
 
   int dev = 0, sms = 148;
   YB_CHECK_CUDA(cudaGetDevice(&dev));
@@ -469,7 +542,17 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   return YB_OK;
 }
 
+int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status, cudaStream_t stream) {
+  YB_REQUIRE(pl->stem_direct && pl->block_n == 64 && pl->kc == 64 && pl->ncta == 1, "conv stem: plan is not a stem plan");
+  YB_REQUIRE(x_nchw && status, "conv stem: null pointer");
+  ConvKParams2 kp = pl->kp2;
+  kp.status = status;
+  kp.stem_x = x_nchw;
+  return launch2<64, 64, 1, true>(pl, kp, stream);
+}
+
 int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream) {
+  YB_REQUIRE(!pl->stem_direct, "conv fwd: stem plans are launched with yolo_conv_fwd_stem");
   ConvKParams2 kp = pl->kp2;
   kp.status = status;
 #define YB_L2(BN, KC)                                                        \

@@ -45,12 +45,14 @@ struct ConvKParams2 {
   int ksize, stride, pad;
   int ksize_w, stride_w;
   int act, has_residual, upsample2x, out_fp32, check_nan, a_im2col;
+  const float* stem_x;  // STEM mode: fp32 NCHW image (set per launch)
+  int stem_h, stem_w;
 };
 
 struct ConvPlan {
   ConvKParams kp;
   ConvKParams2 kp2;
-  int impl, ncta, grid2;
+  int impl, ncta, grid2, stem_direct;
   const void* w;
   yolo_conv_desc d;
   int block_n, kc, grid_x, grid_y, smem_bytes;
@@ -70,3 +72,4 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
 int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out, int im2col, PFN_encodeTiled encTiled,
                      const void* residual, void* y);
 int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream);
+int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status, cudaStream_t stream);

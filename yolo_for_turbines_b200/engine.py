@@ -72,6 +72,8 @@ class PackedConv:
         self.c_out_run = self.c_out * (2 if self.fold else 1)
         self.c_out_pad_run = self.c_out_pad * (2 if self.fold else 1)
         self.kw_run = 2 if self.fold_s2 else self.k_eff
+        # fused stem: the kernel gathers the 3x3x3 taps from the NCHW image itself (needs the folded layout)
+        self.stem_direct = bool(self.stem and self.fold and self.c_in == 3 and self.c_out == 32)
         self.w = torch.empty(self.c_out_pad_run * self.k_eff * self.kw_run * self.c_in_run, dtype=torch.bfloat16,
                              device=device)
         self.scale = torch.empty(self.c_out_pad_run, dtype=torch.float32, device=device)
@@ -288,8 +290,11 @@ class ForwardPlan:
         self.total_bytes = 0
         roots = sorted({id(t.resolve()[0]): t.resolve()[0] for op in self.ops for t in (op.src, op.dst, op.res) if t}.values(),
                        key=lambda r: r.first)
+        self.stem_direct = bool(first_pc.stem_direct and engine.stem_direct)
         for r in roots:
             need = B * r.H * r.W * r.C * (4 if r.fp32 else 2)
+            if self.stem_direct and r is self.input_root:
+                need = 256  # no patch matrix: the stem kernel reads the image directly
             best = None
             for ent in pool:
                 if ent[1] <= r.first and ent[0].numel() >= need and (best is None or ent[0].numel() < best[0].numel()):
@@ -330,6 +335,8 @@ class ForwardPlan:
             d.a_mode, d.block_n_hint, d.stages_hint = 0, engine.block_n_hint, engine.stages_hint
             d.impl_hint, d.cta_pair_hint = engine.impl_hint, engine.cta_pair_hint
             x_ptr = sroot.buf.data_ptr() + soff * 2
+            if self.stem_direct and op is self.ops[0]:
+                d.stem_c, x_ptr = 3, 0
             y_ptr = droot.buf.data_ptr() + doff * (4 if op.dst.fp32 else 2)
             r_ptr = None
             if op.res is not None:
@@ -340,7 +347,7 @@ class ForwardPlan:
                                                   C.c_void_p(y_ptr))
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = use_graph
-        self.launches_per_forward = len(self.ops) + 1
+        self.launches_per_forward = len(self.ops) + (0 if self.stem_direct else 1)
 
     # ------------------------------------------------------------------------------------------
     def head_views(self):
@@ -358,14 +365,18 @@ class ForwardPlan:
     def _launch_convs(self):
         st = stream_ptr(self.engine.device)
         sp = ptr(self.status)
-        for op in self.ops:
+        for op in (self.ops[1:] if self.stem_direct else self.ops):
             lib.yolo_conv_fwd(op.plan_ptr, sp, st)
 
     def _launch_input(self, x):
+        """Everything that reads the caller's tensor (its address changes per call, so it stays out of the CUDA
+        graph): the fused stem conv, or the patchify / NHWC conversion of the non-fused paths."""
         st = stream_ptr(self.engine.device)
         self.status.zero_()
         dst = ptr(self.input_root.buf)
-        if self.stem:
+        if self.stem_direct:
+            lib.yolo_conv_fwd_stem(self.ops[0].plan_ptr, ptr(x), ptr(self.status), st)
+        elif self.stem:
             lib.yolo_input_patchify(ptr(x), self.B, x.shape[1], self.H, self.W, dst, ptr(self.status), st)
         else:
             lib.yolo_nchw_to_nhwc_bf16(ptr(x), self.B, x.shape[1], self.H, self.W, self.input_act.C, self.input_root.C,
@@ -404,6 +415,7 @@ class Engine:
         self.model, self.device = model, torch.device(device)
         self.block_n_hint, self.stages_hint = 0, 0
         self.impl_hint, self.cta_pair_hint = 0, 0  # 0 = library defaults (include/yolo_b200.h)
+        self.stem_direct = os.environ.get("YOLO_B200_NO_FUSED_STEM") != "1"
         self.allow_fold = hasattr(model, "layers") and hasattr(model, "num_classes") and os.environ.get("YOLO_B200_NO_FOLD") != "1"
         self.packed: Dict[int, PackedConv] = {}
         blocks = [m for m in model.modules() if isinstance(m, CNNBlock)]
