@@ -224,27 +224,35 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         const int rem = valid ? m - b * (H * W2) : 0;
         const int i = rem / W2, j0 = (rem - i * W2) * 2;
         const float* xb = p.stem_x + size_t(b) * 3 * plane;
+        // the pair's two 3x3 windows span columns j0-1 .. j0+2: 9 (row, channel) lines of [left | mid.x mid.y | right],
+        // all loads issued before any use (one memory round trip per tile)
+        float xv[3][3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const int ii = i + kh - 1;
+            const bool rin = valid && ii >= 0 && ii < H;
+            const float* line = xb + size_t(c) * plane + size_t(rin ? ii : 0) * W + j0;
+            const float2 mid = rin ? __ldg(reinterpret_cast<const float2*>(line)) : make_float2(0.f, 0.f);
+            xv[c][kh][0] = (rin && j0 > 0) ? __ldg(line - 1) : 0.f;
+            xv[c][kh][1] = mid.x;
+            xv[c][kh][2] = mid.y;
+            xv[c][kh][3] = (rin && j0 + 2 < W) ? __ldg(line + 2) : 0.f;
+          }
+          saw_nan |= (xv[c][1][1] != xv[c][1][1]) | (xv[c][1][2] != xv[c][1][2]);  // each image element checked once
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          const int j = j0 + half;
           float v[32];
 #pragma unroll
           for (int k = 27; k < 32; ++k) v[k] = 0.f;
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-            const int ii = i + kh - 1;
+          for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const int jj = j + kw - 1;
-              const bool in = valid && ii >= 0 && ii < H && jj >= 0 && jj < W;
+            for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                const float xv = in ? __ldg(xb + size_t(c) * plane + size_t(ii) * W + jj) : 0.f;
-                v[(kh * 3 + kw) * 3 + c] = xv;
-                if (kh == 1 && kw == 1) saw_nan |= (xv != xv);
-              }
-            }
-          }
+              for (int c = 0; c < 3; ++c) v[(kh * 3 + kw) * 3 + c] = xv[c][kh][kw + half];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t chunk = uint32_t(half * 4 + q) ^ uint32_t(gr & 7);
