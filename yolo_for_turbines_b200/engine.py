@@ -415,7 +415,8 @@ class Engine:
         self.model, self.device = model, torch.device(device)
         self.block_n_hint, self.stages_hint = 0, 0
         self.impl_hint, self.cta_pair_hint = 0, 0  # 0 = library defaults (include/yolo_b200.h)
-        self.stem_direct = os.environ.get("YOLO_B200_NO_FUSED_STEM") != "1"
+        # fused stem (no patch matrix): correct but not faster yet (gather-warp bound, 0.43 vs 0.22 + 0.24 ms), so opt-in
+        self.stem_direct = os.environ.get("YOLO_B200_FUSED_STEM") == "1"
         self.allow_fold = hasattr(model, "layers") and hasattr(model, "num_classes") and os.environ.get("YOLO_B200_NO_FOLD") != "1"
         self.packed: Dict[int, PackedConv] = {}
         blocks = [m for m in model.modules() if isinstance(m, CNNBlock)]
