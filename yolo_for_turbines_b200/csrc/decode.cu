@@ -101,9 +101,31 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode_dense(const DecodeParams
   const long long pix0 = (long long)blockIdx.x * DEC_PIX;
   const int npix = (int)min((long long)DEC_PIX, total_pix - pix0);
   const float* src = p.head + pix0 * pitch;
-  for (int i = threadIdx.x; i < npix * pitch; i += DEC_THREADS) {
-    const int r = i / pitch, c = i - r * pitch;
-    s_head[r * sp + c] = src[i];
+  if ((pitch & 3) == 0) {  // 16-byte loads, 8 in flight per thread before the (scalar, padded-row) smem stores
+    const int nvec = npix * pitch / 4;
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    for (int base = threadIdx.x; base < nvec; base += DEC_THREADS * 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * DEC_THREADS;
+        v[u] = i < nvec ? __ldg(src4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * DEC_THREADS;
+        if (i < nvec) {
+          const int e = i * 4, r = e / pitch, c = e - r * pitch;
+          float* dst = s_head + r * sp + c;
+          dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w;
+        }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < npix * pitch; i += DEC_THREADS) {
+      const int r = i / pitch, c = i - r * pitch;
+      s_head[r * sp + c] = src[i];
+    }
   }
   __syncthreads();
   const int C = 5 + p.nc;

@@ -192,6 +192,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
   __shared__ float s_carea[32];
   __shared__ uint32_t s_row[32], s_binx[32], s_biny[32];
   __shared__ uint32_t s_alive, s_cgen, s_kept, s_win[4];
+  __shared__ uint32_t s_bins[NMS_QPT][NMS_THREADS];  // 32 KB
   __shared__ int s_cpos[32];
   __shared__ int s_end;
   const bool thr_pos = thr > 0.f;
@@ -217,20 +218,17 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
     }
     const int m = s1 - s0;
     const bool regpath = m <= NMS_REG_CAP;
-    float4 bx[NMS_QPT];
-    uint32_t bins[NMS_QPT];
+    // per owned box: packed spatial bins in shared memory (slot-major => conflict free), dead / general bits in
+    // two registers.  Coordinates are re-read from global memory only for the rare box that shares bins with a
+    // survivor, so the per-round loop can walk just the live later slots (a dynamic index, hence not registers).
     uint32_t supp = 0, gen = thr_pos ? 0u : 0xffffu;
     if (regpath) {
-#pragma unroll
       for (int j = 0; j < NMS_QPT; ++j) {
         const int q = s0 + j * NMS_THREADS + tid;
         if (q < s1) {
-          bx[j] = cbox[q];
           if (suppressed[q] & 2) gen |= 1u << j;
-          bins[j] = nms_pack_bins(bx[j]);
+          s_bins[j][tid] = nms_pack_bins(cbox[q]);
         } else {
-          bx[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          bins[j] = 0;
           supp |= 1u << j;
         }
       }
@@ -316,24 +314,30 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
             const uint32_t ri = s_row[i];
             if ((alive >> i) & 1u) { kept |= 1u << i; alive &= ~ri; }
           }
-          if ((kept >> lane) & 1u) keep[val2[s_cpos[lane]]] = 1;  // keep[] is zero-initialised
           if (lane == 0) s_kept = kept;
+          if ((kept >> lane) & 1u) keep[val2[s_cpos[lane]]] = 1;  // keep[] is zero-initialised
         }
         __syncthreads();
-        // (c) the chunk's survivors knock out the later boxes this thread owns
+        // (c) the chunk's survivors knock out the later boxes this thread owns: only live slots are visited
         const uint32_t kept = s_kept;
         const uint32_t kgen = kept & s_cgen;
-#pragma unroll
-        for (int j = 0; j < NMS_QPT; ++j) {
-          if (j * NMS_THREADS + tid >= f_new && !((supp >> j) & 1u)) {
+        {
+          // slots whose position j*NT + tid is >= f_new: all slots above jf, plus slot jf itself when tid >= rf
+          const int jf = f_new / NMS_THREADS, rf = f_new - jf * NMS_THREADS;
+          uint32_t later = (jf >= NMS_QPT) ? 0u : (0xffffu << jf) & 0xffffu;
+          if (jf < NMS_QPT && tid < rf) later &= ~(1u << jf);
+          for (uint32_t act = later & ~supp; act; act &= act - 1) {
+            const int j = __ffs(act) - 1;
             const bool qgen = (gen >> j) & 1u;
-            uint32_t cand = qgen ? kept : ((nms_candidates(bins[j], s_binx, s_biny) & kept) | kgen);
+            uint32_t cand = qgen ? kept : ((nms_candidates(s_bins[j][tid], s_binx, s_biny) & kept) | kgen);
             if (cand) {
-              const float al = area[s0 + j * NMS_THREADS + tid];
+              const int q = s0 + j * NMS_THREADS + tid;
+              const float4 b = cbox[q];
+              const float al = area[q];
               while (cand) {
                 const int t = __ffs(cand) - 1;
                 cand &= cand - 1;
-                if (nms_pair(s_cbox[t], s_carea[t], bx[j], al, qgen || ((kgen >> t) & 1u), thr, thr_pos)) {
+                if (nms_pair(s_cbox[t], s_carea[t], b, al, qgen || ((kgen >> t) & 1u), thr, thr_pos)) {
                   supp |= 1u << j;
                   break;
                 }
