@@ -125,10 +125,11 @@ def test_nms_properties_at_full_size():
 
 
 @pytest.mark.parametrize("n,nc,conf,wh", [(7000, 1, 0.3, (0.02, 0.1)), (8192, 1, 0.0, (0.02, 0.08)), (8193, 1, 0.0, (0.02, 0.08)),
-                                          (23000, 1, 0.01, (0.02, 0.12)), (30000, 2, 0.2, (0.05, 0.4))])
+                                          (23000, 1, 0.01, (0.02, 0.12)), (30000, 2, 0.2, (0.05, 0.4)),
+                                          (24576, 1, -1.0, (0.02, 0.06)), (24577, 1, -1.0, (0.02, 0.06)), (40000, 1, 0.4, (0.02, 0.1))])
 def test_long_single_class_segments_match_oracle(oracle_c, n, nc, conf, wh):
     """One (image, class) segment holding thousands of boxes: the regime of a random-init model (argmax collapses
-    onto a few classes).  <= 8192 boxes take the register-resident path, longer ones the global-memory path."""
+    onto a few classes).  <= 24 576 boxes take the fast (owned-slot) path, longer ones the global-memory path."""
     from yolo_for_turbines_b200.utils import batched_nms
 
     b = synth.synth_boxes(n, nc, 4242 + n, tie_frac=0.02, wh=wh)

@@ -163,7 +163,7 @@ __device__ __forceinline__ bool nms_pair(const float4 e, const float ae, const f
 //       with it -- disjoint extents cannot suppress (iou == 0 < thr) -- so the usual cost per (box,
 //       chunk) is a few shared-memory words instead of up to 32 IoU tests.
 constexpr int NMS_WARPS = NMS_THREADS / 32;
-constexpr int NMS_QPT = 16;
+constexpr int NMS_QPT = 48;  // owned boxes per thread: 48 x 512 = 24 576 boxes per segment take the fast path
 constexpr int NMS_REG_CAP = NMS_THREADS * NMS_QPT;
 
 __device__ __forceinline__ int nms_bin(float v) {  // monotone and clamped => overlapping extents share a bin
@@ -192,7 +192,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
   __shared__ float s_carea[32];
   __shared__ uint32_t s_row[32], s_binx[32], s_biny[32];
   __shared__ uint32_t s_alive, s_cgen, s_kept, s_win[4];
-  __shared__ uint32_t s_bins[NMS_QPT][NMS_THREADS];  // 32 KB
+  extern __shared__ uint32_t s_bins[];  // [NMS_QPT][NMS_THREADS] packed spatial bins, 96 KB (dynamic)
   __shared__ int s_cpos[32];
   __shared__ int s_end;
   const bool thr_pos = thr > 0.f;
@@ -221,15 +221,15 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
     // per owned box: packed spatial bins in shared memory (slot-major => conflict free), dead / general bits in
     // two registers.  Coordinates are re-read from global memory only for the rare box that shares bins with a
     // survivor, so the per-round loop can walk just the live later slots (a dynamic index, hence not registers).
-    uint32_t supp = 0, gen = thr_pos ? 0u : 0xffffu;
+    uint64_t supp = 0, gen = thr_pos ? 0ull : ~0ull;
     if (regpath) {
       for (int j = 0; j < NMS_QPT; ++j) {
         const int q = s0 + j * NMS_THREADS + tid;
         if (q < s1) {
-          if (suppressed[q] & 2) gen |= 1u << j;
-          s_bins[j][tid] = nms_pack_bins(cbox[q]);
+          if (suppressed[q] & 2) gen |= 1ull << j;
+          s_bins[j * NMS_THREADS + tid] = nms_pack_bins(cbox[q]);
         } else {
-          supp |= 1u << j;
+          supp |= 1ull << j;
         }
       }
     }
@@ -245,7 +245,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
           const int blk = wb + d;
           if ((blk % NMS_WARPS) == warp) {
             uint32_t al = 0;
-            if (blk * 32 < m) al = __ballot_sync(0xffffffffu, ((supp >> (blk / NMS_WARPS)) & 1u) == 0);
+            if (blk * 32 < m) al = __ballot_sync(0xffffffffu, ((supp >> (blk / NMS_WARPS)) & 1ull) == 0);
             if (d == 0) al &= ~((1u << (f & 31)) - 1u);
             if (lane == 0) s_win[d] = al;
           }
@@ -324,12 +324,13 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
         {
           // slots whose position j*NT + tid is >= f_new: all slots above jf, plus slot jf itself when tid >= rf
           const int jf = f_new / NMS_THREADS, rf = f_new - jf * NMS_THREADS;
-          uint32_t later = (jf >= NMS_QPT) ? 0u : (0xffffu << jf) & 0xffffu;
-          if (jf < NMS_QPT && tid < rf) later &= ~(1u << jf);
-          for (uint32_t act = later & ~supp; act; act &= act - 1) {
-            const int j = __ffs(act) - 1;
-            const bool qgen = (gen >> j) & 1u;
-            uint32_t cand = qgen ? kept : ((nms_candidates(s_bins[j][tid], s_binx, s_biny) & kept) | kgen);
+          constexpr uint64_t ALL = (NMS_QPT == 64) ? ~0ull : ((1ull << NMS_QPT) - 1ull);
+          uint64_t later = (jf >= NMS_QPT) ? 0ull : (ALL << jf) & ALL;
+          if (jf < NMS_QPT && tid < rf) later &= ~(1ull << jf);
+          for (uint64_t act = later & ~supp; act; act &= act - 1) {
+            const int j = __ffsll((long long)act) - 1;
+            const bool qgen = (gen >> j) & 1ull;
+            uint32_t cand = qgen ? kept : ((nms_candidates(s_bins[j * NMS_THREADS + tid], s_binx, s_biny) & kept) | kgen);
             if (cand) {
               const int q = s0 + j * NMS_THREADS + tid;
               const float4 b = cbox[q];
@@ -338,7 +339,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
                 const int t = __ffs(cand) - 1;
                 cand &= cand - 1;
                 if (nms_pair(s_cbox[t], s_carea[t], b, al, qgen || ((kgen >> t) & 1u), thr, thr_pos)) {
-                  supp |= 1u << j;
+                  supp |= 1ull << j;
                   break;
                 }
               }
@@ -586,7 +587,9 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int grid = sms * 3;
   if (grid > total) grid = total;
-  k_nms_segments<<<grid, NMS_THREADS, 0, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts,
+  const size_t nms_smem = size_t(NMS_QPT) * NMS_THREADS * sizeof(uint32_t);
+  YB_CHECK_CUDA(cudaFuncSetAttribute(k_nms_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
+  k_nms_segments<<<grid, NMS_THREADS, nms_smem, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts,
                                                    nseg, n_valid, iou_thr, w.suppressed, w.keep, class_bits > 0);
   YB_CHECK_LAUNCH();
 
