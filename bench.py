@@ -43,6 +43,16 @@ def algorithmic_gflop(size: int, nc: int) -> float:
     return GFLOP_PER_IMAGE[(416, nc if nc in (2, 80) else 80)] * (size / 416.0) ** 2
 
 
+def conv_traffic_per_launch(size, nc, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv launch from the committed ncu capture of this
+    workload (profiles/conv_traffic.json); None for workloads that were not captured."""
+    p = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if (size, nc, batch) != (416, 80, 64) or not os.path.isfile(p):
+        return None
+    d = json.load(open(p))
+    return (d["dram_read_bytes_per_step"] + d["dram_write_bytes_per_step"]) / d["conv_launches"]
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -379,12 +389,12 @@ def main():
             "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
                     "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": (plan.launches_per_forward + 3 + nms_launch_count(B)) * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "k_conv_tcgen05 (75 launches per step)",
+            "roofline": {"bound": "tensor", "kernel": "k_conv_v2 (75 launches per step)",
                          "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / pk["bf16_sustained"], "frac_of_burst_peak": achieved / pk["bf16"],
                          "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                          "ms_per_step_conv": ms_conv, "conv_share_of_step": ms_conv / (ms_dev / args.steps),
-                         "traffic": None},
+                         "traffic": conv_traffic_per_launch(S, args.classes, B)},
             "clocks": clocks,
             "stages": {
                 "nms": {"ms_per_step": ms_nms, "candidates_per_sec": B * n_cand / (ms_nms / 1e3), "unit": "boxes/s",
