@@ -203,6 +203,74 @@ int yolo_loss_fwd(float* pred, const int64_t* pstrides5_host, float* target, con
                   int batch, int S, int nc, const float* anchors6_host, int mutate, double* sums6,
                   yb_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * Training step (SURVEY config #4): replaces what autograd + cuDNN run for
+ * `model.train(); out = model(x); loss.backward(); optimizer.step()`
+ * (code/train.py:42-69).  Activations stay NHWC bf16, statistics fp32/fp64,
+ * parameters, gradients and optimizer state fp32.
+ *
+ * Forward of one CNNBlock in train mode (model.py:80-86): yolo_conv_fwd with
+ * scale=1/bias=0/act none writes the raw conv output z; yolo_bn_stats +
+ * yolo_bn_finalize give the nn.BatchNorm2d batch statistics (and update the
+ * running ones); yolo_bn_act_fwd applies BN + activation (+ residual, + the
+ * 2x nearest upsample store of model.py:222).
+ * Backward: yolo_bn_act_bwd turns the gradient of the block output into the
+ * gradient dz of the raw conv output (+ dgamma, dbeta); the data gradient is
+ * yolo_conv_fwd again on dz with transposed / flipped weights (stride-2
+ * layers: on the zero-stuffed copy `stuffed`); yolo_wgrad is the weight
+ * gradient GEMM on tcgen05 (MN-major operands straight from the NHWC tensors).
+ * ------------------------------------------------------------------------- */
+/* sums2c[2c] += sum_p z[p][c], sums2c[2c+1] += sum_p z[p][c]^2 (device doubles, caller zeroes them)          */
+int yolo_bn_stats(const void* z, long long P, int C, int pitch, double* sums2c, yb_stream_t stream);
+/* batch mean / rstd (biased variance), scale = gamma*rstd, bias = beta - mean*scale; running stats updated with
+ * `momentum` and the unbiased variance (nn.BatchNorm2d, model.py:61); running_* may be NULL.                  */
+int yolo_bn_finalize(const double* sums2c, long long P, int C, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
+                     float* scale, float* bias, yb_stream_t stream);
+/* y = act(z*scale + bias) (+ residual); up2x: z is (B,h,w,C) and every pixel is stored to its 2x2 block of the
+ * (B,2h,2w,*) tensor y (nn.Upsample + torch.cat, model.py:189-191, :222)                                       */
+int yolo_bn_act_fwd(const void* z, long long P, int C, int z_pitch, const float* scale, const float* bias, int act,
+                    const void* residual, int res_pitch, void* y, int y_pitch, int up2x, int h, int w,
+                    yb_stream_t stream);
+/* dA: gradient of the block output (up2x: taken as the 2x2 block sums of a (B,2h,2w,*) tensor = backward of
+ * nn.Upsample).  Writes dz (bf16), dgamma/dbeta (fp32, assigned) and, when `stuffed` != NULL, dz zero-stuffed
+ * to (B,2h,2w,*) for the stride-2 convs' data gradient.  sums2c: 2C zeroed doubles, m1m2: 2C floats scratch.  */
+int yolo_bn_act_bwd(const void* dA, int dA_pitch, int up2x, const void* z, int z_pitch, long long P, int C, int h,
+                    int w, const float* scale, const float* bias, const float* mean, const float* rstd, int act,
+                    double* sums2c, float* dgamma, float* dbeta, float* m1m2, void* dz, int dz_pitch,
+                    void* stuffed, int stuffed_pitch, yb_stream_t stream);
+/* bias gradient of the head conv (model.py:137, bias=True): dbias[c] = sum_p dz[p][c], c < C                   */
+int yolo_bias_grad(const void* dz, long long P, int C_pad, int pitch, int C, double* sums2c, float* dbias,
+                   yb_stream_t stream);
+/* Weight gradient GEMM.  `desc` is the FORWARD geometry of the layer (yolo_conv_desc; in_pitch = pitch of x);
+ * x = the layer input (NHWC bf16), dz = gradient of its raw output [P][dz_pitch] bf16; dw_packed =
+ * [c_out_pad][k*k][c_in] fp32, ACCUMULATED (split-K partial tiles are added with red.global).                */
+size_t yolo_wgrad_plan_bytes(void);
+int yolo_wgrad_plan_init(void* plan_host, size_t plan_bytes, const yolo_conv_desc* desc, const void* x,
+                         const void* dz, int dz_pitch, float* dw_packed, int splits_hint);
+int yolo_wgrad(const void* plan_host, yb_stream_t stream);
+/* info6 = n-tile, stages, splits, tiles_m, tiles_n, CTAs */
+int yolo_wgrad_plan_info(const void* plan_host, int32_t* info6);
+/* packed fp32 dW -> nn.Conv2d.weight.grad layout (OIHW, assigned); stem=1: packed rows are the 32-wide patch
+ * order of yolo_input_patchify                                                                                */
+int yolo_unpack_wgrad(const float* packed, int c_out, int c_in, int ksize, int c_in_pad, int stem,
+                      float* grad_oihw, yb_stream_t stream);
+/* OIHW fp32 -> the data-gradient weight pack [rows_pad >= c_in][k*k][cols_pad >= c_out] bf16 with
+ * out[ci][tap][co] = w[co][ci][k*k-1-tap]: yolo_conv_fwd on dz with this pack computes d conv / d input.   */
+int yolo_pack_weights_dgrad(const float* w_oihw, int c_out, int c_in, int ksize, int rows_pad, int cols_pad,
+                            void* w_packed, yb_stream_t stream);
+/* torch.optim.SGD(momentum, weight_decay) (train.py:171-172) on flat fp32 buffers: g' = g*grad_scale + wd*p;
+ * buf = first_step ? g' : momentum*buf + g'; p -= lr*buf                                                      */
+int yolo_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
+                  float weight_decay, float grad_scale, int first_step, yb_stream_t stream);
+/* K8 backward: gradient of the summed, lambda-weighted YOLOLoss terms of one scale (loss.py:54-81) w.r.t. pred.
+ * sums6 = the device sums yolo_loss_fwd produced for the same pred/target; dpred gets all 5+nc entries of every
+ * cell (element strides dstrides5; out_bf16 selects bf16 or fp32), scaled by grad_scale.                      */
+int yolo_loss_bwd(const float* pred, const int64_t* pstrides5_host, const float* target,
+                  const int64_t* tstrides5_host, int batch, int S, int nc, const float* anchors6_host,
+                  const double* sums6, float grad_scale, void* dpred, const int64_t* dstrides5_host, int out_bf16,
+                  yb_stream_t stream);
+
 /* Stable LSD radix sort of (u64 key, i32 value) pairs on bits [0,end_bit)
  * (end_bit multiple of 8); K5's building block, exported for tests and for
  * the mAP score ordering.  n_dev: device int32 holding the live count (<=max_n).

@@ -69,15 +69,21 @@ def _act(x: torch.Tensor, activation: str) -> torch.Tensor:
     raise ValueError(f"Unsupported activation: {activation}")  # model.py:68
 
 
+_TRAINING = False  # set by forward(training=True): nn.BatchNorm2d in train mode (batch statistics)
+
+
 def _cnn_block(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, k: int, stride: int,
                activation: str, bn_act: bool = True) -> torch.Tensor:
-    """model.py:80-86 in eval mode (BatchNorm uses running statistics)."""
+    """model.py:80-86.  Eval mode: BatchNorm uses the running statistics; train mode (model.train(), train.py:38):
+    batch statistics, and the running ones in `sd` are updated in place as nn.BatchNorm2d does."""
     pad = 1 if k == 3 else 0  # model.py:201
     if not bn_act:
         return F.conv2d(x, sd[prefix + "conv.weight"], sd[prefix + "conv.bias"], stride, pad)
     y = F.conv2d(x, sd[prefix + "conv.weight"], None, stride, pad)
     y = F.batch_norm(y, sd[prefix + "batch_norm.running_mean"], sd[prefix + "batch_norm.running_var"],
-                     sd[prefix + "batch_norm.weight"], sd[prefix + "batch_norm.bias"], False, 0.1, 1e-5)
+                     sd[prefix + "batch_norm.weight"], sd[prefix + "batch_norm.bias"], _TRAINING, 0.1, 1e-5)
+    if _TRAINING and prefix + "batch_norm.num_batches_tracked" in sd:
+        sd[prefix + "batch_norm.num_batches_tracked"] += 1
     return _act(y, activation)
 
 
@@ -91,8 +97,17 @@ def _residual_stage(sd, prefix, x, repeats, activation, use_residual=True):
 
 
 def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, num_classes: int = 80,
-            activation: str = "leaky_relu") -> List[torch.Tensor]:
-    """YOLOv3.forward (model.py:172-193), eval mode, from a reference-keyed state_dict."""
+            activation: str = "leaky_relu", training: bool = False) -> List[torch.Tensor]:
+    """YOLOv3.forward (model.py:172-193) from a reference-keyed state_dict; eval mode unless training=True."""
+    global _TRAINING
+    _TRAINING = bool(training)
+    try:
+        return _forward(sd, x, num_classes, activation)
+    finally:
+        _TRAINING = False
+
+
+def _forward(sd, x, num_classes, activation):
     assert torch.sum(torch.isnan(x)) == 0  # model.py:175
     outs, routes = [], []
     i = 0  # index into the reference's nn.ModuleList
@@ -282,6 +297,53 @@ def yolo_loss(predictions: torch.Tensor, targets: torch.Tensor, anchors: torch.T
         box_loss = F.mse_loss(predictions[..., :4][obj], targets[..., :4][obj])
         class_loss = F.cross_entropy(predictions[..., 5:][obj], targets[..., 5][obj].long())
     return [5 * box_loss, 1 * object_loss, 0.5 * no_obj_loss, 1 * class_loss]
+
+
+def train_step_grads(sd: Dict[str, torch.Tensor], x: torch.Tensor, targets: Sequence[torch.Tensor], anchors,
+                     num_classes: int, activation: str = "leaky_relu"):
+    """The autograd part of one training step (train.py:53-67) in fp32: model.train() forward, YOLOLoss on the three
+    scales with anchors scaled by the grid size (train.py:195-197), loss = sum of all twelve terms, backward.
+    `sd` is modified like the module would be (running statistics, num_batches_tracked).  Returns
+    ([box, object, no_object, class] summed over scales, {parameter key: gradient})."""
+    params = {k: v for k, v in sd.items() if k.endswith((".weight", ".bias"))}
+    for v in params.values():
+        v.requires_grad_(True)
+        v.grad = None
+    outs = forward(sd, x, num_classes, activation, training=True)
+    terms = [torch.zeros(()) for _ in range(4)]
+    for o, t, a in zip(outs, targets, anchors):
+        S = o.shape[2]
+        per = yolo_loss(o, t.clone(), torch.tensor(a, dtype=torch.float32) * S)
+        terms = [acc + v for acc, v in zip(terms, per)]
+    sum(terms).backward()
+    grads = {k: v.grad.detach().clone() for k, v in params.items()}
+    for v in params.values():
+        v.requires_grad_(False)
+        v.grad = None
+    return [float(v.detach()) for v in terms], grads
+
+
+def synth_targets(batch: int, size: int, num_classes: int, seed: int, per_scale: int = 4, ignore: int = 1):
+    """Synthetic YOLO targets (B,3,S,S,6) for S = size/32, /16, /8: `per_scale` object cells
+    per image and scale with x,y in (0,1), w,h in (0.5,4) grid units, obj 1, a class label; `ignore` cells of -1."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for S in (size // 32, size // 16, size // 8):
+        t = torch.zeros(batch, 3, S, S, 6)
+        for b in range(batch):
+            cells = torch.randperm(3 * S * S, generator=g)[: per_scale + ignore]
+            for n, c in enumerate(cells.tolist()):
+                a, r = divmod(c, S * S)
+                i, j = divmod(r, S)
+                if n < per_scale:
+                    t[b, a, i, j, 0:2] = torch.rand(2, generator=g)
+                    t[b, a, i, j, 2:4] = 0.5 + 3.5 * torch.rand(2, generator=g)
+                    t[b, a, i, j, 4] = 1.0
+                    t[b, a, i, j, 5] = float(torch.randint(0, num_classes, (1,), generator=g))
+                else:
+                    t[b, a, i, j, 4] = -1.0
+        out.append(t)
+    return out
 
 
 # --- Darknet weight file (model.py:162-170, 227-337) ------------------------------

@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
         "stages_hint", "impl_hint", "cta_pair_hint", "ksize_w", "stride_w", "pad_w_hi_plus1", "stem_c")]
 
 
-_P, _I, _F, _D, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t
+_P, _I, _F, _D, _SZ, _LL = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_longlong
 
 # name -> (restype, argtypes); every int-returning entry is error-checked by _Lib.__getattr__
 SIGNATURES = {
@@ -60,6 +60,20 @@ SIGNATURES = {
     "yolo_map_match": (_I, [_P, _I, _P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P]),
     "yolo_accuracy_counts": (_I, [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64), _I, _I, _I, _F, _P, _P]),
     "yolo_loss_fwd": (_I, [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _I, _P, _P]),
+    "yolo_bn_stats": (_I, [_P, _LL, _I, _I, _P, _P]),
+    "yolo_bn_finalize": (_I, [_P, _LL, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "yolo_bn_act_fwd": (_I, [_P, _LL, _I, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "yolo_bn_act_bwd": (_I, [_P, _I, _I, _P, _I, _LL, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
+    "yolo_bias_grad": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P]),
+    "yolo_wgrad_plan_bytes": (_SZ, []),
+    "yolo_wgrad_plan_init": (_I, [_P, _SZ, C.POINTER(ConvDesc), _P, _P, _I, _P, _I]),
+    "yolo_wgrad": (_I, [_P, _P]),
+    "yolo_wgrad_plan_info": (_I, [_P, C.POINTER(C.c_int32)]),
+    "yolo_unpack_wgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "yolo_pack_weights_dgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "yolo_sgd_step": (_I, [_P, _P, _P, _LL, _F, _F, _F, _F, _I, _P]),
+    "yolo_loss_bwd": (_I, [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _P, _F, _P,
+                           C.POINTER(C.c_int64), _I, _P]),
     "yolo_sort_workspace_bytes": (_SZ, [_I]),
     "yolo_sort_pairs": (_I, [_P, _P, _P, _I, _I, _P, _SZ, _P]),
 }

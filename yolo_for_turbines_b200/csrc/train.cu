@@ -1,0 +1,456 @@
+// Training-step kernels around the conv GEMMs (SURVEY config #4; reference: code/train.py:53-69 with
+// model.train()).  Everything here is HBM-bound NHWC bf16 row work:
+//
+//   forward   CNNBlock in train mode (model.py:80-86 with nn.BatchNorm2d batch statistics):
+//             z = conv(x) [tcgen05 kernel, bf16]  ->  k_bn_stats (sum z, sum z^2 per channel)
+//             -> k_bn_finalize (mean / rstd, running-stat update, scale/bias)  -> k_bn_act_fwd
+//             a = act(z*scale + bias) (+ residual) (optionally stored 2x2-replicated = nn.Upsample)
+//   backward  k_bn_act_bwd_reduce (sum dy, sum dy*xhat)  -> k_bn_bwd_finalize (dgamma, dbeta, means)
+//             -> k_bn_act_bwd_apply  dz = scale * (dy - mean(dy) - xhat * mean(dy*xhat))
+//             (optionally also zero-stuffed to 2x resolution: the stride-2 convs' dgrad input)
+//   k_unpack_wgrad   packed fp32 dW [Cout][tap][Cin] -> nn.Conv2d.weight.grad (OIHW)
+//   k_sgd            torch.optim.SGD(momentum, weight_decay) on the flat parameter buffer (train.py:171-172)
+//
+// Rows are handled 8 channels (one 16-byte load) per thread; per-channel sums go through shared-memory
+// double atomics and one global double atomic per channel per block.
+#include "common.cuh"
+#include "conv_ptx.cuh"
+
+namespace {
+
+using convptx::bf16_hi;
+using convptx::bf16_lo;
+using convptx::pack_bf16;
+
+constexpr int TR_THREADS = 256;
+
+__device__ __forceinline__ void unpack8(const uint4 u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ uint4 ld8(const __nv_bfloat16* base, size_t row, int pitch, int c) {
+  return __ldg(reinterpret_cast<const uint4*>(base + row * size_t(pitch) + c));
+}
+
+__device__ __forceinline__ float act_fwd(float y, int act) { return convptx::apply_act(y, act); }
+// d act(y) / dy
+__device__ __forceinline__ float act_grad(float y, int act) {
+  if (act == YB_ACT_LEAKY) return y > 0.f ? 1.f : 0.1f;
+  if (act == YB_ACT_MISH) {
+    const float sp = y > 20.f ? y : log1pf(expf(y));
+    const float t = tanhf(sp);
+    const float sg = 1.f / (1.f + expf(-y));
+    return t + y * (1.f - t * t) * sg;
+  }
+  return 1.f;
+}
+
+struct RowGeom {
+  long long P;       // rows (pixels) of the layer output
+  int C, groups;     // channels, C / 8
+  int h, w;          // output height / width (only for the 2x variants)
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// per-channel sums over rows: sums[2c] += sum z, sums[2c+1] += sum z^2
+__global__ void __launch_bounds__(TR_THREADS) k_bn_stats(const __nv_bfloat16* __restrict__ z, int pitch, RowGeom g,
+                                                         double* __restrict__ sums) {
+  extern __shared__ double s_acc[];  // [2 * C]
+  for (int i = threadIdx.x; i < 2 * g.C; i += TR_THREADS) s_acc[i] = 0.0;
+  __syncthreads();
+  const int lanes = TR_THREADS / g.groups;
+  const int grp = threadIdx.x % g.groups, lane = threadIdx.x / g.groups;
+  const long long per_block = (g.P + gridDim.x - 1) / gridDim.x;
+  const long long r0 = per_block * blockIdx.x;
+  const long long r1 = r0 + per_block < g.P ? r0 + per_block : g.P;
+  if (lane < lanes) {
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long r = r0 + lane; r < r1; r += lanes) {
+      float f[8];
+      unpack8(ld8(z, size_t(r), pitch, grp * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&s_acc[2 * (grp * 8 + k)], double(s[k]));
+      atomicAdd(&s_acc[2 * (grp * 8 + k) + 1], double(q[k]));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * g.C; i += TR_THREADS) atomicAdd(&sums[i], s_acc[i]);
+}
+
+// nn.BatchNorm2d training semantics: normalise with the biased batch variance, update the running
+// statistics with momentum and the UNBIASED variance.
+__global__ void k_bn_finalize(const double* __restrict__ sums, long long P, int C, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                              float* running_var, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                              float* __restrict__ scale, float* __restrict__ bias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = double(P);
+  const double mean = sums[2 * c] / n;
+  double var = sums[2 * c + 1] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = float(1.0 / sqrt(var + double(eps)));
+  const float sc = gamma[c] * rstd;
+  mean_out[c] = float(mean);
+  rstd_out[c] = rstd;
+  scale[c] = sc;
+  bias[c] = beta[c] - float(mean) * sc;
+  if (running_mean) {
+    const double unbiased = P > 1 ? var * n / (n - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * float(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * float(unbiased);
+  }
+}
+
+// a = act(z * scale + bias) (+ residual); up2x: every pixel is stored to its 2x2 block of a (2h, 2w) tensor
+__global__ void __launch_bounds__(TR_THREADS) k_bn_act_fwd(const __nv_bfloat16* __restrict__ z, int z_pitch, RowGeom g,
+                                                           const float* __restrict__ scale, const float* __restrict__ bias,
+                                                           int act, const __nv_bfloat16* __restrict__ res, int res_pitch,
+                                                           __nv_bfloat16* __restrict__ y, int y_pitch, int up2x) {
+  const long long idx = (long long)blockIdx.x * TR_THREADS + threadIdx.x;
+  if (idx >= g.P * g.groups) return;
+  const long long r = idx / g.groups;
+  const int c = int(idx - r * g.groups) * 8;
+  float f[8];
+  unpack8(ld8(z, size_t(r), z_pitch, c), f);
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] = act_fwd(fmaf(f[k], sc[k], bi[k]), act);
+  if (res) {
+    float rr[8];
+    unpack8(ld8(res, size_t(r), res_pitch, c), rr);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] += rr[k];
+  }
+  const uint4 o = pack8(f);
+  if (!up2x) {
+    *reinterpret_cast<uint4*>(y + size_t(r) * y_pitch + c) = o;
+  } else {
+    const long long hw = (long long)g.h * g.w;
+    const long long img = r / hw;
+    const int rem = int(r - img * hw);
+    const int i = rem / g.w, j = rem - i * g.w;
+    const size_t W2 = size_t(2 * g.w);
+    const size_t r00 = (size_t(img) * (2 * g.h) + 2 * i) * W2 + 2 * j;
+    *reinterpret_cast<uint4*>(y + r00 * y_pitch + c) = o;
+    *reinterpret_cast<uint4*>(y + (r00 + 1) * y_pitch + c) = o;
+    *reinterpret_cast<uint4*>(y + (r00 + W2) * y_pitch + c) = o;
+    *reinterpret_cast<uint4*>(y + (r00 + W2 + 1) * y_pitch + c) = o;
+  }
+}
+
+// gradient arriving at this layer's output, 8 channels of row r; up2x = backward of nn.Upsample(2): the sum of
+// the 2x2 block of the (2h, 2w) gradient tensor
+__device__ __forceinline__ void load_dA(const __nv_bfloat16* __restrict__ dA, int pitch, const RowGeom& g, long long r, int c,
+                                        int up2x, float (&d)[8]) {
+  if (!up2x) {
+    unpack8(ld8(dA, size_t(r), pitch, c), d);
+    return;
+  }
+  const long long hw = (long long)g.h * g.w;
+  const long long img = r / hw;
+  const int rem = int(r - img * hw);
+  const int i = rem / g.w, j = rem - i * g.w;
+  const size_t W2 = size_t(2 * g.w);
+  const size_t r00 = (size_t(img) * (2 * g.h) + 2 * i) * W2 + 2 * j;
+  float t[8];
+  unpack8(ld8(dA, r00, pitch, c), d);
+  unpack8(ld8(dA, r00 + 1, pitch, c), t);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) d[k] += t[k];
+  unpack8(ld8(dA, r00 + W2, pitch, c), t);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) d[k] += t[k];
+  unpack8(ld8(dA, r00 + W2 + 1, pitch, c), t);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) d[k] += t[k];
+}
+
+struct BnBwdParams {
+  const __nv_bfloat16* dA; int dA_pitch, up2x;
+  const __nv_bfloat16* z; int z_pitch;
+  const float *scale, *bias, *mean, *rstd;
+  int act;
+  RowGeom g;
+};
+
+// sums[2c] += sum dy, sums[2c+1] += sum dy * xhat   with dy = dA * act'(z*scale+bias), xhat = (z-mean)*rstd
+__global__ void __launch_bounds__(TR_THREADS) k_bn_act_bwd_reduce(const BnBwdParams p, double* __restrict__ sums) {
+  extern __shared__ double s_acc[];
+  const RowGeom& g = p.g;
+  for (int i = threadIdx.x; i < 2 * g.C; i += TR_THREADS) s_acc[i] = 0.0;
+  __syncthreads();
+  const int lanes = TR_THREADS / g.groups;
+  const int grp = threadIdx.x % g.groups, lane = threadIdx.x / g.groups;
+  const long long per_block = (g.P + gridDim.x - 1) / gridDim.x;
+  const long long r0 = per_block * blockIdx.x;
+  const long long r1 = r0 + per_block < g.P ? r0 + per_block : g.P;
+  if (lane < lanes) {
+    const int c = grp * 8;
+    float sc[8], bi[8], mu[8], rs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = p.scale[c + k]; bi[k] = p.bias[c + k]; mu[k] = p.mean[c + k]; rs[k] = p.rstd[c + k]; }
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long r = r0 + lane; r < r1; r += lanes) {
+      float zf[8], d[8];
+      unpack8(ld8(p.z, size_t(r), p.z_pitch, c), zf);
+      load_dA(p.dA, p.dA_pitch, g, r, c, p.up2x, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float dy = d[k] * act_grad(fmaf(zf[k], sc[k], bi[k]), p.act);
+        s[k] += dy;
+        q[k] = fmaf(dy, (zf[k] - mu[k]) * rs[k], q[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&s_acc[2 * (c + k)], double(s[k]));
+      atomicAdd(&s_acc[2 * (c + k) + 1], double(q[k]));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * g.C; i += TR_THREADS) atomicAdd(&sums[i], s_acc[i]);
+}
+
+// BatchNorm layer: dbeta = sum dy, dgamma = sum dy*xhat, m1 = dbeta / P, m2 = dgamma / P.
+// Bias-only conv (gamma == nullptr): sums[2c] is the bias gradient.
+__global__ void k_bn_bwd_finalize(const double* __restrict__ sums, long long P, int C, int has_bn, float* __restrict__ dgamma,
+                                  float* __restrict__ dbeta, float* __restrict__ m1, float* __restrict__ m2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s = sums[2 * c], q = sums[2 * c + 1];
+  dbeta[c] = float(s);
+  if (has_bn) {
+    dgamma[c] = float(q);
+    m1[c] = float(s / double(P));
+    m2[c] = float(q / double(P));
+  }
+}
+
+// dz = scale * (dy - m1 - xhat * m2); optional zero-stuffed copy at 2x resolution (value at (2i, 2j))
+__global__ void __launch_bounds__(TR_THREADS) k_bn_act_bwd_apply(const BnBwdParams p, const float* __restrict__ m1,
+                                                                 const float* __restrict__ m2, __nv_bfloat16* __restrict__ dz,
+                                                                 int dz_pitch, __nv_bfloat16* __restrict__ stuffed,
+                                                                 int stuffed_pitch) {
+  const RowGeom& g = p.g;
+  const long long idx = (long long)blockIdx.x * TR_THREADS + threadIdx.x;
+  if (idx >= g.P * g.groups) return;
+  const long long r = idx / g.groups;
+  const int c = int(idx - r * g.groups) * 8;
+  float zf[8], d[8], o[8];
+  unpack8(ld8(p.z, size_t(r), p.z_pitch, c), zf);
+  load_dA(p.dA, p.dA_pitch, g, r, c, p.up2x, d);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float sc = p.scale[c + k];
+    const float dy = d[k] * act_grad(fmaf(zf[k], sc, p.bias[c + k]), p.act);
+    const float xh = (zf[k] - p.mean[c + k]) * p.rstd[c + k];
+    o[k] = sc * (dy - m1[c + k] - xh * m2[c + k]);
+  }
+  const uint4 u = pack8(o);
+  *reinterpret_cast<uint4*>(dz + size_t(r) * dz_pitch + c) = u;
+  if (stuffed) {
+    const long long hw = (long long)g.h * g.w;
+    const long long img = r / hw;
+    const int rem = int(r - img * hw);
+    const int i = rem / g.w, j = rem - i * g.w;
+    const size_t W2 = size_t(2 * g.w);
+    const size_t r00 = (size_t(img) * (2 * g.h) + 2 * i) * W2 + 2 * j;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(stuffed + r00 * stuffed_pitch + c) = u;
+    *reinterpret_cast<uint4*>(stuffed + (r00 + 1) * stuffed_pitch + c) = zero;
+    *reinterpret_cast<uint4*>(stuffed + (r00 + W2) * stuffed_pitch + c) = zero;
+    *reinterpret_cast<uint4*>(stuffed + (r00 + W2 + 1) * stuffed_pitch + c) = zero;
+  }
+}
+
+// packed fp32 [c_out_pad][taps][c_in_pad] -> OIHW (c_out, c_in, k, k); stem: packed [c_out_pad][32] with
+// K index (kh*3+kw)*c_in + c (the patch-matrix order of yolo_input_patchify)
+__global__ void k_unpack_wgrad(const float* __restrict__ packed, int c_out, int c_in, int taps, int c_in_pad, int stem,
+                               float* __restrict__ grad) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)c_out * c_in * taps;
+  if (idx >= total) return;
+  const int tap = int(idx % taps);
+  const int ci = int((idx / taps) % c_in);
+  const int co = int(idx / ((long long)taps * c_in));
+  grad[idx] = stem ? packed[size_t(co) * c_in_pad + tap * c_in + ci] : packed[(size_t(co) * taps + tap) * c_in_pad + ci];
+}
+
+// data-gradient weights: out[ci][tap'][co] = w[co][ci][taps-1-tap'] (transposed, spatially flipped), bf16,
+// zero padded to [rows_pad][taps][cols_pad] -- the K-major B operand of the forward kernel run on dz
+__global__ void k_pack_weights_dgrad(const float* __restrict__ w, int c_out, int c_in, int taps, int rows_pad, int cols_pad,
+                                     __nv_bfloat16* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)rows_pad * taps * cols_pad;
+  if (idx >= total) return;
+  const int co = int(idx % cols_pad);
+  const int tap = int((idx / cols_pad) % taps);
+  const int ci = int(idx / ((long long)cols_pad * taps));
+  float v = 0.f;
+  if (co < c_out && ci < c_in) v = w[(size_t(co) * c_in + ci) * taps + (taps - 1 - tap)];
+  out[idx] = __float2bfloat16_rn(v);
+}
+
+// torch.optim.SGD: g' = g * gscale + wd * p;  buf = first ? g' : mu * buf + g';  p -= lr * buf
+__global__ void __launch_bounds__(256) k_sgd(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                                            long long n, float lr, float mu, float wd, float gscale, int first) {
+  const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 pv = *reinterpret_cast<float4*>(p + i);
+    const float4 gv = *reinterpret_cast<const float4*>(g + i);
+    float4 bv = first ? make_float4(0, 0, 0, 0) : *reinterpret_cast<float4*>(buf + i);
+    float* pp = &pv.x; const float* gp = &gv.x; float* bp = &bv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gg = fmaf(wd, pp[k], gp[k] * gscale);
+      bp[k] = first ? gg : fmaf(mu, bp[k], gg);
+      pp[k] -= lr * bp[k];
+    }
+    *reinterpret_cast<float4*>(p + i) = pv;
+    *reinterpret_cast<float4*>(buf + i) = bv;
+  } else {
+    for (long long j = i; j < n; ++j) {
+      const float gg = fmaf(wd, p[j], g[j] * gscale);
+      const float b = first ? gg : fmaf(mu, buf[j], gg);
+      buf[j] = b;
+      p[j] -= lr * b;
+    }
+  }
+}
+
+int check_rows(long long P, int C, int pitch, const char* what) {
+  YB_REQUIRE(P >= 1 && C >= 8 && C % 8 == 0 && C <= 2048 && pitch >= C && pitch % 8 == 0, "%s: bad rows (P %lld, C %d, pitch %d)",
+             what, P, C, pitch);
+  return YB_OK;
+}
+int reduce_grid(long long P, int groups) {
+  const int lanes = TR_THREADS / groups;
+  long long blocks = (P + (long long)lanes * 8 - 1) / ((long long)lanes * 8);  // >= 8 rows per thread
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" int yolo_bn_stats(const void* z, long long P, int C, int pitch, double* sums2c, yb_stream_t stream) {
+  YB_REQUIRE(z && sums2c, "yolo_bn_stats: null pointer");
+  if (int rc = check_rows(P, C, pitch, "yolo_bn_stats")) return rc;
+  RowGeom g{P, C, C / 8, 0, 0};
+  k_bn_stats<<<reduce_grid(P, g.groups), TR_THREADS, 2 * C * sizeof(double), (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(z), pitch, g, sums2c);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+extern "C" int yolo_bn_finalize(const double* sums2c, long long P, int C, const float* gamma, const float* beta, float eps,
+                                float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
+                                float* scale, float* bias, yb_stream_t stream) {
+  YB_REQUIRE(sums2c && gamma && beta && mean && rstd && scale && bias && P >= 1 && C >= 1, "yolo_bn_finalize: bad argument");
+  k_bn_finalize<<<yb_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums2c, P, C, gamma, beta, eps, momentum, running_mean,
+                                                                   running_var, mean, rstd, scale, bias);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+extern "C" int yolo_bn_act_fwd(const void* z, long long P, int C, int z_pitch, const float* scale, const float* bias, int act,
+                               const void* residual, int res_pitch, void* y, int y_pitch, int up2x, int h, int w,
+                               yb_stream_t stream) {
+  YB_REQUIRE(z && scale && bias && y, "yolo_bn_act_fwd: null pointer");
+  if (int rc = check_rows(P, C, z_pitch, "yolo_bn_act_fwd")) return rc;
+  YB_REQUIRE(y_pitch >= C && y_pitch % 8 == 0 && (!residual || (res_pitch >= C && res_pitch % 8 == 0)), "yolo_bn_act_fwd: bad pitch");
+  YB_REQUIRE(!up2x || (h >= 1 && w >= 1 && P % ((long long)h * w) == 0), "yolo_bn_act_fwd: bad 2x geometry");
+  RowGeom g{P, C, C / 8, h, w};
+  const long long n = P * g.groups;
+  k_bn_act_fwd<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(z), z_pitch, g, scale, bias, act, static_cast<const __nv_bfloat16*>(residual), res_pitch,
+      static_cast<__nv_bfloat16*>(y), y_pitch, up2x);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+extern "C" int yolo_bn_act_bwd(const void* dA, int dA_pitch, int up2x, const void* z, int z_pitch, long long P, int C, int h, int w,
+                               const float* scale, const float* bias, const float* mean, const float* rstd, int act,
+                               double* sums2c /* zeroed */, float* dgamma, float* dbeta, float* m1m2 /* [2C] scratch */,
+                               void* dz, int dz_pitch, void* stuffed, int stuffed_pitch, yb_stream_t stream_) {
+  YB_REQUIRE(dA && z && scale && bias && mean && rstd && sums2c && dgamma && dbeta && m1m2 && dz, "yolo_bn_act_bwd: null pointer");
+  if (int rc = check_rows(P, C, z_pitch, "yolo_bn_act_bwd")) return rc;
+  YB_REQUIRE(dA_pitch >= C && dA_pitch % 8 == 0 && dz_pitch >= C && dz_pitch % 8 == 0, "yolo_bn_act_bwd: bad pitch");
+  YB_REQUIRE((!up2x && !stuffed) || (h >= 1 && w >= 1 && P % ((long long)h * w) == 0), "yolo_bn_act_bwd: bad 2x geometry");
+  YB_REQUIRE(!stuffed || (stuffed_pitch >= C && stuffed_pitch % 8 == 0), "yolo_bn_act_bwd: bad stuffed pitch");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  BnBwdParams p;
+  p.dA = static_cast<const __nv_bfloat16*>(dA); p.dA_pitch = dA_pitch; p.up2x = up2x;
+  p.z = static_cast<const __nv_bfloat16*>(z); p.z_pitch = z_pitch;
+  p.scale = scale; p.bias = bias; p.mean = mean; p.rstd = rstd; p.act = act;
+  p.g = RowGeom{P, C, C / 8, h, w};
+  k_bn_act_bwd_reduce<<<reduce_grid(P, p.g.groups), TR_THREADS, 2 * C * sizeof(double), stream>>>(p, sums2c);
+  YB_CHECK_LAUNCH();
+  k_bn_bwd_finalize<<<yb_cdiv(C, 128), 128, 0, stream>>>(sums2c, P, C, 1, dgamma, dbeta, m1m2, m1m2 + C);
+  YB_CHECK_LAUNCH();
+  const long long n = P * p.g.groups;
+  k_bn_act_bwd_apply<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, stream>>>(
+      p, m1m2, m1m2 + C, static_cast<__nv_bfloat16*>(dz), dz_pitch, static_cast<__nv_bfloat16*>(stuffed), stuffed_pitch);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+extern "C" int yolo_bias_grad(const void* dz, long long P, int C_pad, int pitch, int C, double* sums2c /* zeroed */, float* dbias,
+                              yb_stream_t stream_) {
+  YB_REQUIRE(dz && sums2c && dbias && C >= 1 && C <= C_pad, "yolo_bias_grad: bad argument");
+  if (int rc = check_rows(P, C_pad, pitch, "yolo_bias_grad")) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RowGeom g{P, C_pad, C_pad / 8, 0, 0};
+  k_bn_stats<<<reduce_grid(P, g.groups), TR_THREADS, 2 * C_pad * sizeof(double), stream>>>(static_cast<const __nv_bfloat16*>(dz),
+                                                                                          pitch, g, sums2c);
+  YB_CHECK_LAUNCH();
+  k_bn_bwd_finalize<<<yb_cdiv(C, 128), 128, 0, stream>>>(sums2c, P, C, 0, nullptr, dbias, nullptr, nullptr);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+extern "C" int yolo_unpack_wgrad(const float* packed, int c_out, int c_in, int ksize, int c_in_pad, int stem, float* grad_oihw,
+                                 yb_stream_t stream) {
+  YB_REQUIRE(packed && grad_oihw && c_out >= 1 && c_in >= 1 && (ksize == 1 || ksize == 3) && c_in_pad >= (stem ? 9 * c_in : c_in),
+             "yolo_unpack_wgrad: bad argument");
+  const long long total = (long long)c_out * c_in * ksize * ksize;
+  k_unpack_wgrad<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(packed, c_out, c_in, ksize * ksize, c_in_pad, stem,
+                                                                                  grad_oihw);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+extern "C" int yolo_pack_weights_dgrad(const float* w_oihw, int c_out, int c_in, int ksize, int rows_pad, int cols_pad,
+                                       void* w_packed, yb_stream_t stream) {
+  YB_REQUIRE(w_oihw && w_packed && c_out >= 1 && c_in >= 1 && (ksize == 1 || ksize == 3) && rows_pad >= c_in && cols_pad >= c_out,
+             "yolo_pack_weights_dgrad: bad argument");
+  const long long total = (long long)rows_pad * ksize * ksize * cols_pad;
+  k_pack_weights_dgrad<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, c_out, c_in, ksize * ksize, rows_pad, cols_pad, static_cast<__nv_bfloat16*>(w_packed));
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+extern "C" int yolo_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
+                             float weight_decay, float grad_scale, int first_step, yb_stream_t stream) {
+  YB_REQUIRE(param && grad && momentum_buf && n >= 0, "yolo_sgd_step: bad argument");
+  YB_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(momentum_buf)) & 15) == 0,
+             "yolo_sgd_step: buffers must be 16-byte aligned");
+  if (n == 0) return YB_OK;
+  const long long threads = (n + 3) / 4;
+  k_sgd<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, n, lr, momentum, weight_decay,
+                                                                            grad_scale, first_step);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
