@@ -70,6 +70,48 @@ def _act(x: torch.Tensor, activation: str) -> torch.Tensor:
 
 
 _TRAINING = False  # set by forward(training=True): nn.BatchNorm2d in train mode (batch statistics)
+_BF16_SIM = False  # set by forward(bf16_sim=True): round where the CUDA path stores bf16 (see train_step_grads)
+
+
+class _RoundBoth(torch.autograd.Function):
+    """value -> bf16 -> fp32 in forward AND on the gradient in backward: a tensor the CUDA path keeps in bf16
+    together with its gradient (activations a / dA, raw conv outputs z / dz)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+class _RoundFwd(torch.autograd.Function):
+    """bf16 value, fp32 gradient: conv weights (bf16 operand packs, fp32 weight gradients)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBwd(torch.autograd.Function):
+    """fp32 value, bf16 gradient: the head logits (fp32 out, loss gradient written as the head conv's bf16 dz)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def _rb(x):
+    return _RoundBoth.apply(x) if _BF16_SIM else x
 
 
 def _cnn_block(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, k: int, stride: int,
@@ -77,9 +119,13 @@ def _cnn_block(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, k: int
     """model.py:80-86.  Eval mode: BatchNorm uses the running statistics; train mode (model.train(), train.py:38):
     batch statistics, and the running ones in `sd` are updated in place as nn.BatchNorm2d does."""
     pad = 1 if k == 3 else 0  # model.py:201
+    w = sd[prefix + "conv.weight"]
+    if _BF16_SIM:
+        w = _RoundFwd.apply(w)
     if not bn_act:
-        return F.conv2d(x, sd[prefix + "conv.weight"], sd[prefix + "conv.bias"], stride, pad)
-    y = F.conv2d(x, sd[prefix + "conv.weight"], None, stride, pad)
+        y = F.conv2d(x, w, sd[prefix + "conv.bias"], stride, pad)
+        return _RoundBwd.apply(y) if _BF16_SIM else y
+    y = _rb(F.conv2d(x, w, None, stride, pad))
     y = F.batch_norm(y, sd[prefix + "batch_norm.running_mean"], sd[prefix + "batch_norm.running_var"],
                      sd[prefix + "batch_norm.weight"], sd[prefix + "batch_norm.bias"], _TRAINING, 0.1, 1e-5)
     if _TRAINING and prefix + "batch_norm.num_batches_tracked" in sd:
@@ -90,21 +136,24 @@ def _cnn_block(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, k: int
 def _residual_stage(sd, prefix, x, repeats, activation, use_residual=True):
     """model.py:115-121."""
     for r in range(repeats):
-        y = _cnn_block(sd, f"{prefix}layers.{r}.0.", x, 1, 1, activation)
+        y = _rb(_cnn_block(sd, f"{prefix}layers.{r}.0.", x, 1, 1, activation))
         y = _cnn_block(sd, f"{prefix}layers.{r}.1.", y, 3, 1, activation)
-        x = x + y if use_residual else y
+        x = _rb(x + y if use_residual else y)
     return x
 
 
 def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, num_classes: int = 80,
-            activation: str = "leaky_relu", training: bool = False) -> List[torch.Tensor]:
-    """YOLOv3.forward (model.py:172-193) from a reference-keyed state_dict; eval mode unless training=True."""
-    global _TRAINING
-    _TRAINING = bool(training)
+            activation: str = "leaky_relu", training: bool = False, bf16_sim: bool = False) -> List[torch.Tensor]:
+    """YOLOv3.forward (model.py:172-193) from a reference-keyed state_dict; eval mode unless training=True.
+    bf16_sim=True keeps the reference's op sequence but rounds values (and, under autograd, gradients) to bf16
+    at the points where the CUDA training path stores bf16 tensors: the image, conv weights, every raw conv
+    output and every block output.  With the flag off this is the reference's fp32 arithmetic exactly."""
+    global _TRAINING, _BF16_SIM
+    _TRAINING, _BF16_SIM = bool(training), bool(bf16_sim)
     try:
-        return _forward(sd, x, num_classes, activation)
+        return _forward(sd, _RoundFwd.apply(x) if bf16_sim else x, num_classes, activation)
     finally:
-        _TRAINING = False
+        _TRAINING = _BF16_SIM = False
 
 
 def _forward(sd, x, num_classes, activation):
@@ -115,9 +164,9 @@ def _forward(sd, x, num_classes, activation):
         if item == "s":  # model.py:213-219: three modules
             x = _residual_stage(sd, f"layers.{i}.", x, 1, activation, use_residual=False)
             _nan_guard(x)
-            x = _cnn_block(sd, f"layers.{i + 1}.", x, 1, 1, activation)
+            x = _rb(_cnn_block(sd, f"layers.{i + 1}.", x, 1, 1, activation))
             _nan_guard(x)
-            p = _cnn_block(sd, f"layers.{i + 2}.pred_block.0.", x, 3, 1, activation)
+            p = _rb(_cnn_block(sd, f"layers.{i + 2}.pred_block.0.", x, 3, 1, activation))
             p = _cnn_block(sd, f"layers.{i + 2}.pred_block.1.", p, 1, 1, activation, bn_act=False)
             b, _, h, w = p.shape  # model.py:147-148
             outs.append(p.reshape(b, 3, num_classes + 5, h, w).permute(0, 1, 3, 4, 2))
@@ -128,7 +177,7 @@ def _forward(sd, x, num_classes, activation):
             x = torch.cat([x, routes.pop()], dim=1)
             i += 1
         elif item[0] == "c":
-            x = _cnn_block(sd, f"layers.{i}.", x, item[2], item[3], activation)
+            x = _rb(_cnn_block(sd, f"layers.{i}.", x, item[2], item[3], activation))
             _nan_guard(x)
             i += 1
         else:
@@ -300,7 +349,7 @@ def yolo_loss(predictions: torch.Tensor, targets: torch.Tensor, anchors: torch.T
 
 
 def train_step_grads(sd: Dict[str, torch.Tensor], x: torch.Tensor, targets: Sequence[torch.Tensor], anchors,
-                     num_classes: int, activation: str = "leaky_relu"):
+                     num_classes: int, activation: str = "leaky_relu", bf16_sim: bool = False):
     """The autograd part of one training step (train.py:53-67) in fp32: model.train() forward, YOLOLoss on the three
     scales with anchors scaled by the grid size (train.py:195-197), loss = sum of all twelve terms, backward.
     `sd` is modified like the module would be (running statistics, num_batches_tracked).  Returns
@@ -309,7 +358,7 @@ def train_step_grads(sd: Dict[str, torch.Tensor], x: torch.Tensor, targets: Sequ
     for v in params.values():
         v.requires_grad_(True)
         v.grad = None
-    outs = forward(sd, x, num_classes, activation, training=True)
+    outs = forward(sd, x, num_classes, activation, training=True, bf16_sim=bf16_sim)
     terms = [torch.zeros(()) for _ in range(4)]
     for o, t, a in zip(outs, targets, anchors):
         S = o.shape[2]
