@@ -35,17 +35,57 @@ __device__ __forceinline__ uint4 ld8(const __nv_bfloat16* base, size_t row, int 
   return __ldg(reinterpret_cast<const uint4*>(base + row * size_t(pitch) + c));
 }
 
-__device__ __forceinline__ float act_fwd(float y, int act) { return convptx::apply_act(y, act); }
+// Mish via one exp: tanh(softplus(y)) = m / (m + 2) with n = e^y, m = n (n + 2); sigmoid(y) = n / (1 + n).
+// (The inference epilogue keeps the libm form; both agree far below one bf16 ulp.)
+__device__ __forceinline__ float mish_tanh_sp(float y, float& sg) {
+  const float n = __expf(fminf(y, 20.f));
+  const float m = n * (n + 2.f);
+  sg = __fdividef(n, 1.f + n);
+  return y > 20.f ? 1.f : __fdividef(m, m + 2.f);
+}
+__device__ __forceinline__ float act_fwd(float y, int act) {
+  if (act == YB_ACT_LEAKY) return fmaxf(y, 0.1f * y);
+  if (act == YB_ACT_MISH) {
+    float sg;
+    return y * mish_tanh_sp(y, sg);
+  }
+  return y;
+}
 // d act(y) / dy
 __device__ __forceinline__ float act_grad(float y, int act) {
   if (act == YB_ACT_LEAKY) return y > 0.f ? 1.f : 0.1f;
   if (act == YB_ACT_MISH) {
-    const float sp = y > 20.f ? y : log1pf(expf(y));
-    const float t = tanhf(sp);
-    const float sg = 1.f / (1.f + expf(-y));
-    return t + y * (1.f - t * t) * sg;
+    float sg;
+    const float t = mish_tanh_sp(y, sg);
+    return fmaf(y * (1.f - t * t), sg, t);
   }
   return 1.f;
+}
+__device__ __forceinline__ void ld8f(const float* __restrict__ p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// Block-level finish of the per-channel reductions: every thread holds 8 + 8 float partial sums for the 8
+// channels of its group; they are transposed through shared memory (row stride 257 floats: conflict free),
+// summed over the block's row lanes, and each block issues ONE double atomic per output.
+constexpr int RED_STRIDE = 257;
+__device__ __forceinline__ void block_channel_reduce(const float (&s)[8], const float (&q)[8], int groups, int lanes, bool active,
+                                                     int C, float* red /* [16][RED_STRIDE] */, double* __restrict__ sums) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[k * RED_STRIDE + threadIdx.x] = active ? s[k] : 0.f;
+    red[(8 + k) * RED_STRIDE + threadIdx.x] = active ? q[k] : 0.f;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 2 * C; o += TR_THREADS) {
+    const int c = o >> 1, which = o & 1;
+    const int grp = c >> 3, k = c & 7;
+    const float* row = red + (which * 8 + k) * RED_STRIDE + grp;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += row[l * groups];
+    atomicAdd(&sums[o], double(acc));
+  }
 }
 
 struct RowGeom {
@@ -58,30 +98,36 @@ struct RowGeom {
 // per-channel sums over rows: sums[2c] += sum z, sums[2c+1] += sum z^2
 __global__ void __launch_bounds__(TR_THREADS) k_bn_stats(const __nv_bfloat16* __restrict__ z, int pitch, RowGeom g,
                                                          double* __restrict__ sums) {
-  extern __shared__ double s_acc[];  // [2 * C]
-  for (int i = threadIdx.x; i < 2 * g.C; i += TR_THREADS) s_acc[i] = 0.0;
-  __syncthreads();
+  __shared__ float red[16 * RED_STRIDE];
   const int lanes = TR_THREADS / g.groups;
   const int grp = threadIdx.x % g.groups, lane = threadIdx.x / g.groups;
   const long long per_block = (g.P + gridDim.x - 1) / gridDim.x;
   const long long r0 = per_block * blockIdx.x;
   const long long r1 = r0 + per_block < g.P ? r0 + per_block : g.P;
-  if (lane < lanes) {
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (long long r = r0 + lane; r < r1; r += lanes) {
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool active = lane < lanes;
+  if (active) {
+    long long r = r0 + lane;
+    for (; r + 3ll * lanes < r1; r += 4ll * lanes) {  // four independent 16-byte loads in flight per thread
+      uint4 u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[j] = ld8(z, size_t(r + (long long)j * lanes), pitch, grp * 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        unpack8(u[j], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
+      }
+    }
+    for (; r < r1; r += lanes) {
       float f[8];
       unpack8(ld8(z, size_t(r), pitch, grp * 8), f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] = fmaf(f[k], f[k], q[k]); }
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      atomicAdd(&s_acc[2 * (grp * 8 + k)], double(s[k]));
-      atomicAdd(&s_acc[2 * (grp * 8 + k) + 1], double(q[k]));
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * g.C; i += TR_THREADS) atomicAdd(&sums[i], s_acc[i]);
+  block_channel_reduce(s, q, g.groups, lanes, active, g.C, red, sums);
 }
 
 // nn.BatchNorm2d training semantics: normalise with the biased batch variance, update the running
@@ -186,40 +232,45 @@ struct BnBwdParams {
 
 // sums[2c] += sum dy, sums[2c+1] += sum dy * xhat   with dy = dA * act'(z*scale+bias), xhat = (z-mean)*rstd
 __global__ void __launch_bounds__(TR_THREADS) k_bn_act_bwd_reduce(const BnBwdParams p, double* __restrict__ sums) {
-  extern __shared__ double s_acc[];
+  __shared__ float red[16 * RED_STRIDE];
   const RowGeom& g = p.g;
-  for (int i = threadIdx.x; i < 2 * g.C; i += TR_THREADS) s_acc[i] = 0.0;
-  __syncthreads();
   const int lanes = TR_THREADS / g.groups;
   const int grp = threadIdx.x % g.groups, lane = threadIdx.x / g.groups;
   const long long per_block = (g.P + gridDim.x - 1) / gridDim.x;
   const long long r0 = per_block * blockIdx.x;
   const long long r1 = r0 + per_block < g.P ? r0 + per_block : g.P;
-  if (lane < lanes) {
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool active = lane < lanes;
+  if (active) {
     const int c = grp * 8;
     float sc[8], bi[8], mu[8], rs[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { sc[k] = p.scale[c + k]; bi[k] = p.bias[c + k]; mu[k] = p.mean[c + k]; rs[k] = p.rstd[c + k]; }
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (long long r = r0 + lane; r < r1; r += lanes) {
-      float zf[8], d[8];
-      unpack8(ld8(p.z, size_t(r), p.z_pitch, c), zf);
-      load_dA(p.dA, p.dA_pitch, g, r, c, p.up2x, d);
+    ld8f(p.scale + c, sc); ld8f(p.bias + c, bi); ld8f(p.mean + c, mu); ld8f(p.rstd + c, rs);
+    auto accum = [&](const float (&zf)[8], const float (&d)[8]) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float dy = d[k] * act_grad(fmaf(zf[k], sc[k], bi[k]), p.act);
         s[k] += dy;
         q[k] = fmaf(dy, (zf[k] - mu[k]) * rs[k], q[k]);
       }
+    };
+    long long r = r0 + lane;
+    if (!p.up2x) {
+      for (; r + lanes < r1; r += 2ll * lanes) {  // two rows (four 16-byte loads) in flight per thread
+        const uint4 z0 = ld8(p.z, size_t(r), p.z_pitch, c), z1 = ld8(p.z, size_t(r + lanes), p.z_pitch, c);
+        const uint4 d0 = ld8(p.dA, size_t(r), p.dA_pitch, c), d1 = ld8(p.dA, size_t(r + lanes), p.dA_pitch, c);
+        float zf[8], d[8];
+        unpack8(z0, zf); unpack8(d0, d); accum(zf, d);
+        unpack8(z1, zf); unpack8(d1, d); accum(zf, d);
+      }
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      atomicAdd(&s_acc[2 * (c + k)], double(s[k]));
-      atomicAdd(&s_acc[2 * (c + k) + 1], double(q[k]));
+    for (; r < r1; r += lanes) {
+      float zf[8], d[8];
+      unpack8(ld8(p.z, size_t(r), p.z_pitch, c), zf);
+      load_dA(p.dA, p.dA_pitch, g, r, c, p.up2x, d);
+      accum(zf, d);
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * g.C; i += TR_THREADS) atomicAdd(&sums[i], s_acc[i]);
+  block_channel_reduce(s, q, g.groups, lanes, active, g.C, red, sums);
 }
 
 // BatchNorm layer: dbeta = sum dy, dgamma = sum dy*xhat, m1 = dbeta / P, m2 = dgamma / P.
@@ -250,12 +301,13 @@ __global__ void __launch_bounds__(TR_THREADS) k_bn_act_bwd_apply(const BnBwdPara
   float zf[8], d[8], o[8];
   unpack8(ld8(p.z, size_t(r), p.z_pitch, c), zf);
   load_dA(p.dA, p.dA_pitch, g, r, c, p.up2x, d);
+  float sc[8], bi[8], mu[8], rs[8], a1[8], a2[8];
+  ld8f(p.scale + c, sc); ld8f(p.bias + c, bi); ld8f(p.mean + c, mu); ld8f(p.rstd + c, rs); ld8f(m1 + c, a1); ld8f(m2 + c, a2);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const float sc = p.scale[c + k];
-    const float dy = d[k] * act_grad(fmaf(zf[k], sc, p.bias[c + k]), p.act);
-    const float xh = (zf[k] - p.mean[c + k]) * p.rstd[c + k];
-    o[k] = sc * (dy - m1[c + k] - xh * m2[c + k]);
+    const float dy = d[k] * act_grad(fmaf(zf[k], sc[k], bi[k]), p.act);
+    const float xh = (zf[k] - mu[k]) * rs[k];
+    o[k] = sc[k] * (dy - a1[k] - xh * a2[k]);
   }
   const uint4 u = pack8(o);
   *reinterpret_cast<uint4*>(dz + size_t(r) * dz_pitch + c) = u;
@@ -336,8 +388,8 @@ int check_rows(long long P, int C, int pitch, const char* what) {
 }
 int reduce_grid(long long P, int groups) {
   const int lanes = TR_THREADS / groups;
-  long long blocks = (P + (long long)lanes * 8 - 1) / ((long long)lanes * 8);  // >= 8 rows per thread
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  long long blocks = (P + (long long)lanes * 16 - 1) / ((long long)lanes * 16);  // >= 16 rows per thread
+  if (blocks > 148 * 6) blocks = 148 * 6;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
@@ -348,7 +400,7 @@ extern "C" int yolo_bn_stats(const void* z, long long P, int C, int pitch, doubl
   YB_REQUIRE(z && sums2c, "yolo_bn_stats: null pointer");
   if (int rc = check_rows(P, C, pitch, "yolo_bn_stats")) return rc;
   RowGeom g{P, C, C / 8, 0, 0};
-  k_bn_stats<<<reduce_grid(P, g.groups), TR_THREADS, 2 * C * sizeof(double), (cudaStream_t)stream>>>(
+  k_bn_stats<<<reduce_grid(P, g.groups), TR_THREADS, 0, (cudaStream_t)stream>>>(
       static_cast<const __nv_bfloat16*>(z), pitch, g, sums2c);
   YB_CHECK_LAUNCH();
   return YB_OK;
@@ -395,7 +447,7 @@ extern "C" int yolo_bn_act_bwd(const void* dA, int dA_pitch, int up2x, const voi
   p.z = static_cast<const __nv_bfloat16*>(z); p.z_pitch = z_pitch;
   p.scale = scale; p.bias = bias; p.mean = mean; p.rstd = rstd; p.act = act;
   p.g = RowGeom{P, C, C / 8, h, w};
-  k_bn_act_bwd_reduce<<<reduce_grid(P, p.g.groups), TR_THREADS, 2 * C * sizeof(double), stream>>>(p, sums2c);
+  k_bn_act_bwd_reduce<<<reduce_grid(P, p.g.groups), TR_THREADS, 0, stream>>>(p, sums2c);
   YB_CHECK_LAUNCH();
   k_bn_bwd_finalize<<<yb_cdiv(C, 128), 128, 0, stream>>>(sums2c, P, C, 1, dgamma, dbeta, m1m2, m1m2 + C);
   YB_CHECK_LAUNCH();
@@ -412,7 +464,7 @@ extern "C" int yolo_bias_grad(const void* dz, long long P, int C_pad, int pitch,
   if (int rc = check_rows(P, C_pad, pitch, "yolo_bias_grad")) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   RowGeom g{P, C_pad, C_pad / 8, 0, 0};
-  k_bn_stats<<<reduce_grid(P, g.groups), TR_THREADS, 2 * C_pad * sizeof(double), stream>>>(static_cast<const __nv_bfloat16*>(dz),
+  k_bn_stats<<<reduce_grid(P, g.groups), TR_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(dz),
                                                                                           pitch, g, sums2c);
   YB_CHECK_LAUNCH();
   k_bn_bwd_finalize<<<yb_cdiv(C, 128), 128, 0, stream>>>(sums2c, P, C, 0, nullptr, dbias, nullptr, nullptr);

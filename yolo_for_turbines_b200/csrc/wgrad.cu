@@ -14,6 +14,10 @@
 // stride), one filter tap per tile.  The reduction over pixels is split across CTAs (split-K); partial tiles
 // are accumulated into the fp32 gradient with vector reductions (red.global.add.v4.f32).
 //
+// A CTA accumulates up to `tp` filter taps at once (tp * NT <= 512 TMEM columns): the dz box of a pixel chunk is
+// loaded once and multiplied against the tp shifted x boxes, which matters for the early layers (Cin = 32, 64)
+// where one tap alone is a 128 x 32 tile with next to no work per pipeline stage.
+//
 // Warp roles (192 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue.
 #include <string.h>
 
@@ -39,6 +43,7 @@ struct WgradKParams {
   int c_in, c_out_pad, taps, ksize_w, stride, stride_w, pad, x_im2col;
   int xc, dc;                   // channels per x / dz box (64 -> 128B swizzle, 32 -> 64B swizzle)
   int num_chunks, chunks_per_split, splits, tiles_m, tiles_n, n_per_tap, stages;
+  int tp, tmem_cols;            // taps per CTA, TMEM columns allocated (power of two >= tp * NT)
 };
 
 struct WgradPlan {
@@ -63,8 +68,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 template <int NT>
 __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__ WgradKParams p) {
   constexpr uint32_t B_BYTES = KP * NT * 2;
-  constexpr uint32_t STAGE_BYTES = WG_A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = NT < 32 ? 32 : NT;
+  const uint32_t STAGE_BYTES = WG_A_BYTES + uint32_t(p.tp) * B_BYTES;
+  const uint32_t TMEM_COLS = uint32_t(p.tmem_cols);
   // bf16 x bf16 -> fp32, A and B both MN-major (bits 15, 16), N = NT, M = 128
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(NT >> 3) << 17) |
                              (uint32_t(128 >> 4) << 24);
@@ -82,8 +87,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
   const int nt = bid % p.tiles_n; bid /= p.tiles_n;
   const int mt = bid % p.tiles_m; bid /= p.tiles_m;
   const int split = bid;
-  const int tap = nt / p.n_per_tap, ci0 = (nt - tap * p.n_per_tap) * NT;
-  const int tr = tap / p.ksize_w, tq = tap - tr * p.ksize_w;
+  const int tg = nt / p.n_per_tap, ci0 = (nt - tg * p.n_per_tap) * NT;
+  const int tap0 = tg * p.tp;
+  const int ntaps = p.taps - tap0 < p.tp ? p.taps - tap0 : p.tp;  // taps this CTA accumulates
   const int co0 = mt * 128;
   const int chunk0 = split * p.chunks_per_split;
   int nchunks = p.num_chunks - chunk0;
@@ -116,7 +122,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
     // ===== TMA producer =====
     int s = 0;
     uint32_t ph = 0;
-    const uint32_t tx_bytes = uint32_t(a_boxes) * KP * d_row_bytes + B_BYTES;
+    const uint32_t tx_bytes = uint32_t(a_boxes) * KP * d_row_bytes + uint32_t(ntaps) * B_BYTES;
     for (int c = 0; c < nchunks; ++c) {
       const int p0 = (chunk0 + c) * KP;
       int cw = 0, ch = 0, img = 0;
@@ -133,12 +139,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
         mbar_expect_tx(full_bar(s), tx_bytes);
         const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + WG_A_BYTES;
         for (int j = 0; j < a_boxes; ++j) tma_load_2d(&p.tmD, full_bar(s), sa + j * KP * d_row_bytes, co0 + j * p.dc, p0);
-        for (int j = 0; j < b_boxes; ++j) {
-          if (p.x_im2col)
-            tma_load_im2col_4d(&p.tmX, full_bar(s), sb + j * KP * x_row_bytes, ci0 + j * p.xc, cw, ch, img, (uint16_t)tq,
-                               (uint16_t)tr);
-          else
-            tma_load_2d(&p.tmX, full_bar(s), sb + j * KP * x_row_bytes, ci0 + j * p.xc, p0);
+        for (int t = 0; t < ntaps; ++t) {
+          const int tap = tap0 + t;
+          const int tr = tap / p.ksize_w, tq = tap - tr * p.ksize_w;
+          for (int j = 0; j < b_boxes; ++j) {
+            const uint32_t dst = sb + t * B_BYTES + j * KP * x_row_bytes;
+            if (p.x_im2col)
+              tma_load_im2col_4d(&p.tmX, full_bar(s), dst, ci0 + j * p.xc, cw, ch, img, (uint16_t)tq, (uint16_t)tr);
+            else
+              tma_load_2d(&p.tmX, full_bar(s), dst, ci0 + j * p.xc, p0);
+          }
         }
       }
       __syncwarp();
@@ -156,9 +166,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
       tc_fence_after();
       if (elect_one()) {
         const uint64_t soff = uint64_t((uint32_t(s) * STAGE_BYTES) >> 4);
+        for (int t = 0; t < ntaps; ++t) {
+          const uint64_t boff = soff + uint64_t((uint32_t(t) * B_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < KP / 16; ++k)
-          umma_bf16(tmem_base, adesc0 + soff + a_kstep * k, bdesc0 + soff + b_kstep * k, IDESC, (c | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < KP / 16; ++k)
+            umma_bf16(tmem_base + uint32_t(t * NT), adesc0 + soff + a_kstep * k, bdesc0 + boff + b_kstep * k, IDESC,
+                      (c | k) != 0 ? 1u : 0u);
+        }
         umma_commit(empty_bar(s));
         if (c == nchunks - 1) umma_commit(tmem_full_bar);
       }
@@ -171,16 +185,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
     const int co = co0 + quad * 32 + lane;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    float* row = p.dw + (size_t(co) * p.taps + tap) * p.c_in + ci0;
 #pragma unroll 1
-    for (int n = 0; n < NT; n += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + n, v);
-      if (co < p.c_out_pad) {
+    for (int t = 0; t < ntaps; ++t) {
+      float* row = p.dw + (size_t(co) * p.taps + tap0 + t) * p.c_in + ci0;
+#pragma unroll 1
+      for (int n = 0; n < NT; n += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(t * NT + n), v);
+        if (co < p.c_out_pad) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          red_add_v4(row + n + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                     __uint_as_float(v[4 * j + 3]));
+          for (int j = 0; j < 8; ++j)
+            red_add_v4(row + n + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
       }
     }
   }
@@ -287,7 +304,14 @@ extern "C" int yolo_wgrad_plan_init(void* plan_host, size_t plan_bytes, const yo
   kp.num_chunks = (int)((P + KP - 1) / KP);
   kp.tiles_m = (d->c_out_pad + 127) / 128;
   kp.n_per_tap = d->c_in / nt;
-  kp.tiles_n = kp.taps * kp.n_per_tap;
+  int tp = 512 / nt;                       // accumulators that fit TMEM
+  if (tp > kp.taps) tp = kp.taps;
+  if (kp.taps == 9 && tp >= 3 && tp < 9) tp = 3;   // 3 balanced groups instead of e.g. 4 + 4 + 1
+  if (nt == 256) tp = 1;                   // 48 KB per tap and stage: keep the ring deep instead
+  kp.tp = tp;
+  kp.tmem_cols = 32;
+  while (kp.tmem_cols < tp * nt) kp.tmem_cols *= 2;
+  kp.tiles_n = ((kp.taps + tp - 1) / tp) * kp.n_per_tap;
   const int tiles = kp.tiles_m * kp.tiles_n;
   int dev = 0, sms = 148;
   YB_CHECK_CUDA(cudaGetDevice(&dev));
@@ -298,7 +322,7 @@ extern "C" int yolo_wgrad_plan_init(void* plan_host, size_t plan_bytes, const yo
   if (splits < 1) splits = 1;
   kp.chunks_per_split = (kp.num_chunks + splits - 1) / splits;
   kp.splits = (kp.num_chunks + kp.chunks_per_split - 1) / kp.chunks_per_split;  // no empty CTA
-  const uint32_t stage_bytes = WG_A_BYTES + KP * nt * 2;
+  const uint32_t stage_bytes = WG_A_BYTES + uint32_t(tp) * KP * nt * 2;
   int stages = (int)((220u * 1024u) / stage_bytes);
   if (stages > 8) stages = 8;
   kp.stages = stages;
@@ -326,7 +350,7 @@ extern "C" int yolo_wgrad(const void* plan_host, yb_stream_t stream_) {
 extern "C" int yolo_wgrad_plan_info(const void* plan_host, int32_t* info6) {
   const WgradPlan* pl = static_cast<const WgradPlan*>(plan_host);
   YB_REQUIRE(pl && pl->magic == WG_MAGIC && info6, "wgrad plan info: bad plan");
-  info6[0] = pl->nt; info6[1] = pl->kp.stages; info6[2] = pl->kp.splits; info6[3] = pl->kp.tiles_m;
+  info6[0] = pl->nt + 1000 * pl->kp.tp; info6[1] = pl->kp.stages; info6[2] = pl->kp.splits; info6[3] = pl->kp.tiles_m;
   info6[4] = pl->kp.tiles_n; info6[5] = pl->grid;
   return YB_OK;
 }
