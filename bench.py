@@ -153,6 +153,97 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU
+def run_train_workload(args, dev, dist, rank, world, local):
+    """BASELINE configs[3]: the turbine-defect model (2 classes, TURBINE_ANCHORS), one training step per step:
+    train-mode forward + YOLOLoss x3 + backward + gradient all-reduce (NCCL, bucketed, overlapped) + SGD.
+    Batch 32 per GPU (config.BATCH_SIZE) unless --batch is given; weak scaling."""
+    from oracle import yolo_oracle as orc  # synthetic targets only (test infrastructure, not on the timed path)
+    from yolo_for_turbines_b200 import config as cfg
+    from yolo_for_turbines_b200.model import YOLOv3
+    from yolo_for_turbines_b200.train import Trainer
+
+    B = args.batch if args.batch != 64 else 32
+    S = args.size
+    torch.manual_seed(0)
+    model = YOLOv3(num_classes=2, activation=args.activation).to(dev).train()
+    tr = Trainer(model, cfg.TURBINE_ANCHORS, lr=1e-4, momentum=0.9, weight_decay=5e-4)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    xs = [torch.rand(B, 3, S, S, generator=g, device=dev) for _ in range(3)]
+    tgs = [[t.to(dev) for t in orc.synth_targets(B, S, 2, 10 * rank + i)] for i in range(3)]
+    hx = [torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(77 + rank + i)).pin_memory() for i in range(2)]
+    htg = [[t.pin_memory() for t in orc.synth_targets(B, S, 2, 500 + 10 * rank + i)] for i in range(2)]
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for i in range(max(args.warmup, 3) + 10):
+        tr.step(xs[i % 3], tgs[i % 3])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        losses = tr.step(xs[i % 3], tgs[i % 3])
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    # end to end: pinned host images + targets uploaded every step, the four loss terms read back every step
+    dx = [torch.empty_like(xs[0]) for _ in range(2)]
+    dt = [[torch.empty_like(t, device=dev) for t in htg[0]] for _ in range(2)]
+    host_loss = torch.empty(4, dtype=torch.float32).pin_memory()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        j = i % 2
+        dx[j].copy_(hx[j], non_blocking=True)
+        for a, b in zip(dt[j], htg[j]):
+            a.copy_(b, non_blocking=True)
+        host_loss.copy_(tr.step(dx[j], dt[j]), non_blocking=True)
+    t1.record()
+    barrier()
+    ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+    clocks = sampler.finish()
+    if rank == 0:
+        pk = peaks()
+        plan = tr.plan(B, S, S)
+        imgs = B * world * args.steps
+        gflop = 3.0 * algorithmic_gflop(S, 2)     # forward + data gradient + weight gradient
+        achieved = gflop * B * args.steps / ms_dev
+        h2d = B * 3 * S * S * 4 + sum(t.numel() * 4 for t in htg[0])
+        line = {
+            "metric": "yolov3_turbine_train_images_per_sec", "value": imgs / (ms_dev / 1e3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"YOLOv3-{S} turbine model (2 classes, TURBINE_ANCHORS, {args.activation}) training step "
+                                   f"fwd+YOLOLoss+bwd+SGD, batch {B}/GPU (BASELINE configs[3])", "global_batch": B * world,
+                       "parallelism": f"dp{world}", "allreduce_bytes": int(tr.n_trainable) * 4 if world > 1 else 0,
+                       "l2": f"3 rotating batches; {plan.total_bytes / 1e9:.1f} GB of saved activations per step exceed the 126 MB L2"},
+            "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
+            "gpu_launches": tr.launches_per_step(plan) * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "k_conv_v2 (fwd + dgrad) and k_wgrad, whole step", "achieved": achieved,
+                         "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                         "note": "algorithmic FLOPs = 3 x forward (SURVEY 8d) over the WHOLE step time; the step is "
+                                 "currently dominated by HBM-bound BatchNorm/activation passes, see DESIGN.md", "traffic": None},
+            "clocks": clocks, "final_loss_terms": [float(v) for v in losses.tolist()],
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,6 +258,9 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=2, help="images per CPU-baseline step")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="detect", choices=["detect", "train"],
+                    help="detect = BASELINE configs[1] (the headline); train = configs[3], one SGD step per step")
+    ap.add_argument("--activation", default="mish", help="train workload: the reference trains with mish (train.py:299)")
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--conv-impl", type=int, default=0)
@@ -201,6 +295,10 @@ def main():
             sys.stdout.flush()
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
+
+    if args.workload == "train":
+        run_train_workload(args, dev, dist, rank, world, local)
+        return
 
     from yolo_for_turbines_b200 import config as cfg
     from yolo_for_turbines_b200.model import YOLOv3

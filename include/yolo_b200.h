@@ -265,11 +265,12 @@ int yolo_sgd_step(float* param, const float* grad, float* momentum_buf, long lon
                   float weight_decay, float grad_scale, int first_step, yb_stream_t stream);
 /* K8 backward: gradient of the summed, lambda-weighted YOLOLoss terms of one scale (loss.py:54-81) w.r.t. pred.
  * sums6 = the device sums yolo_loss_fwd produced for the same pred/target; dpred gets all 5+nc entries of every
- * cell (element strides dstrides5; out_bf16 selects bf16 or fp32), scaled by grad_scale.                      */
+ * cell (element strides dstrides5; out_bf16 selects bf16 or fp32), scaled by grad_scale and, per term, by
+ * term_scales4_host = upstream gradients of [box, object, no-object, class] (NULL = all 1).                  */
 int yolo_loss_bwd(const float* pred, const int64_t* pstrides5_host, const float* target,
                   const int64_t* tstrides5_host, int batch, int S, int nc, const float* anchors6_host,
-                  const double* sums6, float grad_scale, void* dpred, const int64_t* dstrides5_host, int out_bf16,
-                  yb_stream_t stream);
+                  const double* sums6, float grad_scale, const float* term_scales4_host, void* dpred,
+                  const int64_t* dstrides5_host, int out_bf16, yb_stream_t stream);
 
 /* Stable LSD radix sort of (u64 key, i32 value) pairs on bits [0,end_bit)
  * (end_bit multiple of 8); K5's building block, exported for tests and for

@@ -100,3 +100,53 @@ def test_second_step_uses_momentum_and_new_weights():
     m.eval()
     outs = m(xs)
     assert all(torch.isfinite(o).all() for o in outs)
+
+
+def test_dropin_training_loop_matches_fused_trainer():
+    """The reference's loop body (train.py:42-69) with the drop-in modules -- model.train(), `out = model(x)`,
+    three YOLOLoss calls, GradScaler.scale(loss).backward(), scaler.step(torch SGD) -- against Trainer.step on a
+    copy of the same model: same losses, same gradients (the 2^16 loss scale is exact in bf16/fp32), same update."""
+    import copy
+
+    from oracle import yolo_oracle as orc
+    from yolo_for_turbines_b200.loss import YOLOLoss
+    from yolo_for_turbines_b200.train import Trainer
+
+    m, sd, x, tg = _setup(2, "mish", 96, 2, 21)
+    m2 = copy.deepcopy(m)
+    m, m2 = m.cuda().train(), m2.cuda().train()
+    xs, ts = x.cuda(), [t.cuda() for t in tg]
+    lr, mu, wd = 1e-3, 0.9, 5e-4
+
+    opt = torch.optim.SGD(m.parameters(), lr=lr, momentum=mu, weight_decay=wd)
+    scaler = torch.amp.GradScaler()
+    loss_fn = YOLOLoss()
+    scaled_anchors = [torch.tensor(a) * s for a, s in zip(orc.TURBINE_ANCHORS, (3, 6, 12))]
+    for _ in range(2):
+        opt.zero_grad()
+        with torch.amp.autocast(device_type="cuda"):
+            out = m(xs)
+            terms = [loss_fn(o, t.clone(), a.cuda()) for o, t, a in zip(out, ts, scaled_anchors)]
+            loss = sum(sum(t) for t in terms)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+    torch.cuda.synchronize()
+    assert out[0].shape == (2, 3, 3, 3, 7) and torch.isfinite(loss)
+
+    tr = Trainer(m2, orc.TURBINE_ANCHORS, lr=lr, momentum=mu, weight_decay=wd)
+    for _ in range(2):
+        fused = tr.step(xs, ts)
+    torch.cuda.synchronize()
+    assert abs(float(fused.sum()) - float(loss)) <= 2e-3 * abs(float(loss))
+    for (k, p), (_, q) in zip(m.named_parameters(), m2.named_parameters()):
+        # second-step gradients: the first update already went through both paths
+        g1, g2 = p.grad.float(), q.grad    # GradScaler.step() has already unscaled p.grad in place
+        denom = float(g2.abs().max()) + 1e-12
+        assert float((g1 - g2).abs().max()) <= 2e-2 * denom, (k, float((g1 - g2).abs().max()), denom)
+        assert torch.allclose(p.detach(), q.detach(), rtol=1e-3, atol=1e-5), k
+    sd1, sd2 = m.state_dict(), m2.state_dict()
+    for k in sd1:
+        if "running" in k:
+            assert torch.allclose(sd1[k], sd2[k], rtol=1e-3, atol=1e-5), k
+    assert int(sd1["layers.0.batch_norm.num_batches_tracked"]) == 2

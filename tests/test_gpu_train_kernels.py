@@ -221,7 +221,7 @@ def test_loss_backward_matches_autograd(nc, S, B, bf16):
     ps, ts = (C.c_int64 * 5)(*pd.stride()), (C.c_int64 * 5)(*td.stride())
     lib.yolo_loss_fwd(ptr(pd), ps, ptr(td), ts, B, S, nc, anc, 0, ptr(sums), st)
     dp = torch.empty(pd.shape, dtype=torch.bfloat16 if bf16 else torch.float32, device=dev)
-    lib.yolo_loss_bwd(ptr(pd), ps, ptr(td), ts, B, S, nc, anc, ptr(sums), 1.0, ptr(dp), (C.c_int64 * 5)(*dp.stride()), int(bf16), st)
+    lib.yolo_loss_bwd(ptr(pd), ps, ptr(td), ts, B, S, nc, anc, ptr(sums), 1.0, None, ptr(dp), (C.c_int64 * 5)(*dp.stride()), int(bf16), st)
     torch.cuda.synchronize()
     got = dp.float().cpu()
     tol = (2.0 ** -8 if bf16 else 1e-5) * max(1e-3, float(ref.abs().max()))

@@ -72,8 +72,8 @@ SIGNATURES = {
     "yolo_unpack_wgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "yolo_pack_weights_dgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "yolo_sgd_step": (_I, [_P, _P, _P, _LL, _F, _F, _F, _F, _I, _P]),
-    "yolo_loss_bwd": (_I, [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _P, _F, _P,
-                           C.POINTER(C.c_int64), _I, _P]),
+    "yolo_loss_bwd": (_I, [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _P, _F,
+                           C.POINTER(_F), _P, C.POINTER(C.c_int64), _I, _P]),
     "yolo_sort_workspace_bytes": (_SZ, [_I]),
     "yolo_sort_pairs": (_I, [_P, _P, _P, _I, _I, _P, _SZ, _P]),
 }

@@ -147,6 +147,7 @@ struct LossBwdParams {
   float anchors[6];
   const double* sums;
   float gscale;
+  float tw[4];  // upstream gradient of the [box, object, no-object, class] terms (1 when the terms are just summed)
   void* dpred;
   int out_bf16;
 };
@@ -181,23 +182,24 @@ __global__ void __launch_bounds__(256) k_loss_bwd(const LossBwdParams p) {
     const CBox gb = yb_make_cbox(gx, gy, gw, gh, YB_BOX_CENTER);
     const float iou = yb_iou(pb, __fmul_rn(pw, ph), gb, __fmul_rn(gw, gh));
     const float lw = logf(1e-16f + gw / aw), lh = logf(1e-16f + gh / ah);
-    const float kb = p.gscale * 5.f * 2.f / (4.f * n_obj);
+    const float kb = p.gscale * p.tw[0] * 5.f * 2.f / (4.f * n_obj);
     put_grad(p, d0, kb * (tx - gx));
     put_grad(p, d0 + dc, kb * (sy - gy) * sy * (1.f - sy));
     put_grad(p, d0 + 2 * dc, kb * (sw - lw) * sw * (1.f - sw));
     put_grad(p, d0 + 3 * dc, kb * (th - lh));
-    put_grad(p, d0 + 4 * dc, p.gscale * 2.f * (to - iou * tobj) / n_obj);
+    put_grad(p, d0 + 4 * dc, p.gscale * p.tw[1] * 2.f * (to - iou * tobj) / n_obj);
     float mx = -INFINITY;
     for (int c = 0; c < p.nc; ++c) mx = fmaxf(mx, q[(5 + c) * pc]);
     float se = 0.f;
     for (int c = 0; c < p.nc; ++c) se += expf(q[(5 + c) * pc] - mx);
     const int label = int(t[5 * tc]);
-    const float inv = p.gscale / (se * n_obj);
+    const float gc = p.gscale * p.tw[3] / n_obj;
+    const float inv = gc / se;
     for (int c = 0; c < p.nc; ++c)
-      put_grad(p, d0 + (5 + c) * dc, expf(q[(5 + c) * pc] - mx) * inv - (c == label ? p.gscale / n_obj : 0.f));
+      put_grad(p, d0 + (5 + c) * dc, expf(q[(5 + c) * pc] - mx) * inv - (c == label ? gc : 0.f));
   } else {
     float g4 = 0.f;
-    if (tobj == 0.0f) g4 = p.gscale * 0.5f / (n_noobj * (1.f + expf(-q[4 * pc])));
+    if (tobj == 0.0f) g4 = p.gscale * p.tw[2] * 0.5f / (n_noobj * (1.f + expf(-q[4 * pc])));
     for (int c = 0; c < 5 + p.nc; ++c) put_grad(p, d0 + c * dc, c == 4 ? g4 : 0.f);
   }
 }
@@ -206,8 +208,8 @@ __global__ void __launch_bounds__(256) k_loss_bwd(const LossBwdParams p) {
 
 extern "C" int yolo_loss_bwd(const float* pred, const int64_t* pstrides5_host, const float* target,
                              const int64_t* tstrides5_host, int batch, int S, int nc, const float* anchors6_host,
-                             const double* sums6, float grad_scale, void* dpred, const int64_t* dstrides5_host, int out_bf16,
-                             yb_stream_t stream) {
+                             const double* sums6, float grad_scale, const float* term_scales4_host, void* dpred,
+                             const int64_t* dstrides5_host, int out_bf16, yb_stream_t stream) {
   YB_REQUIRE(pred && target && pstrides5_host && tstrides5_host && anchors6_host && sums6 && dpred && dstrides5_host,
              "yolo_loss_bwd: null pointer");
   YB_REQUIRE(batch >= 0 && S >= 1 && nc >= 1, "yolo_loss_bwd: bad shape");
@@ -218,6 +220,7 @@ extern "C" int yolo_loss_bwd(const float* pred, const int64_t* pstrides5_host, c
   p.batch = batch; p.S = S; p.nc = nc;
   for (int k = 0; k < 6; ++k) p.anchors[k] = anchors6_host[k];
   p.sums = sums6; p.gscale = grad_scale; p.dpred = dpred; p.out_bf16 = out_bf16;
+  for (int k = 0; k < 4; ++k) p.tw[k] = term_scales4_host ? term_scales4_host[k] : 1.f;
   const long long cells = 3ll * S * S * batch;
   k_loss_bwd<<<(unsigned)((cells + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
   YB_CHECK_LAUNCH();

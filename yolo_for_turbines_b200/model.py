@@ -8,7 +8,8 @@ tcgen05 kernels through `engine.Engine` and fails loudly (no CPU or ATen fallbac
 not on a CUDA device or libyolo_b200.so is missing.
 
 Deviations, all deliberate:
-  * eval mode only for now (BatchNorm folded from running statistics); train mode raises.
+  * train mode (`model.train()`): the whole network is one autograd node (train._TrainForwardFn) running the
+    batch-statistics forward and the hand-written backward; standalone blocks still need .eval().
   * the reference's 28 per-layer NaN syncs (model.py:175,183) are one device status word checked
     once per forward; the same AssertionError / ValueError("Nan in layer") are raised.
   * compute is bf16 with fp32 accumulation; head outputs are returned as fp32.
@@ -97,6 +98,7 @@ class _EngineHolder:
     def __getstate__(self):
         d = self.__dict__.copy()
         d.pop("_yb_engine", None)
+        d.pop("_yb_train", None)
         return d
 
 
@@ -255,7 +257,24 @@ class YOLOv3(_EngineHolder, nn.Module):
             plan.run(x)
         return plan, plan.head_views()
 
+    def _train_session(self, device):
+        from .train import Trainer
+
+        sess = self.__dict__.get("_yb_train")
+        if sess is None or sess.device != device:
+            from . import config as cfg
+            sess = Trainer(self, cfg.ANCHORS, lr=0.0, own_params=False)
+            self.__dict__["_yb_train"] = sess
+        return sess
+
     def forward(self, x):
+        if self.training:
+            # model.train() (train.py:38): batch-statistics BatchNorm, outputs attached to autograd so that the
+            # reference's loss.backward() / optimizer.step() loop runs unchanged (see train._TrainForwardFn)
+            require_cuda(x, "YOLOv3 input")
+            if x.dim() != 4 or x.shape[1] != self.in_channels:
+                raise YoloB200Error(f"expected (B,{self.in_channels},H,W) input, got {tuple(x.shape)}")
+            return self._train_session(x.device).autograd_forward(x)
         plan, views = self.forward_async(x)
         outs = [v.clone(memory_format=torch.preserve_format) for v in views]
         plan.check_status()  # AssertionError on NaN input / ValueError("Nan in layer"), model.py:175,184

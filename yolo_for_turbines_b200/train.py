@@ -317,11 +317,64 @@ class TrainPlan:
                 on_op_done(i)
 
 
+def make_buckets(firsts, n_trainable: int, bucket_elems: int):
+    """All-reduce schedule over the flat gradient buffer.  `firsts` = (offset of the op's first parameter, op index)
+    for every op that owns trainable parameters; parameters are laid out in module order = forward op order, and the
+    backward pass finishes ops in DESCENDING index order.  Returns [(first_op, lo, hi)] in firing order: the slice
+    [lo, hi) is complete -- and is all-reduced on the side stream -- as soon as op `first_op` has run its backward.
+    Slices are disjoint, cover [0, n_trainable) and hold at least `bucket_elems` elements (except the last one)."""
+    firsts = sorted(firsts)
+    buckets, hi_idx, hi = [], len(firsts), n_trainable
+    while hi_idx > 0:
+        j = hi_idx - 1
+        while j > 0 and hi - firsts[j][0] < bucket_elems:
+            j -= 1
+        lo = firsts[j][0] if j > 0 else 0
+        buckets.append((min(f[1] for f in firsts[j:hi_idx]), lo, hi))
+        hi, hi_idx = lo, j
+    return buckets
+
+
+class _TrainForwardFn(torch.autograd.Function):
+    """Train-mode forward of the whole network as ONE autograd node: forward = TrainPlan.forward, backward = the head
+    gradients converted to the head convs' bf16 dz + TrainPlan.backward; parameter gradients are returned to autograd."""
+
+    @staticmethod
+    def forward(ctx, trainer, x, *params):
+        require_cuda(x, "YOLOv3 input")
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        with torch.cuda.device(trainer.device):
+            trainer.repack_if_changed()
+            plan = trainer.plan(x.shape[0], x.shape[2], x.shape[3])
+            plan.forward(x)
+        ctx.trainer, ctx.plan = trainer, plan
+        ctx.n_params = len(params)
+        return tuple(v.clone(memory_format=torch.preserve_format) for v in plan.head_views())
+
+    @staticmethod
+    def backward(ctx, *gheads):
+        tr, plan = ctx.trainer, ctx.plan
+        with torch.cuda.device(tr.device):
+            tr.dw_packed.zero_()
+            plan.sums[plan.sums.numel() // 2:].zero_()
+            for op, (na, nc), g in zip(plan.heads, plan.head_meta, gheads):
+                dzv = op.dz.view(plan.B, op.ho, op.wo, op.pc.c_out_pad)[..., : na * (nc + 5)]
+                if g is None:
+                    dzv.zero_()
+                else:   # (B, 3, S, S, 5+nc) -> NHWC channel order a*(5+nc)+c, bf16
+                    dzv.copy_(g.permute(0, 2, 3, 1, 4).reshape(plan.B, op.ho, op.wo, na * (nc + 5)))
+            plan.backward()
+        grads = [tr.grad_view.get(id(p)) for p in tr.all_params]
+        return (None, None) + tuple(g.clone() if g is not None else None for g in grads)
+
+
 class Trainer:
     """SGD training of a drop-in `YOLOv3` (or any module built from its blocks) on the sm_100a path."""
 
     def __init__(self, model, anchors, lr: float, momentum: float = 0.0, weight_decay: float = 0.0,
-                 process_group=None, bucket_mb: float = 32.0, max_plans: int = 2):
+                 process_group=None, bucket_mb: float = 32.0, max_plans: int = 2, own_params: bool = True,
+                 data_parallel: bool = True):
         from .model import CNNBlock
 
         p0 = next(model.parameters())
@@ -333,7 +386,7 @@ class Trainer:
         self.max_plans = max_plans
         self.pg = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if data_parallel and (process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         dev = self.device
         with torch.cuda.device(dev):
@@ -360,17 +413,27 @@ class Trainer:
             for p in frozen:
                 offs[id(p)] = n
                 n += (p.numel() + 3) // 4 * 4
-            self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
+            # own_params=False (the autograd wrapper of model.YOLOv3.forward): parameters and optimizer stay the
+            # caller's; only the flat gradient buffer exists and its views are handed to autograd.
+            self.own_params = bool(own_params)
             self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
-            self.flat_m = torch.zeros(max(self.n_trainable, 4), dtype=torch.float32, device=dev)
+            self.grad_view = {}
+            if self.own_params:
+                self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
+                self.flat_m = torch.zeros(max(self.n_trainable, 4), dtype=torch.float32, device=dev)
             for p in trainable + frozen:
                 o = offs[id(p)]
-                view = self.flat_p[o:o + p.numel()].view_as(p)
-                view.copy_(p.data)
-                p.data = view
+                if self.own_params:
+                    view = self.flat_p[o:o + p.numel()].view_as(p)
+                    view.copy_(p.data)
+                    p.data = view
                 if p.requires_grad:
-                    p.grad = self.flat_g[o:o + p.numel()].view_as(p)
+                    self.grad_view[id(p)] = self.flat_g[o:o + p.numel()].view_as(p)
+                    if self.own_params:
+                        p.grad = self.grad_view[id(p)]
             self.param_off = offs
+            self.all_params = params
+            self._packed_sig = None
 
             # ---- packed weight-gradient arena + transposed weight packs --------------------------------
             self.dw_off, tot = {}, 0
@@ -408,6 +471,20 @@ class Trainer:
                     lib.yolo_fold_bn(None, None, None, None, ptr(b.conv.bias), 0.0, pc.c_out, pc.c_out_pad, ptr(pc.scale),
                                      ptr(pc.bias), st)
 
+    def repack_if_changed(self):
+        """Autograd mode: the caller's optimizer updates the parameters in place between forwards."""
+        sig = tuple((p._version, p.data_ptr()) for p in self.all_params)
+        if sig != self._packed_sig:
+            self.repack()
+            self._packed_sig = sig
+
+    # ---- autograd wrapper (model.YOLOv3.forward in train mode) -------------------------------------------
+    def autograd_forward(self, x: torch.Tensor):
+        """`out = model(x)` of train.py:54 with model.train(): returns the three head tensors attached to the autograd
+        graph, so that the reference's own `loss.backward()` / optimizer / GradScaler code runs unchanged."""
+        outs = _TrainForwardFn.apply(self, x, *self.all_params)
+        return list(outs)
+
     def plan(self, B, H, W) -> TrainPlan:
         key = (B, H, W)
         p = self.plans.get(key)
@@ -418,11 +495,11 @@ class Trainer:
                 p = TrainPlan(self, B, H, W)
                 for op in p.ops:
                     blk = op.block
-                    gv = lambda t: t.grad if (t is not None and t.requires_grad) else None  # noqa: E731
+                    gv = lambda t: self.grad_view.get(id(t)) if t is not None else None  # noqa: E731
                     op.g_w = gv(blk.conv.weight)
                     op.g_b = gv(blk.conv.bias) if blk.conv.bias is not None else None
                     if blk.batch_norm_act:
-                        op.g_gamma, op.g_beta = blk.batch_norm.weight.grad, blk.batch_norm.bias.grad
+                        op.g_gamma, op.g_beta = gv(blk.batch_norm.weight), gv(blk.batch_norm.bias)
                         if op.g_gamma is None or op.g_beta is None:   # frozen BN affine: scratch sinks
                             sink = torch.empty(2 * op.pc.c_out_pad, dtype=torch.float32, device=self.device)
                             op.g_gamma = op.g_gamma if op.g_gamma is not None else sink[:op.pc.c_out_pad]
@@ -448,7 +525,7 @@ class Trainer:
             calls.append((op, nc, pred, tgt, ps, ts, anc, sums, S))
         for op, nc, pred, tgt, ps, ts, anc, sums, S in calls:
             ds = (C.c_int64 * 5)(*plan.head_grad_strides(op, nc))
-            lib.yolo_loss_bwd(ptr(pred), ps, ptr(tgt), ts, plan.B, S, nc, anc, ptr(sums), 1.0, ptr(op.dz), ds, 1, st)
+            lib.yolo_loss_bwd(ptr(pred), ps, ptr(tgt), ts, plan.B, S, nc, anc, ptr(sums), 1.0, None, ptr(op.dz), ds, 1, st)
         # [box, object, no-object, class] summed over the three scales, weighted as loss.py:78-81 (device, no sync)
         s = plan.loss_sums.view(3, 6)
         n_obj, n_no = s[:, 5], s[:, 1]
@@ -461,32 +538,21 @@ class Trainer:
         return torch.stack([5 * box.sum(), obj.sum(), 0.5 * noobj.sum(), cls.sum()]).to(torch.float32)
 
     def _buckets(self, plan: TrainPlan):
-        """Contiguous ranges of the flat gradient buffer, each ready once the backward pass has gone below its
-        first op (parameters are laid out in module order = forward op order)."""
         if getattr(plan, "_bk", None) is None:
             firsts = []
             for i, op in enumerate(plan.ops):
                 ps = [p for p in op.block.parameters() if p.requires_grad]
                 if ps:
                     firsts.append((min(self.param_off[id(p)] for p in ps), i))
-            firsts.sort()
-            buckets, lo_idx = [], len(firsts)
-            hi = self.n_trainable
-            while lo_idx > 0:
-                j = lo_idx - 1
-                while j > 0 and hi - firsts[j][0] < self.bucket_elems:
-                    j -= 1
-                lo = firsts[j][0] if j > 0 else 0
-                first_op = min(f[1] for f in firsts[j:lo_idx])
-                buckets.append((first_op, lo, hi))
-                hi, lo_idx = lo, j
-            plan._bk = buckets
+            plan._bk = make_buckets(firsts, self.n_trainable, self.bucket_elems)
         return plan._bk
 
     def step(self, x: torch.Tensor, targets: Sequence[torch.Tensor], lr: Optional[float] = None) -> torch.Tensor:
         """One optimisation step (train.py:42-69).  Returns the device tensor [box, object, no_object, class] of
         the loss terms summed over the three scales (their sum is the reference's `loss`); no host sync."""
         require_cuda(x, "Trainer.step input")
+        if not self.own_params:
+            raise YoloB200Error("Trainer.step needs own_params=True (the autograd wrapper leaves the update to the caller)")
         if x.dim() != 4 or x.shape[1] != self.model.in_channels:
             raise YoloB200Error(f"expected (B,{self.model.in_channels},H,W) input, got {tuple(x.shape)}")
         if x.dtype != torch.float32 or not x.is_contiguous():
