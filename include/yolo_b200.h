@@ -227,6 +227,11 @@ int yolo_bn_stats(const void* z, long long P, int C, int pitch, double* sums2c, 
 int yolo_bn_finalize(const double* sums2c, long long P, int C, const float* gamma, const float* beta, float eps,
                      float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
                      float* scale, float* bias, yb_stream_t stream);
+/* yolo_bn_stats + yolo_bn_finalize in ONE launch: the block that finishes last (ticket in *counter, a device uint32
+ * that must be 0 on entry and is 0 again on exit) finalises the layer.                                           */
+int yolo_bn_stats_finalize(const void* z, long long P, int C, int pitch, double* sums2c, unsigned int* counter,
+                           const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                           float* running_var, float* mean, float* rstd, float* scale, float* bias, yb_stream_t stream);
 /* y = act(z*scale + bias) (+ residual); up2x: z is (B,h,w,C) and every pixel is stored to its 2x2 block of the
  * (B,2h,2w,*) tensor y (nn.Upsample + torch.cat, model.py:189-191, :222)                                       */
 int yolo_bn_act_fwd(const void* z, long long P, int C, int z_pitch, const float* scale, const float* bias, int act,
@@ -234,11 +239,12 @@ int yolo_bn_act_fwd(const void* z, long long P, int C, int z_pitch, const float*
                     yb_stream_t stream);
 /* dA: gradient of the block output (up2x: taken as the 2x2 block sums of a (B,2h,2w,*) tensor = backward of
  * nn.Upsample).  Writes dz (bf16), dgamma/dbeta (fp32, assigned) and, when `stuffed` != NULL, dz zero-stuffed
- * to (B,2h,2w,*) for the stride-2 convs' data gradient.  sums2c: 2C zeroed doubles, m1m2: 2C floats scratch.  */
+ * to (B,2h,2w,*) for the stride-2 convs' data gradient.  sums2c: 2C zeroed doubles, counter: zero uint32 (left zero),
+ * c1c0: 2C floats scratch.  Two launches: reduce (+ finalize by the last block) and apply.                       */
 int yolo_bn_act_bwd(const void* dA, int dA_pitch, int up2x, const void* z, int z_pitch, long long P, int C, int h,
                     int w, const float* scale, const float* bias, const float* mean, const float* rstd, int act,
-                    double* sums2c, float* dgamma, float* dbeta, float* m1m2, void* dz, int dz_pitch,
-                    void* stuffed, int stuffed_pitch, yb_stream_t stream);
+                    double* sums2c, unsigned int* counter, float* dgamma, float* dbeta, float* c1c0, void* dz,
+                    int dz_pitch, void* stuffed, int stuffed_pitch, yb_stream_t stream);
 /* bias gradient of the head conv (model.py:137, bias=True): dbias[c] = sum_p dz[p][c], c < C                   */
 int yolo_bias_grad(const void* dz, long long P, int C_pad, int pitch, int C, double* sums2c, float* dbias,
                    yb_stream_t stream);
@@ -259,6 +265,10 @@ int yolo_unpack_wgrad(const float* packed, int c_out, int c_in, int ksize, int c
  * out[ci][tap][co] = w[co][ci][k*k-1-tap]: yolo_conv_fwd on dz with this pack computes d conv / d input.   */
 int yolo_pack_weights_dgrad(const float* w_oihw, int c_out, int c_in, int ksize, int rows_pad, int cols_pad,
                             void* w_packed, yb_stream_t stream);
+/* Both operand packs of one layer in one pass (training: the weights change every step).  The padding entries of
+ * w_fwd [c_out_pad][k*k][c_in_pad] and w_dgrad [c_in_pad][k*k][c_out_pad] are NOT written: zero them once.       */
+int yolo_pack_weights_train(const float* w_oihw, int c_out, int c_in, int ksize, int c_in_pad, int c_out_pad,
+                            void* w_fwd, void* w_dgrad, yb_stream_t stream);
 /* torch.optim.SGD(momentum, weight_decay) (train.py:171-172) on flat fp32 buffers: g' = g*grad_scale + wd*p;
  * buf = first_step ? g' : momentum*buf + g'; p -= lr*buf                                                      */
 int yolo_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,

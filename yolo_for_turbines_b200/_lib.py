@@ -63,7 +63,9 @@ SIGNATURES = {
     "yolo_bn_stats": (_I, [_P, _LL, _I, _I, _P, _P]),
     "yolo_bn_finalize": (_I, [_P, _LL, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "yolo_bn_act_fwd": (_I, [_P, _LL, _I, _I, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
-    "yolo_bn_act_bwd": (_I, [_P, _I, _I, _P, _I, _LL, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
+    "yolo_bn_act_bwd": (_I, [_P, _I, _I, _P, _I, _LL, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
+    "yolo_bn_stats_finalize": (_I, [_P, _LL, _I, _I, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "yolo_pack_weights_train": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "yolo_bias_grad": (_I, [_P, _LL, _I, _I, _I, _P, _P, _P]),
     "yolo_wgrad_plan_bytes": (_SZ, []),
     "yolo_wgrad_plan_init": (_I, [_P, _SZ, C.POINTER(ConvDesc), _P, _P, _I, _P, _I]),

@@ -132,26 +132,85 @@ __global__ void __launch_bounds__(TR_THREADS) k_bn_stats(const __nv_bfloat16* __
 
 // nn.BatchNorm2d training semantics: normalise with the biased batch variance, update the running
 // statistics with momentum and the UNBIASED variance.
-__global__ void k_bn_finalize(const double* __restrict__ sums, long long P, int C, const float* __restrict__ gamma,
-                              const float* __restrict__ beta, float eps, float momentum, float* running_mean,
-                              float* running_var, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                              float* __restrict__ scale, float* __restrict__ bias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double n = double(P);
-  const double mean = sums[2 * c] / n;
-  double var = sums[2 * c + 1] / n - mean * mean;
+struct BnFinalize {
+  long long P;
+  const float *gamma, *beta;
+  float eps, momentum;
+  float *running_mean, *running_var, *mean, *rstd, *scale, *bias;
+};
+__device__ __forceinline__ void bn_finalize_channel(const BnFinalize& f, int c, double s, double q) {
+  const double n = double(f.P);
+  const double mean = s / n;
+  double var = q / n - mean * mean;
   if (var < 0.0) var = 0.0;
-  const float rstd = float(1.0 / sqrt(var + double(eps)));
-  const float sc = gamma[c] * rstd;
-  mean_out[c] = float(mean);
-  rstd_out[c] = rstd;
-  scale[c] = sc;
-  bias[c] = beta[c] - float(mean) * sc;
-  if (running_mean) {
-    const double unbiased = P > 1 ? var * n / (n - 1.0) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * float(mean);
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * float(unbiased);
+  const float rstd = float(1.0 / sqrt(var + double(f.eps)));
+  const float sc = f.gamma[c] * rstd;
+  f.mean[c] = float(mean);
+  f.rstd[c] = rstd;
+  f.scale[c] = sc;
+  f.bias[c] = f.beta[c] - float(mean) * sc;
+  if (f.running_mean) {
+    const double unbiased = f.P > 1 ? var * n / (n - 1.0) : var;
+    f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * float(mean);
+    f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * float(unbiased);
+  }
+}
+__global__ void k_bn_finalize(const double* __restrict__ sums, int C, const BnFinalize f) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) bn_finalize_channel(f, c, sums[2 * c], sums[2 * c + 1]);
+}
+
+// The block that takes the last ticket sees every other block's (L2-resident) atomics: it finishes the layer.
+__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+    if (is_last) *counter = 0u;  // ready for the next launch
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// k_bn_stats + k_bn_finalize in one launch
+__global__ void __launch_bounds__(TR_THREADS) k_bn_stats_fused(const __nv_bfloat16* __restrict__ z, int pitch, RowGeom g,
+                                                               double* __restrict__ sums, unsigned int* counter,
+                                                               const BnFinalize f) {
+  __shared__ float red[16 * RED_STRIDE];
+  const int lanes = TR_THREADS / g.groups;
+  const int grp = threadIdx.x % g.groups, lane = threadIdx.x / g.groups;
+  const long long per_block = (g.P + gridDim.x - 1) / gridDim.x;
+  const long long r0 = per_block * blockIdx.x;
+  const long long r1 = r0 + per_block < g.P ? r0 + per_block : g.P;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool active = lane < lanes;
+  if (active) {
+    long long r = r0 + lane;
+    for (; r + 3ll * lanes < r1; r += 4ll * lanes) {
+      uint4 u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[j] = ld8(z, size_t(r + (long long)j * lanes), pitch, grp * 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v[8];
+        unpack8(u[j], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
+      }
+    }
+    for (; r < r1; r += lanes) {
+      float v[8];
+      unpack8(ld8(z, size_t(r), pitch, grp * 8), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s[k] += v[k]; q[k] = fmaf(v[k], v[k], q[k]); }
+    }
+  }
+  block_channel_reduce(s, q, g.groups, lanes, active, g.C, red, sums);
+  if (last_block_done(counter)) {
+    for (int c = threadIdx.x; c < g.C; c += TR_THREADS) bn_finalize_channel(f, c, __ldcg(sums + 2 * c), __ldcg(sums + 2 * c + 1));
   }
 }
 
@@ -230,8 +289,26 @@ struct BnBwdParams {
   RowGeom g;
 };
 
-// sums[2c] += sum dy, sums[2c+1] += sum dy * xhat   with dy = dA * act'(z*scale+bias), xhat = (z-mean)*rstd
-__global__ void __launch_bounds__(TR_THREADS) k_bn_act_bwd_reduce(const BnBwdParams p, double* __restrict__ sums) {
+// Pass 1: sums[2c] += sum dy, sums[2c+1] += sum dy * z with dy = dA * act'(z*scale+bias); the last block turns them
+// into dbeta = sum dy, dgamma = sum dy*xhat = rstd * (sum dy*z - mean * sum dy) and the two coefficient vectors of
+// pass 2:  dz = scale*dy + c1*z + c0,  c1 = -scale*rstd*dgamma/P,  c0 = -scale*dbeta/P - c1*mean
+// (= scale * (dy - mean(dy) - xhat * mean(dy*xhat)), the BatchNorm backward).
+struct BnBwdFinalize {
+  long long P;
+  float *dgamma, *dbeta, *c1, *c0;
+};
+__device__ __forceinline__ void bn_bwd_finalize_channel(const BnBwdParams& p, const BnBwdFinalize& f, int c, double s, double q) {
+  const double mu = double(p.mean[c]), rs = double(p.rstd[c]), sc = double(p.scale[c]);
+  const double dgam = rs * (q - mu * s);
+  f.dbeta[c] = float(s);
+  f.dgamma[c] = float(dgam);
+  const double c1 = -sc * rs * dgam / double(f.P);
+  f.c1[c] = float(c1);
+  f.c0[c] = float(-sc * s / double(f.P) - c1 * mu);
+}
+
+__global__ void __launch_bounds__(TR_THREADS, 3) k_bn_act_bwd_reduce(const BnBwdParams p, double* __restrict__ sums,
+                                                                     unsigned int* counter, const BnBwdFinalize f) {
   __shared__ float red[16 * RED_STRIDE];
   const RowGeom& g = p.g;
   const int lanes = TR_THREADS / g.groups;
@@ -243,14 +320,14 @@ __global__ void __launch_bounds__(TR_THREADS) k_bn_act_bwd_reduce(const BnBwdPar
   const bool active = lane < lanes;
   if (active) {
     const int c = grp * 8;
-    float sc[8], bi[8], mu[8], rs[8];
-    ld8f(p.scale + c, sc); ld8f(p.bias + c, bi); ld8f(p.mean + c, mu); ld8f(p.rstd + c, rs);
+    float sc[8], bi[8];
+    ld8f(p.scale + c, sc); ld8f(p.bias + c, bi);
     auto accum = [&](const float (&zf)[8], const float (&d)[8]) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float dy = d[k] * act_grad(fmaf(zf[k], sc[k], bi[k]), p.act);
         s[k] += dy;
-        q[k] = fmaf(dy, (zf[k] - mu[k]) * rs[k], q[k]);
+        q[k] = fmaf(dy, zf[k], q[k]);
       }
     };
     long long r = r0 + lane;
@@ -271,28 +348,23 @@ __global__ void __launch_bounds__(TR_THREADS) k_bn_act_bwd_reduce(const BnBwdPar
     }
   }
   block_channel_reduce(s, q, g.groups, lanes, active, g.C, red, sums);
-}
-
-// BatchNorm layer: dbeta = sum dy, dgamma = sum dy*xhat, m1 = dbeta / P, m2 = dgamma / P.
-// Bias-only conv (gamma == nullptr): sums[2c] is the bias gradient.
-__global__ void k_bn_bwd_finalize(const double* __restrict__ sums, long long P, int C, int has_bn, float* __restrict__ dgamma,
-                                  float* __restrict__ dbeta, float* __restrict__ m1, float* __restrict__ m2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double s = sums[2 * c], q = sums[2 * c + 1];
-  dbeta[c] = float(s);
-  if (has_bn) {
-    dgamma[c] = float(q);
-    m1[c] = float(s / double(P));
-    m2[c] = float(q / double(P));
+  if (last_block_done(counter)) {
+    for (int c = threadIdx.x; c < g.C; c += TR_THREADS)
+      bn_bwd_finalize_channel(p, f, c, __ldcg(sums + 2 * c), __ldcg(sums + 2 * c + 1));
   }
 }
 
-// dz = scale * (dy - m1 - xhat * m2); optional zero-stuffed copy at 2x resolution (value at (2i, 2j))
-__global__ void __launch_bounds__(TR_THREADS) k_bn_act_bwd_apply(const BnBwdParams p, const float* __restrict__ m1,
-                                                                 const float* __restrict__ m2, __nv_bfloat16* __restrict__ dz,
-                                                                 int dz_pitch, __nv_bfloat16* __restrict__ stuffed,
-                                                                 int stuffed_pitch) {
+// bias-only conv: sums[2c] is the bias gradient
+__global__ void k_bias_finalize(const double* __restrict__ sums, int C, float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) dbias[c] = float(sums[2 * c]);
+}
+
+// Pass 2: dz = scale*dy + c1*z + c0; optional zero-stuffed copy at 2x resolution (value at (2i, 2j))
+__global__ void __launch_bounds__(TR_THREADS, 4) k_bn_act_bwd_apply(const BnBwdParams p, const float* __restrict__ c1,
+                                                                    const float* __restrict__ c0, __nv_bfloat16* __restrict__ dz,
+                                                                    int dz_pitch, __nv_bfloat16* __restrict__ stuffed,
+                                                                    int stuffed_pitch) {
   const RowGeom& g = p.g;
   const long long idx = (long long)blockIdx.x * TR_THREADS + threadIdx.x;
   if (idx >= g.P * g.groups) return;
@@ -301,13 +373,17 @@ __global__ void __launch_bounds__(TR_THREADS) k_bn_act_bwd_apply(const BnBwdPara
   float zf[8], d[8], o[8];
   unpack8(ld8(p.z, size_t(r), p.z_pitch, c), zf);
   load_dA(p.dA, p.dA_pitch, g, r, c, p.up2x, d);
-  float sc[8], bi[8], mu[8], rs[8], a1[8], a2[8];
-  ld8f(p.scale + c, sc); ld8f(p.bias + c, bi); ld8f(p.mean + c, mu); ld8f(p.rstd + c, rs); ld8f(m1 + c, a1); ld8f(m2 + c, a2);
+  {
+    float sc[8], bi[8];
+    ld8f(p.scale + c, sc); ld8f(p.bias + c, bi);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float dy = d[k] * act_grad(fmaf(zf[k], sc[k], bi[k]), p.act);
-    const float xh = (zf[k] - mu[k]) * rs[k];
-    o[k] = sc[k] * (dy - a1[k] - xh * a2[k]);
+    for (int k = 0; k < 8; ++k) o[k] = sc[k] * d[k] * act_grad(fmaf(zf[k], sc[k], bi[k]), p.act);
+  }
+  {
+    float a1[8], a0[8];
+    ld8f(c1 + c, a1); ld8f(c0 + c, a0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] += fmaf(a1[k], zf[k], a0[k]);
   }
   const uint4 u = pack8(o);
   *reinterpret_cast<uint4*>(dz + size_t(r) * dz_pitch + c) = u;
@@ -324,6 +400,22 @@ __global__ void __launch_bounds__(TR_THREADS) k_bn_act_bwd_apply(const BnBwdPara
     *reinterpret_cast<uint4*>(stuffed + (r00 + W2) * stuffed_pitch + c) = zero;
     *reinterpret_cast<uint4*>(stuffed + (r00 + W2 + 1) * stuffed_pitch + c) = zero;
   }
+}
+
+// forward + data-gradient operand packs of one layer in one pass over the fp32 weights:
+//   fwd[co][tap][ci] = w[co][ci][tap]            ([c_out_pad][taps][c_in_pad], padding pre-zeroed by the caller)
+//   bwd[ci][taps-1-tap][co] = w[co][ci][tap]     ([c_in_pad][taps][c_out_pad])
+__global__ void k_pack_weights_both(const float* __restrict__ w, int c_out, int c_in, int taps, int c_in_pad, int c_out_pad,
+                                    __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ bwd) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)c_out * c_in * taps;
+  if (idx >= total) return;
+  const int tap = int(idx % taps);
+  const int ci = int((idx / taps) % c_in);
+  const int co = int(idx / ((long long)taps * c_in));
+  const __nv_bfloat16 v = __float2bfloat16_rn(w[idx]);
+  fwd[(size_t(co) * taps + tap) * c_in_pad + ci] = v;
+  bwd[(size_t(ci) * taps + (taps - 1 - tap)) * c_out_pad + co] = v;
 }
 
 // packed fp32 [c_out_pad][taps][c_in_pad] -> OIHW (c_out, c_in, k, k); stem: packed [c_out_pad][32] with
@@ -388,7 +480,7 @@ int check_rows(long long P, int C, int pitch, const char* what) {
 }
 int reduce_grid(long long P, int groups) {
   const int lanes = TR_THREADS / groups;
-  long long blocks = (P + (long long)lanes * 16 - 1) / ((long long)lanes * 16);  // >= 16 rows per thread
+  long long blocks = (P + (long long)lanes * 8 - 1) / ((long long)lanes * 8);  // >= 8 rows per thread
   if (blocks > 148 * 6) blocks = 148 * 6;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -410,8 +502,22 @@ extern "C" int yolo_bn_finalize(const double* sums2c, long long P, int C, const 
                                 float momentum, float* running_mean, float* running_var, float* mean, float* rstd,
                                 float* scale, float* bias, yb_stream_t stream) {
   YB_REQUIRE(sums2c && gamma && beta && mean && rstd && scale && bias && P >= 1 && C >= 1, "yolo_bn_finalize: bad argument");
-  k_bn_finalize<<<yb_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums2c, P, C, gamma, beta, eps, momentum, running_mean,
-                                                                   running_var, mean, rstd, scale, bias);
+  const BnFinalize f{P, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, bias};
+  k_bn_finalize<<<yb_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums2c, C, f);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+extern "C" int yolo_bn_stats_finalize(const void* z, long long P, int C, int pitch, double* sums2c, unsigned int* counter,
+                                      const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                                      float* running_var, float* mean, float* rstd, float* scale, float* bias,
+                                      yb_stream_t stream) {
+  YB_REQUIRE(z && sums2c && counter && gamma && beta && mean && rstd && scale && bias, "yolo_bn_stats_finalize: null pointer");
+  if (int rc = check_rows(P, C, pitch, "yolo_bn_stats_finalize")) return rc;
+  RowGeom g{P, C, C / 8, 0, 0};
+  const BnFinalize f{P, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale, bias};
+  k_bn_stats_fused<<<reduce_grid(P, g.groups), TR_THREADS, 0, (cudaStream_t)stream>>>(static_cast<const __nv_bfloat16*>(z), pitch, g,
+                                                                                     sums2c, counter, f);
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -434,9 +540,11 @@ extern "C" int yolo_bn_act_fwd(const void* z, long long P, int C, int z_pitch, c
 
 extern "C" int yolo_bn_act_bwd(const void* dA, int dA_pitch, int up2x, const void* z, int z_pitch, long long P, int C, int h, int w,
                                const float* scale, const float* bias, const float* mean, const float* rstd, int act,
-                               double* sums2c /* zeroed */, float* dgamma, float* dbeta, float* m1m2 /* [2C] scratch */,
-                               void* dz, int dz_pitch, void* stuffed, int stuffed_pitch, yb_stream_t stream_) {
-  YB_REQUIRE(dA && z && scale && bias && mean && rstd && sums2c && dgamma && dbeta && m1m2 && dz, "yolo_bn_act_bwd: null pointer");
+                               double* sums2c /* zeroed */, unsigned int* counter /* zero */, float* dgamma, float* dbeta,
+                               float* c1c0 /* [2C] scratch */, void* dz, int dz_pitch, void* stuffed, int stuffed_pitch,
+                               yb_stream_t stream_) {
+  YB_REQUIRE(dA && z && scale && bias && mean && rstd && sums2c && counter && dgamma && dbeta && c1c0 && dz,
+             "yolo_bn_act_bwd: null pointer");
   if (int rc = check_rows(P, C, z_pitch, "yolo_bn_act_bwd")) return rc;
   YB_REQUIRE(dA_pitch >= C && dA_pitch % 8 == 0 && dz_pitch >= C && dz_pitch % 8 == 0, "yolo_bn_act_bwd: bad pitch");
   YB_REQUIRE((!up2x && !stuffed) || (h >= 1 && w >= 1 && P % ((long long)h * w) == 0), "yolo_bn_act_bwd: bad 2x geometry");
@@ -447,13 +555,12 @@ extern "C" int yolo_bn_act_bwd(const void* dA, int dA_pitch, int up2x, const voi
   p.z = static_cast<const __nv_bfloat16*>(z); p.z_pitch = z_pitch;
   p.scale = scale; p.bias = bias; p.mean = mean; p.rstd = rstd; p.act = act;
   p.g = RowGeom{P, C, C / 8, h, w};
-  k_bn_act_bwd_reduce<<<reduce_grid(P, p.g.groups), TR_THREADS, 0, stream>>>(p, sums2c);
-  YB_CHECK_LAUNCH();
-  k_bn_bwd_finalize<<<yb_cdiv(C, 128), 128, 0, stream>>>(sums2c, P, C, 1, dgamma, dbeta, m1m2, m1m2 + C);
+  const BnBwdFinalize f{P, dgamma, dbeta, c1c0, c1c0 + C};
+  k_bn_act_bwd_reduce<<<reduce_grid(P, p.g.groups), TR_THREADS, 0, stream>>>(p, sums2c, counter, f);
   YB_CHECK_LAUNCH();
   const long long n = P * p.g.groups;
   k_bn_act_bwd_apply<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, stream>>>(
-      p, m1m2, m1m2 + C, static_cast<__nv_bfloat16*>(dz), dz_pitch, static_cast<__nv_bfloat16*>(stuffed), stuffed_pitch);
+      p, c1c0, c1c0 + C, static_cast<__nv_bfloat16*>(dz), dz_pitch, static_cast<__nv_bfloat16*>(stuffed), stuffed_pitch);
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -467,7 +574,7 @@ extern "C" int yolo_bias_grad(const void* dz, long long P, int C_pad, int pitch,
   k_bn_stats<<<reduce_grid(P, g.groups), TR_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(dz),
                                                                                           pitch, g, sums2c);
   YB_CHECK_LAUNCH();
-  k_bn_bwd_finalize<<<yb_cdiv(C, 128), 128, 0, stream>>>(sums2c, P, C, 0, nullptr, dbias, nullptr, nullptr);
+  k_bias_finalize<<<yb_cdiv(C, 128), 128, 0, stream>>>(sums2c, C, dbias);
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -490,6 +597,17 @@ extern "C" int yolo_pack_weights_dgrad(const float* w_oihw, int c_out, int c_in,
   const long long total = (long long)rows_pad * ksize * ksize * cols_pad;
   k_pack_weights_dgrad<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       w_oihw, c_out, c_in, ksize * ksize, rows_pad, cols_pad, static_cast<__nv_bfloat16*>(w_packed));
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+extern "C" int yolo_pack_weights_train(const float* w_oihw, int c_out, int c_in, int ksize, int c_in_pad, int c_out_pad,
+                                       void* w_fwd, void* w_dgrad, yb_stream_t stream) {
+  YB_REQUIRE(w_oihw && w_fwd && w_dgrad && c_out >= 1 && c_in >= 1 && (ksize == 1 || ksize == 3) && c_in_pad >= c_in &&
+                 c_out_pad >= c_out, "yolo_pack_weights_train: bad argument");
+  const long long total = (long long)c_out * c_in * ksize * ksize;
+  k_pack_weights_both<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, c_out, c_in, ksize * ksize, c_in_pad, c_out_pad, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }

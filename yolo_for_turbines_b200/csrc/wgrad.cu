@@ -19,6 +19,7 @@
 // where one tap alone is a 128 x 32 tile with next to no work per pipeline stage.
 //
 // Warp roles (192 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2..5 = epilogue.
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -66,13 +67,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 template <int NT>
-__global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__ WgradKParams p) {
+__global__ void __launch_bounds__(WG_THREADS, 2) k_wgrad(const __grid_constant__ WgradKParams p) {
   constexpr uint32_t B_BYTES = KP * NT * 2;
   const uint32_t STAGE_BYTES = WG_A_BYTES + uint32_t(p.tp) * B_BYTES;
   const uint32_t TMEM_COLS = uint32_t(p.tmem_cols);
-  // bf16 x bf16 -> fp32, A and B both MN-major (bits 15, 16), N = NT, M = 128
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(NT >> 3) << 17) |
-                             (uint32_t(128 >> 4) << 24);
+  // bf16 x bf16 -> fp32, A and B both MN-major (bits 15, 16), M = 128; N is filled in per MMA
+  constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(128 >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int stages = p.stages;
@@ -166,11 +166,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const __grid_constant__
       tc_fence_after();
       if (elect_one()) {
         const uint64_t soff = uint64_t((uint32_t(s) * STAGE_BYTES) >> 4);
-        for (int t = 0; t < ntaps; ++t) {
-          const uint64_t boff = soff + uint64_t((uint32_t(t) * B_BYTES) >> 4);
+        // The x boxes of one stage form a uniform array of channel groups LBO apart -- across the groups of one tap
+        // AND across taps -- so up to 256 accumulator columns (several taps) go into ONE MMA.
+        const int total_cols = ntaps * NT;
+        for (int col0 = 0; col0 < total_cols; col0 += 256) {
+          const int n = total_cols - col0 < 256 ? total_cols - col0 : 256;
+          const uint32_t idesc = IDESC_BASE | (uint32_t(n >> 3) << 17);
+          const uint64_t boff = soff + uint64_t((uint32_t(col0 / p.xc) * KP * x_row_bytes) >> 4);
 #pragma unroll
           for (int k = 0; k < KP / 16; ++k)
-            umma_bf16(tmem_base + uint32_t(t * NT), adesc0 + soff + a_kstep * k, bdesc0 + boff + b_kstep * k, IDESC,
+            umma_bf16(tmem_base + uint32_t(col0), adesc0 + soff + a_kstep * k, bdesc0 + boff + b_kstep * k, idesc,
                       (c | k) != 0 ? 1u : 0u);
         }
         umma_commit(empty_bar(s));
@@ -305,6 +310,10 @@ extern "C" int yolo_wgrad_plan_init(void* plan_host, size_t plan_bytes, const yo
   kp.tiles_m = (d->c_out_pad + 127) / 128;
   kp.n_per_tap = d->c_in / nt;
   int tp = 512 / nt;                       // accumulators that fit TMEM
+  if (const char* e = getenv("YOLO_B200_WGRAD_TP")) {      // tuning aid
+    const int v = atoi(e);
+    if (v >= 1 && v < tp) tp = v;
+  }
   if (tp > kp.taps) tp = kp.taps;
   if (kp.taps == 9 && tp >= 3 && tp < 9) tp = 3;   // 3 balanced groups instead of e.g. 4 + 4 + 1
   if (nt == 256) tp = 1;                   // 48 KB per tap and stage: keep the ring deep instead
@@ -316,15 +325,23 @@ extern "C" int yolo_wgrad_plan_init(void* plan_host, size_t plan_bytes, const yo
   int dev = 0, sms = 148;
   YB_CHECK_CUDA(cudaGetDevice(&dev));
   YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int splits = splits_hint > 0 ? splits_hint : (2 * sms + tiles - 1) / tiles;
-  const int max_splits = (kp.num_chunks + 3) / 4;  // at least ~4 chunks of 64 pixels per CTA
+  // Two CTAs share an SM (the epilogue of one overlaps the main loop of the other) when both fit: <= 256 TMEM
+  // columns and <= ~110 KB of shared memory each; otherwise one wave of one CTA per SM.
+  const bool pair_up = kp.tmem_cols <= 256;
+  int splits = splits_hint > 0 ? splits_hint : ((pair_up ? 2 : 1) * sms) / tiles;
+  const int max_splits = (kp.num_chunks + 15) / 16;  // >= ~16 chunks of 64 pixels per CTA: bounds the red.global traffic
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   kp.chunks_per_split = (kp.num_chunks + splits - 1) / splits;
   kp.splits = (kp.num_chunks + kp.chunks_per_split - 1) / kp.chunks_per_split;  // no empty CTA
   const uint32_t stage_bytes = WG_A_BYTES + uint32_t(tp) * KP * nt * 2;
-  int stages = (int)((220u * 1024u) / stage_bytes);
+  int stages = (int)(((pair_up ? 108u : 220u) * 1024u) / stage_bytes);
   if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  if (const char* e = getenv("YOLO_B200_WGRAD_STAGES")) {  // tuning aid
+    const int v = atoi(e);
+    if (v >= 1 && v < stages) stages = v;
+  }
   kp.stages = stages;
   pl->nt = nt;
   pl->smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;

@@ -54,7 +54,7 @@ class _Grad:
 
 class _TrainOp:
     __slots__ = ("pc", "block", "src", "dst", "res", "upsample", "head", "name", "z", "P", "ho", "wo", "fwd_plan",
-                 "dgrad_plan", "wgrad_plan", "wT", "dz", "bn", "dw_off", "g_w", "g_b", "g_gamma", "g_beta", "stuffed")
+                 "dgrad_plan", "wgrad_plan", "wT", "dz", "bn", "dw_off", "g_w", "g_b", "g_gamma", "g_beta", "stuffed", "index")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -148,6 +148,7 @@ class TrainPlan:
         self.sums = torch.zeros(2 * n_bn * 2, dtype=torch.float64, device=dev)      # fwd stats | bwd sums
         self.bnf = torch.empty(6 * n_bn, dtype=torch.float32, device=dev)           # mean rstd scale bias m1 m2
         self.loss_sums = torch.zeros(18, dtype=torch.float64, device=dev)
+        self.counters = torch.zeros(2 * len(self.ops), dtype=torch.int32, device=dev)   # last-block tickets (self-resetting)
         stuffed_elems = max([B * op.src.H * op.src.W * op.pc.c_out_pad for op in self.ops[1:] if op.pc.stride_eff == 2] + [0])
         self.stuffed = alloc(stuffed_elems, torch.bfloat16) if stuffed_elems else None
 
@@ -156,6 +157,7 @@ class TrainPlan:
         boff = 0
         for i, op in enumerate(self.ops):
             cp = op.pc.c_out_pad
+            op.index = i
             op.bn = dict(sums=self.sums[2 * boff: 2 * boff + 2 * cp], bsums=self.sums[2 * n_bn + 2 * boff: 2 * n_bn + 2 * boff + 2 * cp],
                          mean=self.bnf[boff:boff + cp], rstd=self.bnf[n_bn + boff:n_bn + boff + cp],
                          scale=self.bnf[2 * n_bn + boff:2 * n_bn + boff + cp], bias=self.bnf[3 * n_bn + boff:3 * n_bn + boff + cp],
@@ -276,10 +278,10 @@ class TrainPlan:
                 continue
             pc, bn, blk = op.pc, op.bn, op.block.batch_norm
             C_ = pc.c_out
-            lib.yolo_bn_stats(ptr(op.z), op.P, C_, pc.c_out_pad, ptr(bn["sums"]), st)
-            lib.yolo_bn_finalize(ptr(bn["sums"]), op.P, C_, ptr(blk.weight), ptr(blk.bias), float(blk.eps),
-                                 float(blk.momentum if blk.momentum is not None else 0.1), ptr(blk.running_mean),
-                                 ptr(blk.running_var), ptr(bn["mean"]), ptr(bn["rstd"]), ptr(bn["scale"]), ptr(bn["bias"]), st)
+            lib.yolo_bn_stats_finalize(ptr(op.z), op.P, C_, pc.c_out_pad, ptr(bn["sums"]), _p(self.counters, 8 * op.index),
+                                       ptr(blk.weight), ptr(blk.bias), float(blk.eps),
+                                       float(blk.momentum if blk.momentum is not None else 0.1), ptr(blk.running_mean),
+                                       ptr(blk.running_var), ptr(bn["mean"]), ptr(bn["rstd"]), ptr(bn["scale"]), ptr(bn["bias"]), st)
             droot, doff = op.dst.resolve()
             res_ptr, res_pitch = None, 0
             if op.res is not None:
@@ -304,7 +306,8 @@ class TrainPlan:
                 gbuf, goff, gpitch = self._final_grad(op.dst)
                 lib.yolo_bn_act_bwd(_p(gbuf, 2 * goff), gpitch, int(op.upsample), ptr(op.z), pc.c_out_pad, op.P, pc.c_out,
                                     op.ho, op.wo, ptr(bn["scale"]), ptr(bn["bias"]), ptr(bn["mean"]), ptr(bn["rstd"]),
-                                    ACT_CODES[pc.act], ptr(bn["bsums"]), ptr(op.g_gamma), ptr(op.g_beta), ptr(bn["m1m2"]),
+                                    ACT_CODES[pc.act], ptr(bn["bsums"]), _p(self.counters, 8 * op.index + 4), ptr(op.g_gamma),
+                                    ptr(op.g_beta), ptr(bn["m1m2"]),
                                     ptr(op.dz), pc.c_out_pad, ptr(op.stuffed) if op.stuffed is not None else None,
                                     pc.c_out_pad, st)
             if op.g_w is not None:
@@ -449,12 +452,13 @@ class Trainer:
         self.plans: Dict[tuple, TrainPlan] = {}
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.bucket_elems = int(bucket_mb * 1e6 / 4)
-        self.repack()
+        self.repack(full=True)
 
     # ------------------------------------------------------------------------------------------------------
-    def repack(self):
+    def repack(self, full: bool = False):
         """bf16 operand packs of the current fp32 weights: forward [Cout][k][k][Cin] and data-gradient
-        [Cin][k][k][Cout] (flipped)."""
+        [Cin][k][k][Cout] (flipped).  full=True also writes the zero padding (once, at construction); afterwards
+        one launch per layer rewrites the real entries of both packs."""
         dev = self.device
         with torch.cuda.device(dev):
             st = stream_ptr(dev)
@@ -463,9 +467,12 @@ class Trainer:
                 w = b.conv.weight
                 if pc.stem:
                     lib.yolo_pack_stem_weights(ptr(w), pc.c_out, pc.c_in, pc.c_out_pad, ptr(pc.w), st)
-                else:
+                elif full:
                     lib.yolo_pack_weights(ptr(w), pc.c_out, pc.c_in, pc.ksize, pc.c_out_pad, pc.c_in_eff, ptr(pc.w), st)
                     lib.yolo_pack_weights_dgrad(ptr(w), pc.c_out, pc.c_in, pc.ksize, pc.c_in_eff, pc.c_out_pad,
+                                                ptr(self.wT[id(b)]), st)
+                else:
+                    lib.yolo_pack_weights_train(ptr(w), pc.c_out, pc.c_in, pc.ksize, pc.c_in_eff, pc.c_out_pad, ptr(pc.w),
                                                 ptr(self.wT[id(b)]), st)
                 if not b.batch_norm_act:  # head conv: scale 1, bias = conv bias
                     lib.yolo_fold_bn(None, None, None, None, ptr(b.conv.bias), 0.0, pc.c_out, pc.c_out_pad, ptr(pc.scale),
@@ -593,8 +600,8 @@ class Trainer:
     def launches_per_step(self, plan: TrainPlan) -> int:
         n_bn = sum(1 for op in plan.ops if not op.head)
         n_head = len(plan.heads)
-        fwd = 1 + len(plan.ops) + 3 * n_bn
+        fwd = 1 + len(plan.ops) + 2 * n_bn
         loss = 2 * n_head
-        bwd = 3 * n_bn + 2 * n_head + 2 * len(plan.ops) + (len(plan.ops) - 1)
-        upd = 1 + 2 * len(plan.ops) - 1 + n_head
+        bwd = 2 * n_bn + 2 * n_head + 2 * len(plan.ops) + (len(plan.ops) - 1)
+        upd = 1 + len(plan.ops) + n_head
         return fwd + loss + bwd + upd
