@@ -141,6 +141,14 @@ int yolo_nhwc_to_nchw_f32(const void* x, int in_is_fp32, int batch, int c, int h
 int yolo_input_patchify(const float* x, int batch, int c, int h, int w, void* y,
                         uint32_t* status, yb_stream_t stream);
 
+/* Inference pre-processing -- replaces the albumentations/OpenCV CPU pipeline of config.py:101-113
+ * (`set_only_image_transforms`, used by demo.py:37-39): LongestMaxSize(S) with cv2.INTER_LINEAR's uint8 fixed-point
+ * arithmetic, centred zero padding to S x S, /255, HWC -> CHW; fp32 (batch, channels, S, S) out.  descs_dev is a
+ * DEVICE array of yolo_letterbox_desc_bytes()-sized records {const uint8_t* data; int32 h, w, nh, nw, top, left}:
+ * source image (dense HWC uint8, device), resized size and padding offsets (host-computed, see preprocess.py).  */
+size_t yolo_letterbox_desc_bytes(void);
+int yolo_letterbox_u8(const void* descs_dev, int batch, int size, int channels, float* out, yb_stream_t stream);
+
 /* ------------------------------------------------------------------------- *
  * K3  anchor decode -- replaces utils.py:86-148 cells_to_boxes.
  * head: (B,3,S,S,5+nc) with arbitrary element strides st[5]; fp32.

@@ -53,6 +53,8 @@ SIGNATURES = {
     "yolo_nchw_to_nhwc_bf16": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "yolo_nhwc_to_nchw_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "yolo_input_patchify": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "yolo_letterbox_desc_bytes": (_SZ, []),
+    "yolo_letterbox_u8": (_I, [_P, _I, _I, _I, _P, _P]),
     "yolo_decode": (_I, [_P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _I, _I, _P, _I, _I, _P]),
     "yolo_nms_workspace_bytes": (_SZ, [_I, _I]),
     "yolo_nms": (_I, [_P, _P, _I, _I, _F, _D, _I, _I, _P, _P, _P, _SZ, _P]),

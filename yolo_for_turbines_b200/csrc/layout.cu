@@ -211,3 +211,85 @@ extern "C" int yolo_input_patchify(const float* x, int batch, int c, int h, int 
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Inference pre-processing: what code/config.py:101-113 `set_only_image_transforms` does on
+// the CPU through albumentations + OpenCV (demo.py:37-39), for a batch of uint8 HWC images of different sizes:
+//   LongestMaxSize(S) [cv2.resize INTER_LINEAR, uint8 fixed point] -> PadIfNeeded(S, S, constant 0, centred)
+//   -> Normalize(mean 0, std 1, max_pixel 255) -> ToTensorV2 (HWC -> CHW), written as fp32 (B, 3, S, S).
+// One thread per output pixel recomputes OpenCV's coordinate / 11-bit weight arithmetic (resize.cpp, generic
+// linear path; see oracle/preprocess_oracle.py for the restatement that is pinned bit-for-bit against cv2):
+// horizontally a coordinate beyond the border snaps to the border pixel, vertically only the row index is
+// clipped; vertical pass ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
+namespace {
+
+struct LetterboxImage {
+  const uint8_t* data;  // HWC uint8, dense
+  int h, w;             // source size
+  int nh, nw;           // resized size (LongestMaxSize), computed on the host with Python's round-half-even
+  int top, left;        // PadIfNeeded offsets
+};
+
+__device__ __forceinline__ void lb_axis(int d, int src, int dst, bool vertical, int& i0, int& i1, int& w0, int& w1) {
+  const double inv_scale = double(dst) / double(src);
+  const double scale = 1.0 / inv_scale;
+  float f = float((double(d) + 0.5) * scale - 0.5);
+  int s = int(floorf(f));
+  f -= float(s);
+  if (!vertical) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= src - 1) { f = 0.f; s = src - 1; }
+  }
+  w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  i0 = min(max(s, 0), src - 1);
+  i1 = min(max(s + 1, 0), src - 1);
+}
+
+__global__ void __launch_bounds__(256) k_letterbox(const LetterboxImage* __restrict__ imgs, int size, int channels,
+                                                   float* __restrict__ out) {
+  const LetterboxImage im = imgs[blockIdx.z];
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= size || y >= size) return;
+  float* o = out + (size_t(blockIdx.z) * channels * size + y) * size + x;
+  const size_t plane = size_t(size) * size;
+  const int rx = x - im.left, ry = y - im.top;
+  if (rx < 0 || rx >= im.nw || ry < 0 || ry >= im.nh) {
+    for (int c = 0; c < channels; ++c) o[c * plane] = 0.f;
+    return;
+  }
+  const float inv255 = 1.0f / 255.0f;
+  if (im.nh == im.h && im.nw == im.w) {  // LongestMaxSize leaves the image alone when scale == 1
+    const uint8_t* p = im.data + (size_t(ry) * im.w + rx) * channels;
+    for (int c = 0; c < channels; ++c) o[c * plane] = __fmul_rn(float(p[c]), inv255);
+    return;
+  }
+  int x0, x1, a0, a1, y0, y1, b0, b1;
+  lb_axis(rx, im.w, im.nw, false, x0, x1, a0, a1);
+  lb_axis(ry, im.h, im.nh, true, y0, y1, b0, b1);
+  const uint8_t* r0 = im.data + size_t(y0) * im.w * channels;
+  const uint8_t* r1 = im.data + size_t(y1) * im.w * channels;
+  for (int c = 0; c < channels; ++c) {
+    const int s0 = int(r0[x0 * channels + c]) * a0 + int(r0[x1 * channels + c]) * a1;  // horizontal pass, 2^11 scale
+    const int s1 = int(r1[x0 * channels + c]) * a0 + int(r1[x1 * channels + c]) * a1;
+    int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+    v = min(max(v, 0), 255);
+    o[c * plane] = __fmul_rn(float(v), inv255);
+  }
+}
+
+}  // namespace
+
+extern "C" size_t yolo_letterbox_desc_bytes(void) { return sizeof(LetterboxImage); }
+
+// descs_dev: device array of `batch` descriptors laid out as {const uint8_t* data; int32 h, w, nh, nw, top, left}
+// (yolo_letterbox_desc_bytes() bytes each).
+extern "C" int yolo_letterbox_u8(const void* descs_dev, int batch, int size, int channels, float* out, yb_stream_t stream) {
+  YB_REQUIRE(descs_dev && out && batch >= 0 && size >= 1 && channels >= 1 && channels <= 4, "yolo_letterbox_u8: bad argument");
+  if (batch == 0) return YB_OK;
+  dim3 grid((size + 31) / 32, (size + 7) / 8, batch);
+  k_letterbox<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const LetterboxImage*>(descs_dev), size, channels, out);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
