@@ -281,6 +281,13 @@ int yolo_pack_weights_train(const float* w_oihw, int c_out, int c_in, int ksize,
  * buf = first_step ? g' : momentum*buf + g'; p -= lr*buf                                                      */
 int yolo_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                   float weight_decay, float grad_scale, int first_step, yb_stream_t stream);
+/* Training-target encoder -- replaces YOLODataset.__getitem__'s anchor assignment (dataset.py:119-167, iou_aligned
+ * utils.py:22-36) + collate_fn's per-scale stacking (utils.py:694-700) for a batch.  boxes: device [total][5] doubles
+ * x, y, w, h, class in the image's own order; image b owns rows [offsets[b], offsets[b+1]).  anchors18_host: the 9
+ * (w, h) anchors scale-major as fractions of the image.  t0/t1/t2: (batch, 3, S, S, 6) fp32, fully written.        */
+int yolo_encode_targets(const double* boxes, const int32_t* offsets, int batch, const float* anchors18_host, int S0,
+                        int S1, int S2, float ignore_iou_threshold, float* t0, float* t1, float* t2,
+                        yb_stream_t stream);
 /* K8 backward: gradient of the summed, lambda-weighted YOLOLoss terms of one scale (loss.py:54-81) w.r.t. pred.
  * sums6 = the device sums yolo_loss_fwd produced for the same pred/target; dpred gets all 5+nc entries of every
  * cell (element strides dstrides5; out_bf16 selects bf16 or fp32), scaled by grad_scale and, per term, by
