@@ -91,6 +91,9 @@ typedef struct yolo_conv_desc {
    * the desc then describes the pair-folded GEMM (ksize 1, c_in 64 = 2 x 32 taps, c_out 64, w_in = W/2),
    * x is not needed at plan time and the plan is launched with yolo_conv_fwd_stem.                      */
   int32_t stem_c;                     /* image channels (3), 0 = ordinary layer                */
+  /* 1: the plan will be launched with yolo_conv_fwd_stats (reserves 8*c_out_pad bytes of shared memory for the
+   * per-CTA channel sums)                                                                                        */
+  int32_t want_stats;
 } yolo_conv_desc;
 
 /* Size of the opaque, caller-owned plan blob (64-byte aligned storage).       */
@@ -101,6 +104,10 @@ int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yolo_conv_desc
                         const void* x, const void* w_packed, const float* scale,
                         const float* bias, const void* residual, void* y);
 int yolo_conv_fwd(const void* plan_host, uint32_t* status, yb_stream_t stream);
+/* Same launch, plus per-channel statistics of the STORED bf16 output accumulated into sums2c (device doubles,
+ * [2*c] += sum, [2*c+1] += sum of squares; caller zeroes): the BatchNorm batch statistics of the training
+ * forward (model.py:61 under model.train()) without a second pass over the tensor.  bf16, non-upsampled plans. */
+int yolo_conv_fwd_stats(const void* plan_host, uint32_t* status, double* sums2c, yb_stream_t stream);
 /* Fused stem launch: x_nchw = (B,3,H,W) fp32; also ORs YB_STATUS_NAN_INPUT (model.py:175).               */
 int yolo_conv_fwd_stem(const void* plan_host, const float* x_nchw, uint32_t* status, yb_stream_t stream);
 /* tile configuration chosen by plan_init: info8 = block_n, block_k, stages, tiles_n, tiles_m,

@@ -5,7 +5,7 @@ mode=${1:-isolate}; shift
 mkdir -p gpurun_out
 : > gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-files=${@:-"tests/test_gpu_sort_nms.py tests/test_gpu_decode_iou_map.py tests/test_gpu_conv.py tests/test_gpu_model.py"}
+files=${@:-$(ls tests/test_gpu_*.py)}
 rc=0
 for f in $files; do
   name=$(basename $f .py)

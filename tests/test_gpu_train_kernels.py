@@ -255,3 +255,34 @@ def test_sgd_matches_torch():
         lib.yolo_sgd_step(ptr(p), ptr(gd), ptr(buf), n, 0.01, 0.9, 5e-4, 1.0, int(step == 0), stream_ptr(dev))
     torch.cuda.synchronize()
     assert torch.allclose(p[:n].cpu(), ref_p.detach(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,H,cin,cout,k,stride", [(2, 16, 64, 128, 3, 1), (3, 13, 512, 256, 1, 1), (2, 20, 32, 64, 3, 2),
+                                                   (1, 9, 128, 32, 1, 1), (4, 26, 128, 256, 3, 1)])
+def test_conv_epilogue_statistics(B, H, cin, cout, k, stride):
+    """yolo_conv_fwd_stats: the per-channel sum / sum of squares accumulated by the conv epilogue equal those of
+    the bf16 tensor it stored (what yolo_bn_stats computes in a separate pass)."""
+    from yolo_for_turbines_b200._lib import lib, ptr, stream_ptr
+    from yolo_for_turbines_b200.engine import make_conv_plan
+
+    g = torch.Generator().manual_seed(cin + cout + H)
+    dev = torch.device("cuda")
+    pad = 1 if k == 3 else 0
+    Ho = (H + 2 * pad - k) // stride + 1
+    x = torch.randn(B, H, H, cin, generator=g).bfloat16().to(dev)
+    w = (torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k)) ** 0.5).to(dev)
+    wpk = torch.empty(cout * k * k * cin, dtype=torch.bfloat16, device=dev)
+    st = stream_ptr(dev)
+    lib.yolo_pack_weights(ptr(w), cout, cin, k, cout, cin, ptr(wpk), st)
+    ones, zeros = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
+    z = torch.empty(B * Ho * Ho, cout, dtype=torch.bfloat16, device=dev)
+    d = _desc(B, H, H, cin, cin, cout, k, stride)
+    d.want_stats = 1
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    plan = make_conv_plan(d, ptr(x), ptr(wpk), ptr(ones), ptr(zeros), None, ptr(z))
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+    lib.yolo_conv_fwd_stats(plan[1], ptr(status), ptr(sums), st)
+    torch.cuda.synchronize()
+    zd = z.double()
+    ref = torch.stack([zd.sum(0), (zd * zd).sum(0)], dim=1).reshape(-1)
+    assert torch.allclose(sums, ref, rtol=1e-5, atol=1e-4 * float(ref.abs().max())), float((sums - ref).abs().max())

@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "h_in", "w_in", "c_in", "in_pitch", "c_out", "c_out_pad", "out_pitch", "ksize", "stride", "pad",
         "act", "has_residual", "res_pitch", "upsample2x", "out_fp32", "check_nan", "a_mode", "block_n_hint",
-        "stages_hint", "impl_hint", "cta_pair_hint", "ksize_w", "stride_w", "pad_w_hi_plus1", "stem_c")]
+        "stages_hint", "impl_hint", "cta_pair_hint", "ksize_w", "stride_w", "pad_w_hi_plus1", "stem_c", "want_stats")]
 
 
 _P, _I, _F, _D, _SZ, _LL = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_longlong
@@ -44,6 +44,7 @@ SIGNATURES = {
     "yolo_conv_plan_bytes": (_SZ, []),
     "yolo_conv_plan_init": (_I, [_P, _SZ, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "yolo_conv_fwd": (_I, [_P, _P, _P]),
+    "yolo_conv_fwd_stats": (_I, [_P, _P, _P, _P]),
     "yolo_conv_fwd_stem": (_I, [_P, _P, _P, _P]),
     "yolo_conv_plan_info": (_I, [_P, C.POINTER(C.c_int32)]),
     "yolo_conv_fwd_simt": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -44,7 +44,7 @@ struct Cfg {
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) |
                                     (uint32_t((BLOCK_M * NCTA) >> 4) << 24);
   __host__ __device__ static constexpr int NUM_BARS(int stages) { return 2 * stages + 4 + EPI_WARPS * WSLOTS; }
-  static int smem_bytes(int stages) { return stages * STAGE_BYTES + EPI_BYTES + NUM_BARS(stages) * 8 + 16 + 1024; }
+  static int smem_bytes(int stages, int extra) { return stages * STAGE_BYTES + EPI_BYTES + NUM_BARS(stages) * 8 + 16 + 1024 + extra; }
 };
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
@@ -105,8 +105,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   auto tempty_bar = [&](int a) { return bar_base + (2 * stages + 2 + a) * 8; };
   auto res_bar = [&](int w, int sl) { return bar_base + (2 * stages + 4 + w * WSLOTS + sl) * 8; };
   const uint32_t tmem_slot = bar_base + C::NUM_BARS(stages) * 8;
+  const uint32_t stats_base = tmem_slot + 16;  // training forward: [2 * c_out_pad] fp32 channel sums of this CTA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.stats != nullptr) {
+    for (int i = threadIdx.x; i < 2 * p.c_out_pad; i += blockDim.x)
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(stats_base + 4u * i), "r"(0u) : "memory");
+  }
   const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x / NCTA;
@@ -408,6 +413,32 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             tma_store_2d(&p.tmY, slot_addr, nb, m0w);  // rows >= M are clipped by the tensor map
             bulk_commit_group();
           }
+          if (p.stats != nullptr) {
+            // Training forward (BatchNorm batch statistics, model.py:61 in train mode): column sums of the box just
+            // staged, taken from the bf16 values that are actually stored.  Lane l owns the channel pair (2l, 2l+1):
+            // one 4-byte word per row, 32 lanes read one 128-byte row -> conflict free.
+            constexpr int WORDS = C::BOXC / 2;
+            if (lane < WORDS) {
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+              const uint32_t chunk = uint32_t(lane) >> 2, word = uint32_t(lane) & 3u;
+              const int rows = p.M - m0w < 32 ? p.M - m0w : 32;
+#pragma unroll 4
+              for (int r = 0; r < rows; ++r) {
+                const uint32_t rs = (C::BOX_ROW_BYTES == 128) ? uint32_t(r & 7) : uint32_t((r >> 1) & 3);
+                uint32_t wv;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv)
+                             : "r"(slot_addr + uint32_t(r) * C::BOX_ROW_BYTES + ((chunk ^ rs) << 4) + (word << 2)));
+                const float lo = bf16_lo(wv), hi = bf16_hi(wv);
+                s0 += lo; s1 += hi;
+                q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+              }
+              const uint32_t dst = stats_base + 8u * uint32_t(nb + 2 * lane);   // [2c] sum, [2c+1] sum of squares
+              asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(dst), "f"(s0) : "memory");
+              asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(dst + 4), "f"(q0) : "memory");
+              asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(dst + 8), "f"(s1) : "memory");
+              asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(dst + 12), "f"(q1) : "memory");
+            }
+          }
           ++wbox;
         }
       }
@@ -419,6 +450,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   tc_fence_before();
   if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) tmem_dealloc_n<NCTA>(tmem_base, C::TMEM_COLS);
+  if (p.stats != nullptr) {  // one double atomic per channel statistic per CTA
+    for (int i = threadIdx.x; i < 2 * p.c_out_pad; i += blockDim.x) {
+      float v;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stats_base + 4u * i));
+      if (v != 0.f) atomicAdd(p.stats + i, double(v));
+    }
+  }
 }
 
 template <int BN, int KC, int NCTA, bool STEM = false>
@@ -442,12 +480,12 @@ int launch2(const ConvPlan* pl, const ConvKParams2& kp, cudaStream_t stream) {
 }
 
 template <int BN, int KC>
-int smem_for(int ncta, int stages) {
-  return ncta == 2 ? Cfg<BN, KC, 2>::smem_bytes(stages) : Cfg<BN, KC, 1>::smem_bytes(stages);
+int smem_for(int ncta, int stages, int extra) {
+  return ncta == 2 ? Cfg<BN, KC, 2>::smem_bytes(stages, extra) : Cfg<BN, KC, 1>::smem_bytes(stages, extra);
 }
 
-int smem_bytes_v2(int bn, int kc, int ncta, int stages) {
-#define YB_C2(BN, KC) if (bn == BN && kc == KC) return smem_for<BN, KC>(ncta, stages);
+int smem_bytes_v2(int bn, int kc, int ncta, int stages, int extra) {
+#define YB_C2(BN, KC) if (bn == BN && kc == KC) return smem_for<BN, KC>(ncta, stages, extra);
   YB_C2(32, 32) YB_C2(64, 32) YB_C2(128, 32) YB_C2(256, 32) YB_C2(32, 64) YB_C2(64, 64) YB_C2(128, 64) YB_C2(256, 64)
 #undef YB_C2
   return 1 << 30;
@@ -470,14 +508,15 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   const int tiles_n = d->c_out_pad / bn;
   const int taps = d->ksize * yb_kw(d);
   const int num_kb = taps * (d->c_in / kc);
+  const int extra = d->want_stats ? 8 * d->c_out_pad : 0;  // per-CTA channel sums of yolo_conv_fwd_stats
   int stages = d->stages_hint;
   if (stages <= 0) {
     stages = 8;
-    while (stages > 1 && smem_bytes_v2(bn, kc, ncta, stages) > 227 * 1024) --stages;
+    while (stages > 1 && smem_bytes_v2(bn, kc, ncta, stages, extra) > 227 * 1024) --stages;
   }
   // the smem ring spans tiles in a persistent kernel: never clamp it to this layer's k-block count
-  while (stages > 1 && smem_bytes_v2(bn, kc, ncta, stages) > 227 * 1024) --stages;  // a hint is a ceiling
-  const int smem = smem_bytes_v2(bn, kc, ncta, stages);
+  while (stages > 1 && smem_bytes_v2(bn, kc, ncta, stages, extra) > 227 * 1024) --stages;  // a hint is a ceiling
+  const int smem = smem_bytes_v2(bn, kc, ncta, stages, extra);
   YB_REQUIRE(smem <= 227 * 1024, "conv v2: %d stages do not fit shared memory (block_n %d)", stages, bn);
 
   ConvKParams2& kp = pl->kp2;
@@ -528,6 +567,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   kp.act = d->act; kp.has_residual = d->has_residual; kp.upsample2x = d->upsample2x;
   kp.out_fp32 = d->out_fp32; kp.check_nan = d->check_nan; kp.a_im2col = im2col;
   kp.stem_x = nullptr; kp.stem_h = d->h_in; kp.stem_w = d->w_in * 2;
+  kp.stats = nullptr; kp.c_out_pad = d->c_out_pad;
   pl->stem_direct = stem ? 1 : 0;
   if (stem) {
     YB_REQUIRE(bn == 64 && kc == 64 && d->stem_c == 3 && d->ksize == 1 && tiles_n == 1 && !d->has_residual && !direct,
@@ -559,10 +599,13 @@ int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status,
   return launch2<64, 64, 1, true>(pl, kp, stream);
 }
 
-int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream) {
+int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats) {
   YB_REQUIRE(!pl->stem_direct, "conv fwd: stem plans are launched with yolo_conv_fwd_stem");
+  YB_REQUIRE(!stats || (pl->d.want_stats && !(pl->d.upsample2x || pl->d.out_fp32)),
+             "conv fwd: statistics need a plan built with want_stats and the staged bf16 output path");
   ConvKParams2 kp = pl->kp2;
   kp.status = status;
+  kp.stats = stats;
 #define YB_L2(BN, KC)                                                        \
   if (pl->block_n == BN && pl->kc == KC)                                     \
     return pl->ncta == 2 ? launch2<BN, KC, 2>(pl, kp, stream) : launch2<BN, KC, 1>(pl, kp, stream);

@@ -47,6 +47,8 @@ struct ConvKParams2 {
   int act, has_residual, upsample2x, out_fp32, check_nan, a_im2col;
   const float* stem_x;  // STEM mode: fp32 NCHW image (set per launch)
   int stem_h, stem_w;
+  int c_out_pad;
+  double* stats;        // training forward: per-channel [sum, sum of squares] of the stored bf16 output (set per launch)
 };
 
 struct ConvPlan {
@@ -71,5 +73,5 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
 // conv2.cu
 int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out, int im2col, PFN_encodeTiled encTiled,
                      const void* residual, void* y);
-int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream);
+int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats = nullptr);
 int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status, cudaStream_t stream);

@@ -29,6 +29,7 @@ buffers), so `state_dict()`, checkpoints and `model.eval()` inference keep worki
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -191,6 +192,7 @@ class TrainPlan:
             d.c_out, d.c_out_pad, d.out_pitch = pc.c_out, pc.c_out_pad, pc.c_out_pad
             d.ksize, d.stride, d.pad = pc.k_eff, pc.stride_eff, pc.pad_eff
             d.act, d.out_fp32, d.check_nan = 0, int(op.head), 0
+            d.want_stats = int(not op.head)
             x_ptr = C.c_void_p(sroot.buf.data_ptr() + soff * 2)
             if op.head:
                 droot, _ = op.dst.resolve()
@@ -272,16 +274,25 @@ class TrainPlan:
         self.sums.zero_()
         self.status.zero_()
         lib.yolo_input_patchify(ptr(x), self.B, x.shape[1], self.H, self.W, ptr(self.input_act.resolve()[0].buf), sp, st)
+        fused_stats = tr.fused_stats
         for op in self.ops:
-            lib.yolo_conv_fwd(op.fwd_plan[1], sp, st)
             if op.head:
+                lib.yolo_conv_fwd(op.fwd_plan[1], sp, st)
                 continue
             pc, bn, blk = op.pc, op.bn, op.block.batch_norm
             C_ = pc.c_out
-            lib.yolo_bn_stats_finalize(ptr(op.z), op.P, C_, pc.c_out_pad, ptr(bn["sums"]), _p(self.counters, 8 * op.index),
-                                       ptr(blk.weight), ptr(blk.bias), float(blk.eps),
-                                       float(blk.momentum if blk.momentum is not None else 0.1), ptr(blk.running_mean),
-                                       ptr(blk.running_var), ptr(bn["mean"]), ptr(bn["rstd"]), ptr(bn["scale"]), ptr(bn["bias"]), st)
+            mom = float(blk.momentum if blk.momentum is not None else 0.1)
+            if fused_stats:   # batch statistics accumulated by the conv epilogue itself
+                lib.yolo_conv_fwd_stats(op.fwd_plan[1], sp, ptr(bn["sums"]), st)
+                lib.yolo_bn_finalize(ptr(bn["sums"]), op.P, C_, ptr(blk.weight), ptr(blk.bias), float(blk.eps), mom,
+                                     ptr(blk.running_mean), ptr(blk.running_var), ptr(bn["mean"]), ptr(bn["rstd"]),
+                                     ptr(bn["scale"]), ptr(bn["bias"]), st)
+            else:
+                lib.yolo_conv_fwd(op.fwd_plan[1], sp, st)
+                lib.yolo_bn_stats_finalize(ptr(op.z), op.P, C_, pc.c_out_pad, ptr(bn["sums"]), _p(self.counters, 8 * op.index),
+                                           ptr(blk.weight), ptr(blk.bias), float(blk.eps), mom, ptr(blk.running_mean),
+                                           ptr(blk.running_var), ptr(bn["mean"]), ptr(bn["rstd"]), ptr(bn["scale"]),
+                                           ptr(bn["bias"]), st)
             droot, doff = op.dst.resolve()
             res_ptr, res_pitch = None, 0
             if op.res is not None:
@@ -387,6 +398,8 @@ class Trainer:
         self.anchors = [[tuple(map(float, a)) for a in scale] for scale in anchors]   # fractions of the image, config.py:47-57
         self.steps_done = 0
         self.max_plans = max_plans
+        # BatchNorm statistics from the conv epilogue (default) or from a separate pass over z (YOLO_B200_BN_STATS_PASS=1)
+        self.fused_stats = os.environ.get("YOLO_B200_BN_STATS_PASS") != "1"
         self.pg = process_group
         self.world = 1
         if data_parallel and (process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())):
