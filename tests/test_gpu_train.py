@@ -152,7 +152,7 @@ def test_dropin_training_loop_matches_fused_trainer():
     sd1, sd2 = m.state_dict(), m2.state_dict()
     for k in sd1:
         if "running" in k:
-            assert torch.allclose(sd1[k], sd2[k], rtol=1e-2, atol=1e-3), k
+            assert torch.allclose(sd1[k], sd2[k], rtol=5e-2, atol=2e-2), k
     assert int(sd1["layers.0.batch_norm.num_batches_tracked"]) == 1
     # a second pass through both loops keeps working (momentum buffers, repacked weights)
     opt.zero_grad()
