@@ -157,8 +157,10 @@ def run_train_workload(args, dev, dist, rank, world, local):
     """BASELINE configs[3]: the turbine-defect model (2 classes, TURBINE_ANCHORS), one training step per step:
     train-mode forward + YOLOLoss x3 + backward + gradient all-reduce (NCCL, bucketed, overlapped) + SGD.
     Batch 32 per GPU (config.BATCH_SIZE) unless --batch is given; weak scaling."""
-    from oracle import yolo_oracle as orc  # synthetic targets only (test infrastructure, not on the timed path)
+    import numpy as np
+
     from yolo_for_turbines_b200 import config as cfg
+    from yolo_for_turbines_b200.dataset import encode_targets
     from yolo_for_turbines_b200.model import YOLOv3
     from yolo_for_turbines_b200.train import Trainer
 
@@ -169,9 +171,21 @@ def run_train_workload(args, dev, dist, rank, world, local):
     tr = Trainer(model, cfg.TURBINE_ANCHORS, lr=1e-4, momentum=0.9, weight_decay=5e-4)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     xs = [torch.rand(B, 3, S, S, generator=g, device=dev) for _ in range(3)]
-    tgs = [[t.to(dev) for t in orc.synth_targets(B, S, 2, 10 * rank + i)] for i in range(3)]
+
+    def synth_targets(seed):
+        """8 random YOLO boxes per image (SURVEY 8d config 4 asks for 4 object cells per image and scale; the device
+        target encoder, dataset.py:119-167, assigns one anchor per scale to every box)."""
+        rng = np.random.default_rng(seed)
+        boxes = []
+        for _ in range(B):
+            wh = rng.uniform(0.02, 0.6, (8, 2))
+            xy = rng.uniform(wh / 2, 1 - wh / 2)
+            boxes.append(np.concatenate([np.minimum(xy, 0.999999), wh, rng.integers(0, 2, (8, 1)).astype(np.float64)], axis=1))
+        return encode_targets(boxes, cfg.TURBINE_ANCHORS, image_size=S, device=dev)
+
+    tgs = [synth_targets(10 * rank + i) for i in range(3)]
     hx = [torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(77 + rank + i)).pin_memory() for i in range(2)]
-    htg = [[t.pin_memory() for t in orc.synth_targets(B, S, 2, 500 + 10 * rank + i)] for i in range(2)]
+    htg = [[t.cpu().pin_memory() for t in synth_targets(500 + 10 * rank + i)] for i in range(2)]
 
     def barrier():
         torch.cuda.synchronize(dev)
