@@ -49,7 +49,7 @@ struct WgradKParams {
 
 struct WgradPlan {
   WgradKParams kp;
-  int nt, smem_bytes, grid;
+  int nt, smem_bytes, grid, pair;
   uint32_t magic;
 };
 
@@ -211,6 +211,166 @@ __global__ void __launch_bounds__(WG_THREADS, 2) k_wgrad(const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// cta_group::2 variant for the layers with Cout >= 256 and Cin >= 128: a CTA pair owns a 256 (Cout) x n (<= 256
+// columns = Cin x taps) tile.  Each CTA loads the dz boxes of ITS 128 output channels and HALF of the x columns;
+// tcgen05.mma.cta_group::2 (issued by the leader) reads the other half from the peer's shared memory, so the
+// per-SM operand traffic per MMA drops from 12 KB to 8 KB -- the single-CTA kernel's bound.  Barrier protocol as in
+// conv2.cu: both producers complete_tx on the LEADER's full barrier, tcgen05.commit multicasts to both CTAs.
+template <int NT>
+__global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_pair(const __grid_constant__ WgradKParams p) {
+  constexpr uint32_t ROWB = 128;                       // 64-channel boxes only
+  constexpr uint32_t GROUP_BYTES = KP * ROWB;          // one [KP pixels][64 channels] box = 8 KB
+  constexpr uint32_t B_HALF_MAX = 2 * GROUP_BYTES;     // 128 columns per CTA
+  constexpr uint32_t STAGE_BYTES = WG_A_BYTES + B_HALF_MAX;
+  constexpr uint32_t TMEM_COLS = 256;
+  constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(256 >> 4) << 24);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stages = p.stages;
+  const uint32_t bar_base = smem_base + stages * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (stages + s) * 8; };
+  const uint32_t tmem_full_bar = bar_base + 2 * stages * 8;
+  const uint32_t tmem_slot = bar_base + (2 * stages + 1) * 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  int bid = blockIdx.x >> 1;
+  const int nt = bid % p.tiles_n; bid /= p.tiles_n;
+  const int mt = bid % p.tiles_m; bid /= p.tiles_m;
+  const int split = bid;
+  const int tg = nt / p.n_per_tap, ci0 = (nt - tg * p.n_per_tap) * NT;
+  const int tap0 = tg * p.tp;
+  const int ntaps = p.taps - tap0 < p.tp ? p.taps - tap0 : p.tp;
+  const int n_cols = ntaps * NT;                       // 128 or 256 accumulator columns
+  const int groups_half = n_cols / 128;                // 64-channel x boxes THIS CTA loads per stage
+  const int co0 = (mt * 2 + int(rank)) * 128;
+  const int chunk0 = split * p.chunks_per_split;
+  int nchunks = p.num_chunks - chunk0;
+  if (nchunks > p.chunks_per_split) nchunks = p.chunks_per_split;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmD);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_n<2>(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t tx_bytes = 2u * (WG_A_BYTES + uint32_t(groups_half) * GROUP_BYTES);
+    for (int c = 0; c < nchunks; ++c) {
+      const int p0 = (chunk0 + c) * KP;
+      int cw = 0, ch = 0, img = 0;
+      if (p.x_im2col) {
+        const int hw = p.h_out * p.w_out;
+        img = p0 / hw;
+        const int rem = p0 - img * hw;
+        const int po = rem / p.w_out, qo = rem - po * p.w_out;
+        cw = qo * p.stride_w - p.pad;
+        ch = po * p.stride - p.pad;
+      }
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(full_bar(s), tx_bytes);
+        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + WG_A_BYTES;
+        tma_load_2d_2sm(&p.tmD, full_bar(s), sa, co0, p0);
+        tma_load_2d_2sm(&p.tmD, full_bar(s), sa + GROUP_BYTES, co0 + 64, p0);
+        for (int g = 0; g < groups_half; ++g) {
+          const int col = (int(rank) * groups_half + g) * 64;          // column of the pair's tile
+          const int tap = tap0 + col / NT, ci = ci0 + col % NT;
+          const int tr = tap / p.ksize_w, tq = tap - tr * p.ksize_w;
+          if (p.x_im2col)
+            tma_load_im2col_4d_2sm(&p.tmX, full_bar(s), sb + g * GROUP_BYTES, ci, cw, ch, img, (uint16_t)tq, (uint16_t)tr);
+          else
+            tma_load_2d_2sm(&p.tmX, full_bar(s), sb + g * GROUP_BYTES, ci, p0);
+        }
+      }
+      __syncwarp();
+      if (++s == stages) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===== MMA issuer (leader CTA) =====
+      int s = 0;
+      uint32_t ph = 0;
+      const uint64_t adesc0 = make_mnmajor_desc(smem_base, ROWB, GROUP_BYTES);
+      const uint64_t bdesc0 = make_mnmajor_desc(smem_base + WG_A_BYTES, ROWB, GROUP_BYTES);
+      const uint64_t kstep = uint64_t((16u * ROWB) >> 4);
+      const uint32_t idesc = IDESC_BASE | (uint32_t(n_cols >> 3) << 17);
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t soff = uint64_t((uint32_t(s) * STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < KP / 16; ++k)
+            umma_bf16_n<2>(tmem_base, adesc0 + soff + kstep * k, bdesc0 + soff + kstep * k, idesc, (c | k) != 0 ? 1u : 0u);
+          umma_commit_n<2>(empty_bar(s));
+          if (c == nchunks - 1) umma_commit_n<2>(tmem_full_bar);
+        }
+        __syncwarp();
+        if (++s == stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): this CTA's 128 output channels x all n_cols columns =====
+    const int quad = warp & 3;
+    const int co = co0 + quad * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int n = 0; n < n_cols; n += 32) {
+      const int tap = tap0 + n / NT, ci = ci0 + n % NT;
+      float* row = p.dw + (size_t(co) * p.taps + tap) * p.c_in + ci;
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(n), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        red_add_v4(row + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                   __uint_as_float(v[4 * j + 3]));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_n<2>(tmem_base, TMEM_COLS);
+}
+
+template <int NT>
+int launch_wgrad_pair(const WgradPlan* pl, cudaStream_t stream) {
+  auto kern = k_wgrad_pair<NT>;
+  YB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)pl->grid);
+  cfg.blockDim = dim3(WG_THREADS);
+  cfg.dynamicSmemBytes = (size_t)pl->smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pl->kp));
+  return YB_OK;
+}
+
 void* wg_driver_fn(const char* name) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
@@ -309,6 +469,14 @@ extern "C" int yolo_wgrad_plan_init(void* plan_host, size_t plan_bytes, const yo
   kp.num_chunks = (int)((P + KP - 1) / KP);
   kp.tiles_m = (d->c_out_pad + 127) / 128;
   kp.n_per_tap = d->c_in / nt;
+  // CTA pairs (k_wgrad_pair) for Cout multiples of 256 with 64-channel boxes on both operands
+  // Measured (profiles/r1_wgrad_micro.txt): on the 3x3 layers two co-resident single CTAs per SM (831 TFLOP/s) beat
+  // one pair per two SMs (674), on the 1x1 layers the pair wins (21 vs 27 us), so pairs are the default for 1x1 only;
+  // YOLO_B200_WGRAD_PAIR=1 forces them wherever eligible, =0 disables them.
+  const bool eligible = d->c_out_pad % 256 == 0 && nt >= 128 && xc == 64 && dc == 64;
+  bool pair = eligible && d->ksize == 1;
+  if (const char* e = getenv("YOLO_B200_WGRAD_PAIR")) pair = eligible && atoi(e) != 0;
+  pl->pair = pair ? 1 : 0;
   int tp = 512 / nt;                       // accumulators that fit TMEM
   if (const char* e = getenv("YOLO_B200_WGRAD_TP")) {      // tuning aid
     const int v = atoi(e);
@@ -317,24 +485,26 @@ extern "C" int yolo_wgrad_plan_init(void* plan_host, size_t plan_bytes, const yo
   if (tp > kp.taps) tp = kp.taps;
   if (kp.taps == 9 && tp >= 3 && tp < 9) tp = 3;   // 3 balanced groups instead of e.g. 4 + 4 + 1
   if (nt == 256) tp = 1;                   // 48 KB per tap and stage: keep the ring deep instead
+  if (pair) tp = 256 / nt;                 // one 256-column accumulator per pair: 1 tap (Cin >= 256) or 2 taps (Cin = 128)
   kp.tp = tp;
   kp.tmem_cols = 32;
   while (kp.tmem_cols < tp * nt) kp.tmem_cols *= 2;
   kp.tiles_n = ((kp.taps + tp - 1) / tp) * kp.n_per_tap;
+  if (pair) kp.tiles_m = d->c_out_pad / 256;
   const int tiles = kp.tiles_m * kp.tiles_n;
   int dev = 0, sms = 148;
   YB_CHECK_CUDA(cudaGetDevice(&dev));
   YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // Two CTAs share an SM (the epilogue of one overlaps the main loop of the other) when both fit: <= 256 TMEM
   // columns and <= ~110 KB of shared memory each; otherwise one wave of one CTA per SM.
-  const bool pair_up = kp.tmem_cols <= 256;
-  int splits = splits_hint > 0 ? splits_hint : ((pair_up ? 2 : 1) * sms) / tiles;
+  const bool pair_up = kp.tmem_cols <= 256 && !pair;
+  int splits = splits_hint > 0 ? splits_hint : (pair ? sms / 2 : (pair_up ? 2 : 1) * sms) / tiles;
   const int max_splits = (kp.num_chunks + 15) / 16;  // >= ~16 chunks of 64 pixels per CTA: bounds the red.global traffic
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   kp.chunks_per_split = (kp.num_chunks + splits - 1) / splits;
   kp.splits = (kp.num_chunks + kp.chunks_per_split - 1) / kp.chunks_per_split;  // no empty CTA
-  const uint32_t stage_bytes = WG_A_BYTES + uint32_t(tp) * KP * nt * 2;
+  const uint32_t stage_bytes = pair ? WG_A_BYTES + 2u * KP * 128u : WG_A_BYTES + uint32_t(tp) * KP * nt * 2;
   int stages = (int)(((pair_up ? 108u : 220u) * 1024u) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
@@ -345,7 +515,7 @@ extern "C" int yolo_wgrad_plan_init(void* plan_host, size_t plan_bytes, const yo
   kp.stages = stages;
   pl->nt = nt;
   pl->smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
-  pl->grid = kp.splits * tiles;
+  pl->grid = kp.splits * tiles * (pair ? 2 : 1);
   pl->magic = WG_MAGIC;
   return YB_OK;
 }
@@ -354,6 +524,7 @@ extern "C" int yolo_wgrad(const void* plan_host, yb_stream_t stream_) {
   const WgradPlan* pl = static_cast<const WgradPlan*>(plan_host);
   YB_REQUIRE(pl && pl->magic == WG_MAGIC, "wgrad: bad plan");
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (pl->pair) return pl->nt == 256 ? launch_wgrad_pair<256>(pl, stream) : launch_wgrad_pair<128>(pl, stream);
   switch (pl->nt) {
     case 32: return launch_wgrad<32>(pl, stream);
     case 64: return launch_wgrad<64>(pl, stream);
@@ -367,7 +538,7 @@ extern "C" int yolo_wgrad(const void* plan_host, yb_stream_t stream_) {
 extern "C" int yolo_wgrad_plan_info(const void* plan_host, int32_t* info6) {
   const WgradPlan* pl = static_cast<const WgradPlan*>(plan_host);
   YB_REQUIRE(pl && pl->magic == WG_MAGIC && info6, "wgrad plan info: bad plan");
-  info6[0] = pl->nt + 1000 * pl->kp.tp; info6[1] = pl->kp.stages; info6[2] = pl->kp.splits; info6[3] = pl->kp.tiles_m;
+  info6[0] = pl->nt + 1000 * pl->kp.tp + 100000 * pl->pair; info6[1] = pl->kp.stages; info6[2] = pl->kp.splits; info6[3] = pl->kp.tiles_m;
   info6[4] = pl->kp.tiles_n; info6[5] = pl->grid;
   return YB_OK;
 }
