@@ -160,3 +160,29 @@ def test_dropin_training_loop_matches_fused_trainer():
     sum(sum(loss_fn(o, t.clone(), a.cuda())) for o, t, a in zip(out, ts, scaled_anchors)).backward()
     opt.step()
     assert torch.isfinite(tr.step(xs, ts)).all()
+
+
+def test_frozen_parameters_stay_put():
+    """`freeze=True` in the reference marks loaded tensors requires_grad=False (model.py:306-309, 330-334) and
+    torch.optim.SGD then skips them: frozen tensors must not move, trainable ones must."""
+    from oracle import yolo_oracle as orc
+    from yolo_for_turbines_b200.train import Trainer
+
+    m, sd, x, tg = _setup(2, "leaky_relu", 64, 2, 31)
+    m = m.cuda().train()
+    named = list(m.named_parameters())
+    frozen = [k for k, _ in named[:120]]
+    for k, p in named[:120]:
+        p.requires_grad = False
+    before = {k: p.detach().clone() for k, p in named}
+    tr = Trainer(m, orc.TURBINE_ANCHORS, lr=1e-2, momentum=0.9, weight_decay=5e-4)
+    tr.step(x.cuda(), [t.cuda() for t in tg])
+    torch.cuda.synchronize()
+    moved = 0
+    for k, p in m.named_parameters():
+        if k in frozen:
+            assert torch.equal(p.detach(), before[k]), k
+            assert p.grad is None
+        else:
+            moved += int(not torch.equal(p.detach(), before[k]))
+    assert moved == len(named) - len(frozen)

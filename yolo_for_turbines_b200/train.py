@@ -364,6 +364,9 @@ class _TrainForwardFn(torch.autograd.Function):
             plan.forward(x)
         ctx.trainer, ctx.plan = trainer, plan
         ctx.n_params = len(params)
+        eng = trainer.model.__dict__.get("_yb_engine")
+        if eng is not None:
+            eng._sig = None   # running statistics moved: the eval-mode engine must re-fold BatchNorm
         return tuple(v.clone(memory_format=torch.preserve_format) for v in plan.head_views())
 
     @staticmethod
