@@ -16,7 +16,7 @@ S = int(sys.argv[2]) if len(sys.argv) > 2 else 416
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 m = YOLOv3(num_classes=80).eval().to(dev)
-det = Detector(m, cfg.ANCHORS, 0.45, 0.5, "center")
+det = Detector(m, cfg.ANCHORS, 0.45, float(sys.argv[3]) if len(sys.argv) > 3 else 0.5, "center")
 xs = [torch.rand(B, 3, S, S, device=dev) for _ in range(3)]
 for i in range(4):
     res, plan = det(xs[i % 3])

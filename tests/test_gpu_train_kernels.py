@@ -286,3 +286,22 @@ def test_conv_epilogue_statistics(B, H, cin, cout, k, stride):
     zd = z.double()
     ref = torch.stack([zd.sum(0), (zd * zd).sum(0)], dim=1).reshape(-1)
     assert torch.allclose(sums, ref, rtol=1e-5, atol=1e-4 * float(ref.abs().max())), float((sums - ref).abs().max())
+
+
+@pytest.mark.parametrize("cout,cin,k", [(64, 32, 3), (255, 1024, 1), (21, 256, 1), (1024, 512, 3), (128, 384, 1)])
+def test_fused_weight_pack_equals_the_two_reference_packs(cout, cin, k):
+    """yolo_pack_weights_train (one pass, tiled) writes exactly what yolo_pack_weights + yolo_pack_weights_dgrad write."""
+    from yolo_for_turbines_b200._lib import lib, ptr, stream_ptr
+
+    dev = torch.device("cuda")
+    st = stream_ptr(dev)
+    w = torch.randn(cout, cin, k, k, generator=torch.Generator().manual_seed(cout + cin)).to(dev)
+    cpad = (cout + 31) // 32 * 32
+    f_ref = torch.empty(cpad * k * k * cin, dtype=torch.bfloat16, device=dev)
+    b_ref = torch.empty(cin * k * k * cpad, dtype=torch.bfloat16, device=dev)
+    lib.yolo_pack_weights(ptr(w), cout, cin, k, cpad, cin, ptr(f_ref), st)
+    lib.yolo_pack_weights_dgrad(ptr(w), cout, cin, k, cin, cpad, ptr(b_ref), st)
+    f, b = torch.zeros_like(f_ref), torch.zeros_like(b_ref)
+    lib.yolo_pack_weights_train(ptr(w), cout, cin, k, cin, cpad, ptr(f), ptr(b), st)
+    torch.cuda.synchronize()
+    assert torch.equal(f, f_ref) and torch.equal(b, b_ref)

@@ -110,6 +110,7 @@ class _Lib:
             raise AttributeError(name)
         fn = self.raw(name)
         if SIGNATURES[name][0] is not _I or name == "yolo_version":
+            self.__dict__[name] = fn      # cached: later lookups never reach __getattr__
             return fn
 
         def checked(*args):
@@ -120,6 +121,7 @@ class _Lib:
             return rc
 
         checked.__name__ = name
+        self.__dict__[name] = checked     # cached: later lookups never reach __getattr__
         return checked
 
 

@@ -405,17 +405,51 @@ __global__ void __launch_bounds__(TR_THREADS, 4) k_bn_act_bwd_apply(const BnBwdP
 // forward + data-gradient operand packs of one layer in one pass over the fp32 weights:
 //   fwd[co][tap][ci] = w[co][ci][tap]            ([c_out_pad][taps][c_in_pad], padding pre-zeroed by the caller)
 //   bwd[ci][taps-1-tap][co] = w[co][ci][tap]     ([c_in_pad][taps][c_out_pad])
-__global__ void k_pack_weights_both(const float* __restrict__ w, int c_out, int c_in, int taps, int c_in_pad, int c_out_pad,
-                                    __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ bwd) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)c_out * c_in * taps;
-  if (idx >= total) return;
-  const int tap = int(idx % taps);
-  const int ci = int((idx / taps) % c_in);
-  const int co = int(idx / ((long long)taps * c_in));
-  const __nv_bfloat16 v = __float2bfloat16_rn(w[idx]);
-  fwd[(size_t(co) * taps + tap) * c_in_pad + ci] = v;
-  bwd[(size_t(ci) * taps + (taps - 1 - tap)) * c_out_pad + co] = v;
+// One block per 32 (co) x 32 (ci) tile staged through shared memory: OIHW rows are read as contiguous runs of
+// 32*taps floats, both packs are written as 64-byte runs (ci-contiguous / co-contiguous).
+constexpr int PK_T = 32;
+__global__ void __launch_bounds__(256) k_pack_weights_both(const float* __restrict__ w, int c_out, int c_in, int taps,
+                                                          int c_in_pad, int c_out_pad, __nv_bfloat16* __restrict__ fwd,
+                                                          __nv_bfloat16* __restrict__ bwd) {
+  extern __shared__ float s_tile[];  // [PK_T][PK_T * taps + 1]
+  const int L = PK_T * taps, pitch = L + 1;
+  const int ci0 = blockIdx.x * PK_T, co0 = blockIdx.y * PK_T;
+  const int nci = min(PK_T, c_in - ci0);
+  for (int i = threadIdx.x; i < PK_T * L; i += 256) {
+    const int r = i / L, c = i - r * L;
+    float v = 0.f;
+    if (co0 + r < c_out && c < nci * taps) v = w[(size_t(co0 + r) * c_in + ci0) * taps + c];
+    s_tile[r * pitch + c] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PK_T * L; i += 256) {   // forward pack: ci fastest
+    const int cil = i % PK_T, t = (i / PK_T) % taps, r = i / (PK_T * taps);
+    if (co0 + r < c_out && cil < nci)
+      fwd[(size_t(co0 + r) * taps + t) * c_in_pad + ci0 + cil] = __float2bfloat16_rn(s_tile[r * pitch + cil * taps + t]);
+  }
+  for (int i = threadIdx.x; i < PK_T * L; i += 256) {   // data-gradient pack: co fastest, taps flipped
+    const int r = i % PK_T, t = (i / PK_T) % taps, cil = i / (PK_T * taps);
+    if (co0 + r < c_out && cil < nci)
+      bwd[(size_t(ci0 + cil) * taps + (taps - 1 - t)) * c_out_pad + co0 + r] = __float2bfloat16_rn(s_tile[r * pitch + cil * taps + t]);
+  }
+}
+
+// packed fp32 [c_out_pad][taps][c_in_pad] -> OIHW, one block per output channel through shared memory so that both
+// the packed rows and the OIHW row are accessed contiguously
+__global__ void __launch_bounds__(256) k_unpack_wgrad_rows(const float* __restrict__ packed, int c_in, int taps, int c_in_pad,
+                                                          float* __restrict__ grad) {
+  extern __shared__ float s_tile[];  // [taps][c_in]
+  const int co = blockIdx.x;
+  for (int i = threadIdx.x; i < taps * c_in; i += 256) {
+    const int t = i / c_in, ci = i - t * c_in;
+    s_tile[i] = packed[(size_t(co) * taps + t) * c_in_pad + ci];
+  }
+  __syncthreads();
+  float* g = grad + size_t(co) * c_in * taps;
+  for (int i = threadIdx.x; i < taps * c_in; i += 256) {
+    const int ci = i / taps, t = i - ci * taps;
+    g[i] = s_tile[t * c_in + ci];
+  }
 }
 
 // packed fp32 [c_out_pad][taps][c_in_pad] -> OIHW (c_out, c_in, k, k); stem: packed [c_out_pad][32] with
@@ -584,8 +618,13 @@ extern "C" int yolo_unpack_wgrad(const float* packed, int c_out, int c_in, int k
   YB_REQUIRE(packed && grad_oihw && c_out >= 1 && c_in >= 1 && (ksize == 1 || ksize == 3) && c_in_pad >= (stem ? 9 * c_in : c_in),
              "yolo_unpack_wgrad: bad argument");
   const long long total = (long long)c_out * c_in * ksize * ksize;
-  k_unpack_wgrad<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(packed, c_out, c_in, ksize * ksize, c_in_pad, stem,
-                                                                                  grad_oihw);
+  const size_t row_bytes = size_t(ksize) * ksize * c_in * sizeof(float);
+  if (!stem && row_bytes <= 48 * 1024) {
+    k_unpack_wgrad_rows<<<c_out, 256, row_bytes, (cudaStream_t)stream>>>(packed, c_in, ksize * ksize, c_in_pad, grad_oihw);
+  } else {
+    k_unpack_wgrad<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(packed, c_out, c_in, ksize * ksize, c_in_pad,
+                                                                                    stem, grad_oihw);
+  }
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -605,9 +644,10 @@ extern "C" int yolo_pack_weights_train(const float* w_oihw, int c_out, int c_in,
                                        void* w_fwd, void* w_dgrad, yb_stream_t stream) {
   YB_REQUIRE(w_oihw && w_fwd && w_dgrad && c_out >= 1 && c_in >= 1 && (ksize == 1 || ksize == 3) && c_in_pad >= c_in &&
                  c_out_pad >= c_out, "yolo_pack_weights_train: bad argument");
-  const long long total = (long long)c_out * c_in * ksize * ksize;
-  k_pack_weights_both<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      w_oihw, c_out, c_in, ksize * ksize, c_in_pad, c_out_pad, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad));
+  const int taps = ksize * ksize;
+  dim3 grid((c_in + PK_T - 1) / PK_T, (c_out + PK_T - 1) / PK_T);
+  k_pack_weights_both<<<grid, 256, PK_T * (PK_T * taps + 1) * sizeof(float), (cudaStream_t)stream>>>(
+      w_oihw, c_out, c_in, taps, c_in_pad, c_out_pad, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
