@@ -467,6 +467,7 @@ class Trainer:
             self.losses = torch.zeros(4, dtype=torch.float32, device=dev)
         self.plans: Dict[tuple, TrainPlan] = {}
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.debug_local_grads = None   # set to a tensor like flat_g to capture the pre-all-reduce gradients (tests)
         self.bucket_elems = int(bucket_mb * 1e6 / 4)
         self.repack(full=True)
 
@@ -598,6 +599,8 @@ class Trainer:
                         ev.record(main)
                         self.comm_stream.wait_event(ev)
                         with torch.cuda.stream(self.comm_stream):
+                            if self.debug_local_grads is not None:   # tests: this rank's gradient before the exchange
+                                self.debug_local_grads[lo:hi].copy_(self.flat_g[lo:hi])
                             torch.distributed.all_reduce(self.flat_g[lo:hi], group=self.pg)
                 plan.backward(on_op_done)
                 main.wait_stream(self.comm_stream)
