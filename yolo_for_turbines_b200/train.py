@@ -542,6 +542,8 @@ class Trainer:
             if tuple(tgt.shape) != (plan.B, 3, op.ho, op.wo, 6) or tgt.dtype != torch.float32 or tgt.device != dev:
                 raise YoloB200Error(f"target {s}: expected fp32 {(plan.B, 3, op.ho, op.wo, 6)} on {dev}, got {tuple(tgt.shape)}")
             S = op.ho
+            if op.ho != op.wo:
+                raise YoloB200Error("YOLOLoss works on square grids (loss.py:29-81 with the reference's (B,3,S,S,6) targets)")
             anc = (C.c_float * 6)(*[v * S for a in self.anchors[s] for v in a])   # train.py:195-197 scaled anchors
             ps, ts = (C.c_int64 * 5)(*pred.stride()), (C.c_int64 * 5)(*tgt.stride())
             sums = plan.loss_sums[6 * s:6 * s + 6]
