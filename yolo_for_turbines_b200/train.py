@@ -150,6 +150,7 @@ class TrainPlan:
         self.bnf = torch.empty(6 * n_bn, dtype=torch.float32, device=dev)           # mean rstd scale bias m1 m2
         self.loss_sums = torch.zeros(18, dtype=torch.float64, device=dev)
         self.counters = torch.zeros(2 * len(self.ops), dtype=torch.int32, device=dev)   # last-block tickets (self-resetting)
+        self.ev_dz = [torch.cuda.Event() for _ in self.ops]
         stuffed_elems = max([B * op.src.H * op.src.W * op.pc.c_out_pad for op in self.ops[1:] if op.pc.stride_eff == 2] + [0])
         self.stuffed = alloc(stuffed_elems, torch.bfloat16) if stuffed_elems else None
 
@@ -303,10 +304,16 @@ class TrainPlan:
         torch._foreach_add_(tr.bn_counters, 1)   # nn.BatchNorm2d.num_batches_tracked (state_dict parity)
 
     def backward(self, on_op_done=None):
-        """Runs after the head convs' dz have been written (Trainer.step does that with yolo_loss_bwd)."""
+        """Runs after the head convs' dz have been written (Trainer.step does that with yolo_loss_bwd).
+
+        The weight gradients (tensor-core / L2-bound, almost no DRAM traffic) go to a side stream: nothing downstream
+        in the backward pass depends on them, so they overlap with the DRAM-bound BatchNorm / activation passes and
+        with the data-gradient convs of the layers below instead of serialising behind them."""
         tr, dev = self.trainer, self.trainer.device
         st = stream_ptr(dev)
         sp = ptr(self.status)
+        main = torch.cuda.current_stream(dev)
+        side = tr.wgrad_stream
         for i in range(len(self.ops) - 1, -1, -1):
             op = self.ops[i]
             pc, bn = op.pc, op.bn
@@ -322,13 +329,24 @@ class TrainPlan:
                                     ptr(op.dz), pc.c_out_pad, ptr(op.stuffed) if op.stuffed is not None else None,
                                     pc.c_out_pad, st)
             if op.g_w is not None:
-                lib.yolo_wgrad(op.wgrad_plan[1], st)
-                lib.yolo_unpack_wgrad(_p(tr.dw_packed, 4 * tr.dw_off[id(op.block)]), pc.c_out, pc.c_in, pc.ksize,
-                                      pc.c_in_eff, int(pc.stem), ptr(op.g_w), st)
+                if side is not None:
+                    self.ev_dz[i].record(main)          # dz of this op (and everything before it on main) is ready
+                    side.wait_event(self.ev_dz[i])
+                    with torch.cuda.stream(side):
+                        sst = stream_ptr(dev)
+                        lib.yolo_wgrad(op.wgrad_plan[1], sst)
+                        lib.yolo_unpack_wgrad(_p(tr.dw_packed, 4 * tr.dw_off[id(op.block)]), pc.c_out, pc.c_in, pc.ksize,
+                                              pc.c_in_eff, int(pc.stem), ptr(op.g_w), sst)
+                else:
+                    lib.yolo_wgrad(op.wgrad_plan[1], st)
+                    lib.yolo_unpack_wgrad(_p(tr.dw_packed, 4 * tr.dw_off[id(op.block)]), pc.c_out, pc.c_in, pc.ksize,
+                                          pc.c_in_eff, int(pc.stem), ptr(op.g_w), st)
             if i > 0:
                 lib.yolo_conv_fwd(op.dgrad_plan[1], sp, st)
             if on_op_done is not None:
                 on_op_done(i)
+        if side is not None:
+            main.wait_stream(side)
 
 
 def make_buckets(firsts, n_trainable: int, bucket_elems: int):
@@ -467,6 +485,8 @@ class Trainer:
             self.losses = torch.zeros(4, dtype=torch.float32, device=dev)
         self.plans: Dict[tuple, TrainPlan] = {}
         self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        # weight gradients on their own stream (YOLO_B200_WGRAD_STREAM=0: same stream, for A/B timing)
+        self.wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("YOLO_B200_WGRAD_STREAM") != "0" else None
         self.debug_local_grads = None   # set to a tensor like flat_g to capture the pre-all-reduce gradients (tests)
         self.bucket_elems = int(bucket_mb * 1e6 / 4)
         self.repack(full=True)
@@ -600,6 +620,10 @@ class Trainer:
                         ev = torch.cuda.Event()
                         ev.record(main)
                         self.comm_stream.wait_event(ev)
+                        if self.wgrad_stream is not None:   # the bucket's weight gradients are written on the side stream
+                            ev2 = torch.cuda.Event()
+                            ev2.record(self.wgrad_stream)
+                            self.comm_stream.wait_event(ev2)
                         with torch.cuda.stream(self.comm_stream):
                             if self.debug_local_grads is not None:   # tests: this rank's gradient before the exchange
                                 self.debug_local_grads[lo:hi].copy_(self.flat_g[lo:hi])
