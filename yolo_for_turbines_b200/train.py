@@ -276,7 +276,11 @@ class TrainPlan:
         self.status.zero_()
         lib.yolo_input_patchify(ptr(x), self.B, x.shape[1], self.H, self.W, ptr(self.input_act.resolve()[0].buf), sp, st)
         fused_stats = tr.fused_stats
+        pending = tr._packs_pending
+        main = torch.cuda.current_stream(dev)
         for op in self.ops:
+            if pending:
+                main.wait_event(tr.ev_pack[id(op.block)])   # this layer's operand packs (side stream) are ready
             if op.head:
                 lib.yolo_conv_fwd(op.fwd_plan[1], sp, st)
                 continue
@@ -301,6 +305,7 @@ class TrainPlan:
                 res_ptr, res_pitch = _p(rroot.buf, 2 * roff), rroot.C
             lib.yolo_bn_act_fwd(ptr(op.z), op.P, C_, pc.c_out_pad, ptr(bn["scale"]), ptr(bn["bias"]), ACT_CODES[pc.act],
                                 res_ptr, res_pitch, _p(droot.buf, 2 * doff), droot.C, int(op.upsample), op.ho, op.wo, st)
+        tr._packs_pending = False
         torch._foreach_add_(tr.bn_counters, 1)   # nn.BatchNorm2d.num_batches_tracked (state_dict parity)
 
     def backward(self, on_op_done=None):
@@ -489,10 +494,28 @@ class Trainer:
         self.wgrad_stream = torch.cuda.Stream(device=dev) if os.environ.get("YOLO_B200_WGRAD_STREAM") != "0" else None
         self.debug_local_grads = None   # set to a tensor like flat_g to capture the pre-all-reduce gradients (tests)
         self.bucket_elems = int(bucket_mb * 1e6 / 4)
+        self.ev_pack = {id(b): torch.cuda.Event() for b in self.blocks}
+        self._ev_sgd = torch.cuda.Event()
+        self._packs_pending = False
         self.repack(full=True)
 
     # ------------------------------------------------------------------------------------------------------
-    def repack(self, full: bool = False):
+    def repack_async(self):
+        """After the SGD update: repack on the side stream, one event per block; the next forward waits per layer
+        (TrainPlan.forward), so the packs of the deep layers overlap with the first convs of the next step."""
+        dev = self.device
+        if self.wgrad_stream is None:
+            self.repack()
+            self._packs_pending = False
+            return
+        main = torch.cuda.current_stream(dev)
+        self._ev_sgd.record(main)
+        self.wgrad_stream.wait_event(self._ev_sgd)
+        with torch.cuda.stream(self.wgrad_stream):
+            self.repack(events=True)
+        self._packs_pending = True
+
+    def repack(self, full: bool = False, events: bool = False):
         """bf16 operand packs of the current fp32 weights: forward [Cout][k][k][Cin] and data-gradient
         [Cin][k][k][Cout] (flipped).  full=True also writes the zero padding (once, at construction); afterwards
         one launch per layer rewrites the real entries of both packs."""
@@ -514,6 +537,8 @@ class Trainer:
                 if not b.batch_norm_act:  # head conv: scale 1, bias = conv bias
                     lib.yolo_fold_bn(None, None, None, None, ptr(b.conv.bias), 0.0, pc.c_out, pc.c_out_pad, ptr(pc.scale),
                                      ptr(pc.bias), st)
+                if events:
+                    self.ev_pack[id(b)].record(torch.cuda.current_stream(dev))
 
     def repack_if_changed(self):
         """Autograd mode: the caller's optimizer updates the parameters in place between forwards."""
@@ -635,7 +660,7 @@ class Trainer:
             lib.yolo_sgd_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), self.n_trainable,
                               float(self.lr if lr is None else lr), self.momentum, self.weight_decay, 1.0 / self.world,
                               int(self.steps_done == 0), st)
-            self.repack()
+            self.repack_async()
         self.steps_done += 1
         eng = self.model.__dict__.get("_yb_engine")
         if eng is not None:
