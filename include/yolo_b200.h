@@ -94,6 +94,16 @@ typedef struct yolo_conv_desc {
   /* 1: the plan will be launched with yolo_conv_fwd_stats (reserves 8*c_out_pad bytes of shared memory for the
    * per-CTA channel sums)                                                                                        */
   int32_t want_stats;
+  /* Data gradient of a 3x3 / stride-2 / pad-1 layer as two stride-1 sub-convolutions over dz, one per output ROW
+   * parity r (0 | 1), instead of a 4x larger zero-stuffed conv:  dx[2a+r][2b+t][ci] = sum over (da, db) of
+   * Wr[(t,ci)][da][db][co] * dz[a+da][b+db][co]  with da in {0} (r = 0) or {0, 1} (r = 1), db in {0, 1}.
+   * s2_parity = r + 1 selects the mode: the desc is then ksize = 1 | 2, ksize_w = 2, pad = 0, pad_h_hi_plus1 =
+   * ksize, pad_w_hi_plus1 = 2, c_out = c_out_pad = 2 * s2_cin (column n = t * s2_cin + ci), and every GEMM row
+   * (img, a, b) is stored to pixel (2a + r, 2b + t) of the (batch, 2*h_out, 2*w_out) tensor y with out_pitch
+   * elements per PIXEL (the residual operand is read the same way with res_pitch).
+   * Weights: yolo_pack_weights_dgrad_s2.                                                                        */
+  int32_t pad_h_hi_plus1;             /* 0: bottom pad = pad; else bottom pad = value - 1           */
+  int32_t s2_parity, s2_cin;
 } yolo_conv_desc;
 
 /* Size of the opaque, caller-owned plan blob (64-byte aligned storage).       */
@@ -284,6 +294,10 @@ int yolo_pack_weights_dgrad(const float* w_oihw, int c_out, int c_in, int ksize,
  * w_fwd [c_out_pad][k*k][c_in_pad] and w_dgrad [c_in_pad][k*k][c_out_pad] are NOT written: zero them once.       */
 int yolo_pack_weights_train(const float* w_oihw, int c_out, int c_in, int ksize, int c_in_pad, int c_out_pad,
                             void* w_fwd, void* w_dgrad, yb_stream_t stream);
+/* Weight pack of the stride-2 data-gradient sub-convolution of row parity r (see yolo_conv_desc.s2_parity):
+ * out[(t*rows_half + ci)][da][db][co] bf16, zero padded to [2*rows_half][(r+1)*2][cols_pad]; rows_half >= c_in. */
+int yolo_pack_weights_dgrad_s2(const float* w_oihw, int c_out, int c_in, int r, int rows_half, int cols_pad,
+                               void* w_packed, yb_stream_t stream);
 /* torch.optim.SGD(momentum, weight_decay) (train.py:171-172) on flat fp32 buffers: g' = g*grad_scale + wd*p;
  * buf = first_step ? g' : momentum*buf + g'; p -= lr*buf                                                      */
 int yolo_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,

@@ -305,3 +305,51 @@ def test_fused_weight_pack_equals_the_two_reference_packs(cout, cin, k):
     lib.yolo_pack_weights_train(ptr(w), cout, cin, k, cin, cpad, ptr(f), ptr(b), st)
     torch.cuda.synchronize()
     assert torch.equal(f, f_ref) and torch.equal(b, b_ref)
+
+
+@pytest.mark.parametrize("B,H,cin,cout,residual", [(2, 16, 64, 128, False), (3, 12, 32, 64, True), (2, 8, 256, 512, True),
+                                                   (1, 26, 128, 256, False)])
+def test_stride2_dgrad_parity_subconvs(B, H, cin, cout, residual):
+    """Data gradient of a 3x3/s2/p1 conv as two stride-1 sub-convolutions over dz (yolo_conv_desc.s2_parity), with the
+    accumulate-through-residual path, vs autograd."""
+    from yolo_for_turbines_b200._lib import ConvDesc, lib, ptr, stream_ptr
+    from yolo_for_turbines_b200.engine import make_conv_plan
+
+    g = torch.Generator().manual_seed(5 + cin + cout)
+    Ho = H // 2
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * (1.0 / (cout * 9)) ** 0.5).bfloat16().float()
+    dz = torch.randn(B, Ho, Ho, cout, generator=g).bfloat16()
+    acc = torch.randn(B, H, H, cin, generator=g).bfloat16() if residual else None
+    x = torch.zeros(B, cin, H, H, requires_grad=True)
+    F.conv2d(x, w, None, 2, 1).backward(dz.float().permute(0, 3, 1, 2))
+    ref = x.grad.permute(0, 2, 3, 1).contiguous()
+    if residual:
+        ref = ref + acc.float()
+
+    dev = torch.device("cuda")
+    st = stream_ptr(dev)
+    wdev, dzd = w.to(dev).contiguous(), dz.to(dev).contiguous()
+    out = torch.full((B, H, H, cin), float("nan"), dtype=torch.bfloat16, device=dev)
+    accd = acc.to(dev).contiguous() if residual else None
+    ones, zeros = torch.ones(2 * cin, device=dev), torch.zeros(2 * cin, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    keep = []
+    for r in (0, 1):
+        wpk = torch.empty(2 * cin * (r + 1) * 2 * cout, dtype=torch.bfloat16, device=dev)
+        lib.yolo_pack_weights_dgrad_s2(ptr(wdev), cout, cin, r, cin, cout, ptr(wpk), st)
+        d = ConvDesc()
+        d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch = B, Ho, Ho, cout, cout
+        d.c_out, d.c_out_pad, d.out_pitch = 2 * cin, 2 * cin, cin
+        d.ksize, d.stride, d.pad = r + 1, 1, 0
+        d.ksize_w, d.stride_w, d.pad_w_hi_plus1, d.pad_h_hi_plus1 = 2, 1, 2, r + 1
+        d.s2_parity, d.s2_cin = r + 1, cin
+        if residual:
+            d.has_residual, d.res_pitch = 1, cin
+        plan = make_conv_plan(d, ptr(dzd), ptr(wpk), ptr(ones), ptr(zeros), ptr(accd), ptr(out))
+        lib.yolo_conv_fwd(plan[1], ptr(status), st)
+        keep.append((plan, wpk))
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()          # every pixel of dx is written by exactly one of the two launches
+    tol = 2.0 ** -7 * max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) <= tol

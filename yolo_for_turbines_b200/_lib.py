@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "h_in", "w_in", "c_in", "in_pitch", "c_out", "c_out_pad", "out_pitch", "ksize", "stride", "pad",
         "act", "has_residual", "res_pitch", "upsample2x", "out_fp32", "check_nan", "a_mode", "block_n_hint",
-        "stages_hint", "impl_hint", "cta_pair_hint", "ksize_w", "stride_w", "pad_w_hi_plus1", "stem_c", "want_stats")]
+        "stages_hint", "impl_hint", "cta_pair_hint", "ksize_w", "stride_w", "pad_w_hi_plus1", "stem_c", "want_stats", "pad_h_hi_plus1", "s2_parity", "s2_cin")]
 
 
 _P, _I, _F, _D, _SZ, _LL = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_longlong
@@ -76,6 +76,7 @@ SIGNATURES = {
     "yolo_wgrad_plan_info": (_I, [_P, C.POINTER(C.c_int32)]),
     "yolo_unpack_wgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "yolo_pack_weights_dgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "yolo_pack_weights_dgrad_s2": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "yolo_sgd_step": (_I, [_P, _P, _P, _LL, _F, _F, _F, _F, _I, _P]),
     "yolo_loss_bwd": (_I, [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _P, _F,
                            C.POINTER(_F), _P, C.POINTER(C.c_int64), _I, _P]),

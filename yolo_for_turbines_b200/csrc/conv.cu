@@ -276,17 +276,26 @@ int validate_desc(const yolo_conv_desc* d, int* h_out, int* w_out) {
   YB_REQUIRE(d->in_pitch >= d->c_in && d->in_pitch % 8 == 0, "conv: bad in_pitch %d", d->in_pitch);
   YB_REQUIRE(d->c_out >= 1 && d->c_out_pad >= d->c_out && d->c_out_pad % 32 == 0,
              "conv: c_out_pad (%d) must be a multiple of 32 covering c_out (%d)", d->c_out_pad, d->c_out);
-  YB_REQUIRE(d->out_pitch >= d->c_out_pad && d->out_pitch % 8 == 0, "conv: bad out_pitch %d", d->out_pitch);
-  YB_REQUIRE((d->ksize == 1 && d->pad == 0) || (d->ksize == 3 && d->pad == 1),
-             "conv: only 1x1/pad0 and 3x3/pad1 (model.py:201)");
+  YB_REQUIRE(d->out_pitch % 8 == 0, "conv: bad out_pitch %d", d->out_pitch);
+  if (d->s2_parity) {
+    YB_REQUIRE((d->s2_parity == 1 || d->s2_parity == 2) && d->ksize == d->s2_parity && yb_kw(d) == 2 && d->pad == 0 &&
+                   d->stride == 1 && yb_sw(d) == 1 && yb_pad_h_hi(d) == d->ksize - 1 && yb_pad_hi(d) == 1 &&
+                   d->s2_cin >= 32 && d->s2_cin % 32 == 0 && d->c_out_pad == 2 * d->s2_cin && d->c_out == d->c_out_pad &&
+                   !d->upsample2x && !d->out_fp32 && d->stem_c == 0 && d->out_pitch >= d->s2_cin,
+               "conv: bad stride-2 data-gradient geometry");
+  } else {
+    YB_REQUIRE((d->ksize == 1 && d->pad == 0) || (d->ksize == 3 && d->pad == 1),
+               "conv: only 1x1/pad0 and 3x3/pad1 (model.py:201)");
+    YB_REQUIRE(d->out_pitch >= d->c_out_pad, "conv: bad out_pitch %d", d->out_pitch);
+    YB_REQUIRE(!d->has_residual || d->res_pitch >= d->c_out_pad, "conv: bad res_pitch");
+  }
   YB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
   YB_REQUIRE(yb_kw(d) >= 1 && yb_kw(d) <= 3 && (yb_sw(d) == 1 || yb_sw(d) == 2) && yb_pad_hi(d) >= 0 && yb_pad_hi(d) <= 1,
              "conv: bad rectangular geometry (ksize_w %d stride_w %d)", d->ksize_w, d->stride_w);
   YB_REQUIRE(d->act >= YB_ACT_NONE && d->act <= YB_ACT_MISH, "conv: bad activation code %d", d->act);
-  YB_REQUIRE(!d->has_residual || (d->res_pitch >= d->c_out_pad && d->res_pitch % 8 == 0),
-             "conv: bad res_pitch");
+  YB_REQUIRE(!d->has_residual || d->res_pitch % 8 == 0, "conv: bad res_pitch");
   YB_REQUIRE(!(d->has_residual && d->out_fp32), "conv: residual with fp32 output unsupported");
-  *h_out = (d->h_in + 2 * d->pad - d->ksize) / d->stride + 1;
+  *h_out = (d->h_in + d->pad + yb_pad_h_hi(d) - d->ksize) / d->stride + 1;
   *w_out = (d->w_in + d->pad + yb_pad_hi(d) - yb_kw(d)) / yb_sw(d) + 1;
   return YB_OK;
 }
@@ -338,8 +347,9 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
   const int taps = d->ksize * yb_kw(d);
   const int cchunks = d->c_in / kc;
   const int num_kb = taps * cchunks;
-  const int im2col = (d->a_mode == 2) || (d->a_mode == 0 && !(d->ksize == 1 && d->stride == 1));
-  YB_REQUIRE(im2col || (d->ksize == 1 && d->stride == 1), "conv plan: tiled A needs 1x1 stride 1");
+  const bool plain_1x1 = d->ksize == 1 && yb_kw(d) == 1 && d->stride == 1 && yb_sw(d) == 1;
+  const int im2col = (d->a_mode == 2) || (d->a_mode == 0 && !plain_1x1);
+  YB_REQUIRE(im2col || plain_1x1, "conv plan: tiled A needs 1x1 stride 1");
   const long long M = (long long)d->batch * h_out * w_out;
   YB_REQUIRE(M < (1ll << 31), "conv plan: too many output pixels");
 
@@ -366,7 +376,7 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
     cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->w_in * d->in_pitch * 2,
                              (cuuint64_t)d->h_in * d->w_in * d->in_pitch * 2};
     int lower[2] = {-d->pad, -d->pad};  // {W, H}
-    int upper[2] = {yb_pad_hi(d) - (yb_kw(d) - 1), d->pad - (d->ksize - 1)};
+    int upper[2] = {yb_pad_hi(d) - (yb_kw(d) - 1), yb_pad_h_hi(d) - (d->ksize - 1)};
     cuuint32_t estr[4] = {1, (cuuint32_t)yb_sw(d), (cuuint32_t)d->stride, 1};
     cr = encIm2col(&pl->kp.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides,
                    lower, upper, (cuuint32_t)kc, (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -416,7 +426,7 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
   pl->grid_x = d->c_out_pad / bn;
   pl->grid_y = (int)((M + BLOCK_M - 1) / BLOCK_M);
   pl->w = w_packed;
-  pl->impl = (d->impl_hint == 1 && !stem) ? 1 : 2;
+  pl->impl = (d->impl_hint == 1 && !stem && !d->s2_parity) ? 1 : 2;
   pl->stem_direct = 0;
   pl->ncta = 1;
   if (pl->impl == 2) {

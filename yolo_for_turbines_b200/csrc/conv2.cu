@@ -280,7 +280,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     const int ew = warp - 2;
     const uint32_t acc = uint32_t(ew >> 2);
     const int quad = warp & 3;
-    const bool direct = p.upsample2x || p.out_fp32;
+    const bool direct = p.upsample2x || p.out_fp32 || p.s2_parity != 0;
     const uint32_t wslot_base = epi_base + uint32_t(ew) * WSLOTS * C::WBOX_BYTES;
     const uint32_t swz = (C::BOX_ROW_BYTES == 128) ? (lane & 7) : ((lane >> 1) & 3);
     uint32_t tl = 0, wbox = 0;
@@ -306,6 +306,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         const size_t r00 = (size_t(img) * (2 * p.h_out) + 2 * po) * W2 + 2 * qo;
         out_row[0] = r00; out_row[1] = r00 + 1; out_row[2] = r00 + W2; out_row[3] = r00 + W2 + 1;
         n_out_rows = 4;
+      } else if (p.s2_parity) {
+        // GEMM row (img, a, b) -> pixel (2a + r, 2b) of the (2 h_out, 2 w_out) gradient tensor; column half t adds 1
+        const int hw = p.h_out * p.w_out;
+        const int img = m / hw;
+        const int rem = m - img * hw;
+        const int po = rem / p.w_out, qo = rem - po * p.w_out;
+        out_row[0] = (size_t(img) * (2 * p.h_out) + 2 * po + (p.s2_parity - 1)) * size_t(2 * p.w_out) + 2 * qo;
       }
       const bool staged = !direct && wvalid;
       bool acc_ready = false;
@@ -348,6 +355,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           const int n = nb + h * 32;
           float o[32];
           bn_act32(v, o, p.scale, p.bias, n, p.act);
+          size_t drow = size_t(m);   // direct-path addressing: (row, column) of the residual / output element
+          int dcol = n;
+          if (p.s2_parity) {
+            const int th = n >= p.s2_cin ? 1 : 0;
+            drow = out_row[0] + th;
+            dcol = n - th * p.s2_cin;
+          }
           if (p.has_residual) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -358,7 +372,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
                              : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
               } else {
                 r = valid ? __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) +
-                                                                 size_t(m) * p.res_pitch + n) + j)
+                                                                 drow * p.res_pitch + dcol) + j)
                           : make_uint4(0, 0, 0, 0);
               }
               o[8 * j + 0] += bf16_lo(r.x); o[8 * j + 1] += bf16_hi(r.x);
@@ -397,7 +411,9 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
                 w4[j].w = pack_bf16(o[8 * j + 6], o[8 * j + 7]);
               }
               for (int rr = 0; rr < n_out_rows; ++rr) {
-                uint4* yp = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + out_row[rr] * p.out_pitch + n);
+                uint4* yp = p.s2_parity
+                                ? reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + drow * p.out_pitch + dcol)
+                                : reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + out_row[rr] * p.out_pitch + n);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) yp[j] = w4[j];
               }
@@ -533,7 +549,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: tensor map B encode failed (%d)", (int)cr);
   }
-  const int direct = d->upsample2x || d->out_fp32;
+  const int direct = d->upsample2x || d->out_fp32 || d->s2_parity;
   const int boxc = bn < 64 ? bn : 64;
   const CUtensorMapSwizzle bswz = boxc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   if (!direct) {
@@ -568,6 +584,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   kp.out_fp32 = d->out_fp32; kp.check_nan = d->check_nan; kp.a_im2col = im2col;
   kp.stem_x = nullptr; kp.stem_h = d->h_in; kp.stem_w = d->w_in * 2;
   kp.stats = nullptr; kp.c_out_pad = d->c_out_pad;
+  kp.s2_parity = d->s2_parity; kp.s2_cin = d->s2_cin;
   pl->stem_direct = stem ? 1 : 0;
   if (stem) {
     YB_REQUIRE(bn == 64 && kc == 64 && d->stem_c == 3 && d->ksize == 1 && tiles_n == 1 && !d->has_residual && !direct,

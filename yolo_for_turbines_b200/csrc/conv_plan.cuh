@@ -10,6 +10,7 @@ constexpr uint32_t PLAN_MAGIC = 0x59423230u;  // "YB20"
 inline int yb_kw(const yolo_conv_desc* d) { return d->ksize_w > 0 ? d->ksize_w : d->ksize; }
 inline int yb_sw(const yolo_conv_desc* d) { return d->stride_w > 0 ? d->stride_w : d->stride; }
 inline int yb_pad_hi(const yolo_conv_desc* d) { return d->pad_w_hi_plus1 > 0 ? d->pad_w_hi_plus1 - 1 : d->pad; }
+inline int yb_pad_h_hi(const yolo_conv_desc* d) { return d->pad_h_hi_plus1 > 0 ? d->pad_h_hi_plus1 - 1 : d->pad; }
 
 // v1: one CTA per output tile (conv.cu)
 struct ConvKParams {
@@ -48,6 +49,7 @@ struct ConvKParams2 {
   const float* stem_x;  // STEM mode: fp32 NCHW image (set per launch)
   int stem_h, stem_w;
   int c_out_pad;
+  int s2_parity, s2_cin;  // stride-2 data-gradient sub-convolution (yolo_conv_desc.s2_parity)
   double* stats;        // training forward: per-channel [sum, sum of squares] of the stored bf16 output (set per launch)
 };
 

@@ -480,6 +480,26 @@ __global__ void k_pack_weights_dgrad(const float* __restrict__ w, int c_out, int
   out[idx] = __float2bfloat16_rn(v);
 }
 
+// stride-2 data gradient, row parity r: out[(t*rows_half + ci)][da][db][co]; kh = 1 (r = 0) or 2 - 2*da (r = 1);
+// t = 0 uses kw = 1 at db = 0 only, t = 1 uses kw = 2 at db = 0 and kw = 0 at db = 1
+__global__ void k_pack_weights_dgrad_s2(const float* __restrict__ w, int c_out, int c_in, int r, int rows_half, int cols_pad,
+                                        __nv_bfloat16* __restrict__ out) {
+  const int taps = (r + 1) * 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = 2ll * rows_half * taps * cols_pad;
+  if (idx >= total) return;
+  const int co = int(idx % cols_pad);
+  const int tap = int((idx / cols_pad) % taps);
+  const int row = int(idx / ((long long)cols_pad * taps));
+  const int t = row / rows_half, ci = row - t * rows_half;
+  const int da = tap >> 1, db = tap & 1;
+  const int kh = r == 0 ? 1 : 2 - 2 * da;
+  const int kw = t == 0 ? (db == 0 ? 1 : -1) : (db == 0 ? 2 : 0);
+  float v = 0.f;
+  if (kw >= 0 && co < c_out && ci < c_in) v = w[((size_t(co) * c_in + ci) * 3 + kh) * 3 + kw];
+  out[idx] = __float2bfloat16_rn(v);
+}
+
 // torch.optim.SGD: g' = g * gscale + wd * p;  buf = first ? g' : mu * buf + g';  p -= lr * buf
 __global__ void __launch_bounds__(256) k_sgd(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
                                             long long n, float lr, float mu, float wd, float gscale, int first) {
@@ -648,6 +668,17 @@ extern "C" int yolo_pack_weights_train(const float* w_oihw, int c_out, int c_in,
   dim3 grid((c_in + PK_T - 1) / PK_T, (c_out + PK_T - 1) / PK_T);
   k_pack_weights_both<<<grid, 256, PK_T * (PK_T * taps + 1) * sizeof(float), (cudaStream_t)stream>>>(
       w_oihw, c_out, c_in, taps, c_in_pad, c_out_pad, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad));
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+extern "C" int yolo_pack_weights_dgrad_s2(const float* w_oihw, int c_out, int c_in, int r, int rows_half, int cols_pad,
+                                          void* w_packed, yb_stream_t stream) {
+  YB_REQUIRE(w_oihw && w_packed && c_out >= 1 && c_in >= 1 && (r == 0 || r == 1) && rows_half >= c_in && cols_pad >= c_out,
+             "yolo_pack_weights_dgrad_s2: bad argument");
+  const long long total = 2ll * rows_half * (r + 1) * 2 * cols_pad;
+  k_pack_weights_dgrad_s2<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, c_out, c_in, r, rows_half, cols_pad, static_cast<__nv_bfloat16*>(w_packed));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
