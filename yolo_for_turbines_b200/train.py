@@ -151,8 +151,7 @@ class TrainPlan:
         self.loss_sums = torch.zeros(18, dtype=torch.float64, device=dev)
         self.counters = torch.zeros(2 * len(self.ops), dtype=torch.int32, device=dev)   # last-block tickets (self-resetting)
         self.ev_dz = [torch.cuda.Event() for _ in self.ops]
-        stuffed_elems = max([B * op.src.H * op.src.W * op.pc.c_out_pad for op in self.ops[1:] if op.pc.stride_eff == 2] + [0])
-        self.stuffed = alloc(stuffed_elems, torch.bfloat16) if stuffed_elems else None
+        self.stuffed = None   # stride-2 data gradients run as row-parity sub-convolutions over dz: no zero-stuffed copy
 
         # gradient records
         self.grads: Dict[int, _Grad] = {}
@@ -169,7 +168,7 @@ class TrainPlan:
             op.dz = alloc(op.P * cp, torch.bfloat16)
             if op.head:
                 op.dz.zero_()  # the padding channels (255 -> 256, 21 -> 32) are never written again
-            op.stuffed = self.stuffed if (i > 0 and op.pc.stride_eff == 2) else None
+            op.stuffed = None
 
         def grad_of(t) -> _Grad:
             g = self.grads.get(id(t))
@@ -214,22 +213,34 @@ class TrainPlan:
             pc = op.pc
             g = grad_of(op.src)
             s2 = pc.stride_eff == 2
-            dd = ConvDesc()
-            dd.batch, dd.h_in, dd.w_in = B, (op.src.H if s2 else op.ho), (op.src.W if s2 else op.wo)
-            dd.c_in, dd.in_pitch = pc.c_out_pad, pc.c_out_pad
-            dd.c_out, dd.c_out_pad, dd.out_pitch = pc.c_in_eff, pc.c_in_eff, op.src.C
-            dd.ksize, dd.stride, dd.pad = pc.k_eff, 1, pc.pad_eff
-            res_ptr = None
+            res_ptr, res_pitch = None, 0
             if g.init:
-                dd.has_residual, dd.res_pitch, res_ptr = 1, op.src.C, ptr(g.buf)
+                res_ptr, res_pitch = ptr(g.buf), op.src.C
             else:
                 alias = self._pending_alias(op.src)
                 if alias is not None:
                     abuf, aoff, apitch = alias
-                    dd.has_residual, dd.res_pitch, res_ptr = 1, apitch, _p(abuf, 2 * aoff)
-            xin = self.stuffed if s2 else op.dz
-            op.dgrad_plan = E.make_conv_plan(dd, ptr(xin), ptr(trainer.wT[id(op.block)]), ptr(self.ones), ptr(self.zeros),
-                                             res_ptr, ptr(g.buf))
+                    res_ptr, res_pitch = _p(abuf, 2 * aoff), apitch
+            plans = []
+            for r in ((0, 1) if s2 else (None,)):
+                dd = ConvDesc()
+                dd.batch, dd.h_in, dd.w_in = B, op.ho, op.wo
+                dd.c_in, dd.in_pitch = pc.c_out_pad, pc.c_out_pad
+                dd.stride, dd.out_pitch = 1, op.src.C
+                if s2:   # dx[2a+r][2b+t] from dz[a+da][b+db]: stride-1 sub-convolution per output row parity
+                    dd.c_out = dd.c_out_pad = 2 * pc.c_in_eff
+                    dd.ksize, dd.pad = r + 1, 0
+                    dd.ksize_w, dd.stride_w, dd.pad_w_hi_plus1, dd.pad_h_hi_plus1 = 2, 1, 2, r + 1
+                    dd.s2_parity, dd.s2_cin = r + 1, pc.c_in_eff
+                    wts = trainer.wT_s2[id(op.block)][r]
+                else:
+                    dd.c_out, dd.c_out_pad = pc.c_in_eff, pc.c_in_eff
+                    dd.ksize, dd.pad = pc.k_eff, pc.pad_eff
+                    wts = trainer.wT[id(op.block)]
+                if res_ptr is not None:
+                    dd.has_residual, dd.res_pitch = 1, res_pitch
+                plans.append(E.make_conv_plan(dd, ptr(op.dz), ptr(wts), ptr(self.ones), ptr(self.zeros), res_ptr, ptr(g.buf)))
+            op.dgrad_plan = plans
             g.init = True
 
     # the alias contribution to the gradient of tensor t, known statically from the graph:
@@ -347,7 +358,8 @@ class TrainPlan:
                     lib.yolo_unpack_wgrad(_p(tr.dw_packed, 4 * tr.dw_off[id(op.block)]), pc.c_out, pc.c_in, pc.ksize,
                                           pc.c_in_eff, int(pc.stem), ptr(op.g_w), st)
             if i > 0:
-                lib.yolo_conv_fwd(op.dgrad_plan[1], sp, st)
+                for dp in op.dgrad_plan:
+                    lib.yolo_conv_fwd(dp[1], sp, st)
             if on_op_done is not None:
                 on_op_done(i)
         if side is not None:
@@ -486,6 +498,12 @@ class Trainer:
                 tot += pc.c_out_pad * pc.k_eff * pc.k_eff * pc.c_in_eff
                 if b is not first:
                     self.wT[id(b)] = torch.empty(pc.c_in_eff * pc.ksize * pc.ksize * pc.c_out_pad, dtype=torch.bfloat16, device=dev)
+            self.wT_s2 = {}   # stride-2 layers: one data-gradient pack per output row parity
+            for b in self.blocks:
+                pc = self.engine.packed[id(b)]
+                if b is not first and pc.stride_eff == 2:
+                    self.wT_s2[id(b)] = [torch.empty(2 * pc.c_in_eff * (r + 1) * 2 * pc.c_out_pad, dtype=torch.bfloat16, device=dev)
+                                         for r in (0, 1)]
             self.dw_packed = torch.zeros(tot, dtype=torch.float32, device=dev)
             self.losses = torch.zeros(4, dtype=torch.float32, device=dev)
         self.plans: Dict[tuple, TrainPlan] = {}
@@ -534,6 +552,10 @@ class Trainer:
                 else:
                     lib.yolo_pack_weights_train(ptr(w), pc.c_out, pc.c_in, pc.ksize, pc.c_in_eff, pc.c_out_pad, ptr(pc.w),
                                                 ptr(self.wT[id(b)]), st)
+                if id(b) in self.wT_s2:
+                    for r in (0, 1):
+                        lib.yolo_pack_weights_dgrad_s2(ptr(w), pc.c_out, pc.c_in, r, pc.c_in_eff, pc.c_out_pad,
+                                                       ptr(self.wT_s2[id(b)][r]), st)
                 if not b.batch_norm_act:  # head conv: scale 1, bias = conv bias
                     lib.yolo_fold_bn(None, None, None, None, ptr(b.conv.bias), 0.0, pc.c_out, pc.c_out_pad, ptr(pc.scale),
                                      ptr(pc.bias), st)
@@ -672,6 +694,7 @@ class Trainer:
         n_head = len(plan.heads)
         fwd = 1 + len(plan.ops) + 2 * n_bn
         loss = 2 * n_head
-        bwd = 2 * n_bn + 2 * n_head + 2 * len(plan.ops) + (len(plan.ops) - 1)
-        upd = 1 + len(plan.ops) + n_head
+        n_s2 = sum(1 for op in plan.ops[1:] if op.pc.stride_eff == 2)
+        bwd = 2 * n_bn + 2 * n_head + 2 * len(plan.ops) + (len(plan.ops) - 1) + n_s2
+        upd = 1 + len(plan.ops) + n_head + 2 * n_s2
         return fwd + loss + bwd + upd
