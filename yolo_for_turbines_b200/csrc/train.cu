@@ -13,6 +13,8 @@
 //
 // Rows are handled 8 channels (one 16-byte load) per thread; per-channel sums go through shared-memory
 // double atomics and one global double atomic per channel per block.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "conv_ptx.cuh"
 
@@ -408,11 +410,13 @@ __global__ void __launch_bounds__(TR_THREADS, 4) k_bn_act_bwd_apply(const BnBwdP
 // One block per 32 (co) x 32 (ci) tile staged through shared memory: OIHW rows are read as contiguous runs of
 // 32*taps floats, both packs are written as 64-byte runs (ci-contiguous / co-contiguous).
 constexpr int PK_T = 32;
-__global__ void __launch_bounds__(256) k_pack_weights_both(const float* __restrict__ w, int c_out, int c_in, int taps,
+template <int TAPS>
+__global__ void __launch_bounds__(256) k_pack_weights_both(const float* __restrict__ w, int c_out, int c_in, int /*taps*/,
                                                           int c_in_pad, int c_out_pad, __nv_bfloat16* __restrict__ fwd,
                                                           __nv_bfloat16* __restrict__ bwd) {
   extern __shared__ float s_tile[];  // [PK_T][PK_T * taps + 1]
-  const int L = PK_T * taps, pitch = L + 1;
+  constexpr int taps = TAPS;         // compile-time: every index split below is a multiply-shift, not a division
+  constexpr int L = PK_T * taps, pitch = L + 1;
   const int ci0 = blockIdx.x * PK_T, co0 = blockIdx.y * PK_T;
   const int nci = min(PK_T, c_in - ci0);
   for (int i = threadIdx.x; i < PK_T * L; i += 256) {
@@ -436,9 +440,11 @@ __global__ void __launch_bounds__(256) k_pack_weights_both(const float* __restri
 
 // packed fp32 [c_out_pad][taps][c_in_pad] -> OIHW, one block per output channel through shared memory so that both
 // the packed rows and the OIHW row are accessed contiguously
-__global__ void __launch_bounds__(256) k_unpack_wgrad_rows(const float* __restrict__ packed, int c_in, int taps, int c_in_pad,
+template <int TAPS>
+__global__ void __launch_bounds__(256) k_unpack_wgrad_rows(const float* __restrict__ packed, int c_in, int /*taps*/, int c_in_pad,
                                                           float* __restrict__ grad) {
   extern __shared__ float s_tile[];  // [taps][c_in]
+  constexpr int taps = TAPS;
   const int co = blockIdx.x;
   for (int i = threadIdx.x; i < taps * c_in; i += 256) {
     const int t = i / c_in, ci = i - t * c_in;
@@ -535,7 +541,12 @@ int check_rows(long long P, int C, int pitch, const char* what) {
 int reduce_grid(long long P, int groups) {
   const int lanes = TR_THREADS / groups;
   long long blocks = (P + (long long)lanes * 8 - 1) / ((long long)lanes * 8);  // >= 8 rows per thread
-  if (blocks > 148 * 6) blocks = 148 * 6;
+  static int cap = 0;  // every block ends with one double atomic per channel statistic: the tail grows with the grid
+  if (cap == 0) {
+    const char* e = getenv("YOLO_B200_REDUCE_BLOCKS");
+    cap = e && atoi(e) > 0 ? atoi(e) : 148 * 3;
+  }
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
@@ -640,7 +651,10 @@ extern "C" int yolo_unpack_wgrad(const float* packed, int c_out, int c_in, int k
   const long long total = (long long)c_out * c_in * ksize * ksize;
   const size_t row_bytes = size_t(ksize) * ksize * c_in * sizeof(float);
   if (!stem && row_bytes <= 48 * 1024) {
-    k_unpack_wgrad_rows<<<c_out, 256, row_bytes, (cudaStream_t)stream>>>(packed, c_in, ksize * ksize, c_in_pad, grad_oihw);
+    if (ksize == 3)
+      k_unpack_wgrad_rows<9><<<c_out, 256, row_bytes, (cudaStream_t)stream>>>(packed, c_in, 9, c_in_pad, grad_oihw);
+    else
+      k_unpack_wgrad_rows<1><<<c_out, 256, row_bytes, (cudaStream_t)stream>>>(packed, c_in, 1, c_in_pad, grad_oihw);
   } else {
     k_unpack_wgrad<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(packed, c_out, c_in, ksize * ksize, c_in_pad,
                                                                                     stem, grad_oihw);
@@ -666,8 +680,13 @@ extern "C" int yolo_pack_weights_train(const float* w_oihw, int c_out, int c_in,
                  c_out_pad >= c_out, "yolo_pack_weights_train: bad argument");
   const int taps = ksize * ksize;
   dim3 grid((c_in + PK_T - 1) / PK_T, (c_out + PK_T - 1) / PK_T);
-  k_pack_weights_both<<<grid, 256, PK_T * (PK_T * taps + 1) * sizeof(float), (cudaStream_t)stream>>>(
-      w_oihw, c_out, c_in, taps, c_in_pad, c_out_pad, static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad));
+  const size_t smem = PK_T * (PK_T * taps + 1) * sizeof(float);
+  if (taps == 9)
+    k_pack_weights_both<9><<<grid, 256, smem, (cudaStream_t)stream>>>(w_oihw, c_out, c_in, taps, c_in_pad, c_out_pad,
+                                                                     static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad));
+  else
+    k_pack_weights_both<1><<<grid, 256, smem, (cudaStream_t)stream>>>(w_oihw, c_out, c_in, taps, c_in_pad, c_out_pad,
+                                                                     static_cast<__nv_bfloat16*>(w_fwd), static_cast<__nv_bfloat16*>(w_dgrad));
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
