@@ -399,6 +399,8 @@ class ForwardPlan:
         self.graph.replay()
 
     def check_status(self):
+        if getattr(self, "done_event", None) is not None:
+            self.done_event.synchronize()  # the forward ran on a Detector lane stream
         s = int(self.status.item())  # the ONE host sync of a forward (the reference has 28)
         if s & STATUS_NAN_INPUT:
             raise AssertionError("NaN in the input tensor")  # model.py:175
@@ -439,8 +441,10 @@ class Engine:
                     pc.refresh()
             self._sig = sig
 
-    def plan(self, B, H, W) -> ForwardPlan:
-        key = (B, H, W)
+    def plan(self, B, H, W, lane: int = 0) -> ForwardPlan:
+        """`lane` > 0 gives an independent plan (own buffers, own CUDA graph) for the same shape, so that several
+        batches can be in flight on different streams (utils.Detector(lanes=2))."""
+        key = (B, H, W) if lane == 0 else (B, H, W, lane)
         p = self.plans.get(key)
         if p is None:
             with torch.cuda.device(self.device):

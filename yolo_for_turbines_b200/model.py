@@ -234,7 +234,7 @@ class YOLOv3(_EngineHolder, nn.Module):
             self.__dict__["_yb_engine"] = eng
         return eng
 
-    def _prepare(self, x):
+    def _prepare(self, x, lane: int = 0):
         """Input checks + (cached) plan lookup shared by forward_async and utils.Detector."""
         require_cuda(x, "YOLOv3 input")
         if self.training:
@@ -246,7 +246,7 @@ class YOLOv3(_EngineHolder, nn.Module):
         eng.refresh_if_needed()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
-        return eng.plan(x.shape[0], x.shape[2], x.shape[3]), x
+        return eng.plan(x.shape[0], x.shape[2], x.shape[3], lane), x
 
     def forward_async(self, x):
         """Enqueues the whole forward on the current stream and returns (plan, head views) WITHOUT

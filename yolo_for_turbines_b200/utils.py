@@ -136,8 +136,16 @@ class NmsResult:
     boxes: torch.Tensor      # [total, 6] candidates as given
     keep_idx: torch.Tensor   # [total] int32: row indices of survivors, image-major, reference order
     keep_off: torch.Tensor   # [B+1] int32: image b owns keep_idx[keep_off[b]:keep_off[b+1]]
+    ready: Optional[torch.cuda.Event] = None   # set when the result was produced on another stream (Detector lanes)
+
+    def wait(self):
+        """Makes the current stream wait for the result (no-op for results produced on the current stream)."""
+        if self.ready is not None:
+            torch.cuda.current_stream(self.boxes.device).wait_event(self.ready)
+        return self
 
     def kept_rows(self) -> List[torch.Tensor]:
+        self.wait()
         off = self.keep_off.tolist()
         rows = self.boxes[self.keep_idx[: off[-1]].long()]
         return [rows[off[b]:off[b + 1]] for b in range(len(off) - 1)]
@@ -273,15 +281,22 @@ class Detector:
     (demo.py:30-55).  No host sync happens until results are read."""
 
     def __init__(self, model, anchors=None, iou_threshold=config.NMS_IOU_THRESHOLD,
-                 obj_threshold=config.CONF_THRESHOLD, box_format="center"):
+                 obj_threshold=config.CONF_THRESHOLD, box_format="center", lanes: int = 1):
+        """lanes > 1: consecutive calls alternate between `lanes` independent pipelines (own activation buffers, CUDA
+        graph and stream), so the DRAM- / latency-bound stages of one batch (input conversion, decode, NMS) and the
+        tails of its conv kernels overlap with the conv kernels of the next batch.  Results then carry a `ready`
+        event: `NmsResult.wait()` / `kept_rows()` / `plan.check_status()` order the consumer after the lane."""
         self.model = model
+        self.lanes = max(1, int(lanes))
+        self._next_lane = 0
+        self._lane_streams = {}
         self.anchors = config.ANCHORS if anchors is None else anchors
         self.iou_threshold, self.obj_threshold, self.box_format = iou_threshold, obj_threshold, box_format
         self.use_graph = True
         self._state = {}
 
-    def _get_state(self, B, grids, device):
-        key = (B, tuple(grids), str(device))
+    def _get_state(self, B, grids, device, lane=0):
+        key = (B, tuple(grids), str(device), lane)
         st = self._state.get(key)
         if st is None:
             n = sum(3 * s * s for s in grids)
@@ -308,9 +323,37 @@ class Detector:
         """Returns (NmsResult, plan); plan.check_status() reports NaN inputs/layers after the fact.
         Call 1 of a shape runs eagerly (warm-up), call 2 captures convs + decode + NMS (~115 launches) in ONE
         CUDA graph, later calls replay it; only the input conversion (its source pointer changes) stays eager."""
-        plan, x = self.model._prepare(x)
+        if self.lanes == 1:
+            return self._run(x, 0)
+        lane = self._next_lane
+        self._next_lane = (lane + 1) % self.lanes
+        dev = x.device
+        key = (str(dev), lane)
+        ls = self._lane_streams.get(key)
+        if ls is None:
+            ls = self._lane_streams[key] = (torch.cuda.Stream(device=dev), torch.cuda.Event(), torch.cuda.Event())
+        stream, ev_in, ev_done = ls
+        cur = torch.cuda.current_stream(dev)
+        ev_in.record(cur)            # x (and everything the caller enqueued before) is ready
+        stream.wait_event(ev_in)
+        x.record_stream(stream)
+        with torch.cuda.stream(stream):
+            res, plan = self._run(x, lane)
+            ev_done.record(stream)
+        res.ready = ev_done
+        plan.done_event = ev_done
+        return res, plan
+
+    def join(self, device=None):
+        """Makes the current stream wait for everything enqueued on the lane streams so far."""
+        for (dev, _), (stream, _, _) in self._lane_streams.items():
+            if device is None or str(device) == dev:
+                torch.cuda.current_stream(stream.device).wait_stream(stream)
+
+    def _run(self, x: torch.Tensor, lane: int):
+        plan, x = self.model._prepare(x, lane)
         with torch.cuda.device(x.device):
-            st = self._get_state(plan.B, [h.H for h in plan.heads], x.device)
+            st = self._get_state(plan.B, [h.H for h in plan.heads], x.device, lane)
             if st.get("plan") is not plan:  # the model re-planned (new engine): drop the stale graph
                 st.update(plan=plan, graph=None, calls=0, res=None)
             if st["graph"] is not None:
