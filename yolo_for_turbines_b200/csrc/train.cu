@@ -53,13 +53,19 @@ __device__ __forceinline__ float act_fwd(float y, int act) {
   }
   return y;
 }
-// d act(y) / dy
+// d act(y) / dy.  Mish: with n = e^y, m = n (n + 2): tanh(softplus) = t = m / (m + 2), sigmoid = s = n / (1 + n) and
+// d/dy = t + y s (1 - t^2).  Both quotients share ONE reciprocal, r = 1 / ((m + 2)(1 + n)) -- the kernels that call
+// this are bound by the special-function unit (ncu: XU pipe 40 %, DRAM 28 %), so a MUFU per element matters.
 __device__ __forceinline__ float act_grad(float y, int act) {
   if (act == YB_ACT_LEAKY) return y > 0.f ? 1.f : 0.1f;
   if (act == YB_ACT_MISH) {
-    float sg;
-    const float t = mish_tanh_sp(y, sg);
-    return fmaf(y * (1.f - t * t), sg, t);
+    const float n = __expf(fminf(y, 20.f));
+    const float m = n * (n + 2.f);
+    const float a = m + 2.f, b = 1.f + n;
+    const float r = __fdividef(1.f, a * b);   // MUFU.RCP; (m + 2)(1 + n) <= 1.2e26 for y <= 20: no overflow
+    const float t = m * b * r, sg = n * a * r;
+    const float g = fmaf(y * sg, fmaf(-t, t, 1.f), t);
+    return y > 20.f ? 1.f : g;
   }
   return 1.f;
 }
@@ -221,10 +227,12 @@ __global__ void __launch_bounds__(TR_THREADS) k_bn_act_fwd(const __nv_bfloat16* 
                                                            const float* __restrict__ scale, const float* __restrict__ bias,
                                                            int act, const __nv_bfloat16* __restrict__ res, int res_pitch,
                                                            __nv_bfloat16* __restrict__ y, int y_pitch, int up2x) {
-  const long long idx = (long long)blockIdx.x * TR_THREADS + threadIdx.x;
-  if (idx >= g.P * g.groups) return;
-  const long long r = idx / g.groups;
-  const int c = int(idx - r * g.groups) * 8;
+  // 32-bit index split (the host wrapper guarantees P * groups < 2^31): a 64-bit division per thread costs more
+  // instructions than the whole activation, and these kernels are issue-bound
+  const unsigned idx = blockIdx.x * unsigned(TR_THREADS) + threadIdx.x;
+  if (idx >= unsigned(g.P) * unsigned(g.groups)) return;
+  const unsigned r = idx / unsigned(g.groups);
+  const int c = int(idx - r * unsigned(g.groups)) * 8;
   float f[8];
   unpack8(ld8(z, size_t(r), z_pitch, c), f);
   const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
@@ -368,10 +376,10 @@ __global__ void __launch_bounds__(TR_THREADS, 4) k_bn_act_bwd_apply(const BnBwdP
                                                                     int dz_pitch, __nv_bfloat16* __restrict__ stuffed,
                                                                     int stuffed_pitch) {
   const RowGeom& g = p.g;
-  const long long idx = (long long)blockIdx.x * TR_THREADS + threadIdx.x;
-  if (idx >= g.P * g.groups) return;
-  const long long r = idx / g.groups;
-  const int c = int(idx - r * g.groups) * 8;
+  const unsigned idx = blockIdx.x * unsigned(TR_THREADS) + threadIdx.x;   // 32-bit split, see k_bn_act_fwd
+  if (idx >= unsigned(g.P) * unsigned(g.groups)) return;
+  const unsigned r = idx / unsigned(g.groups);
+  const int c = int(idx - r * unsigned(g.groups)) * 8;
   float zf[8], d[8], o[8];
   unpack8(ld8(p.z, size_t(r), p.z_pitch, c), zf);
   load_dA(p.dA, p.dA_pitch, g, r, c, p.up2x, d);
@@ -536,6 +544,7 @@ __global__ void __launch_bounds__(256) k_sgd(float* __restrict__ p, const float*
 int check_rows(long long P, int C, int pitch, const char* what) {
   YB_REQUIRE(P >= 1 && C >= 8 && C % 8 == 0 && C <= 2048 && pitch >= C && pitch % 8 == 0, "%s: bad rows (P %lld, C %d, pitch %d)",
              what, P, C, pitch);
+  YB_REQUIRE(P * (C / 8) < (1ll << 31), "%s: more than 2^31 (row, channel group) pairs", what);
   return YB_OK;
 }
 int reduce_grid(long long P, int groups) {
