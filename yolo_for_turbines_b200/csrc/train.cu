@@ -318,7 +318,8 @@ __device__ __forceinline__ void bn_bwd_finalize_channel(const BnBwdParams& p, co
 }
 
 __global__ void __launch_bounds__(TR_THREADS, 3) k_bn_act_bwd_reduce(const BnBwdParams p, double* __restrict__ sums,
-                                                                     unsigned int* counter, const BnBwdFinalize f) {
+                                                                     unsigned int* counter, const BnBwdFinalize f,
+                                                                     __nv_bfloat16* __restrict__ dy_out, int dy_pitch) {
   __shared__ float red[16 * RED_STRIDE];
   const RowGeom& g = p.g;
   const int lanes = TR_THREADS / g.groups;
@@ -332,13 +333,17 @@ __global__ void __launch_bounds__(TR_THREADS, 3) k_bn_act_bwd_reduce(const BnBwd
     const int c = grp * 8;
     float sc[8], bi[8];
     ld8f(p.scale + c, sc); ld8f(p.bias + c, bi);
-    auto accum = [&](const float (&zf)[8], const float (&d)[8]) {
+    // dy = dA * act'(y) is also WRITTEN (bf16, into the dz buffer): pass 2 then needs neither dA nor the
+    // activation derivative again -- these kernels are issue-bound (ncu), not DRAM-bound
+    auto accum = [&](const float (&zf)[8], float (&d)[8], long long row) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float dy = d[k] * act_grad(fmaf(zf[k], sc[k], bi[k]), p.act);
+        d[k] = dy;
         s[k] += dy;
         q[k] = fmaf(dy, zf[k], q[k]);
       }
+      *reinterpret_cast<uint4*>(dy_out + size_t(row) * dy_pitch + c) = pack8(d);
     };
     long long r = r0 + lane;
     if (!p.up2x) {
@@ -346,15 +351,15 @@ __global__ void __launch_bounds__(TR_THREADS, 3) k_bn_act_bwd_reduce(const BnBwd
         const uint4 z0 = ld8(p.z, size_t(r), p.z_pitch, c), z1 = ld8(p.z, size_t(r + lanes), p.z_pitch, c);
         const uint4 d0 = ld8(p.dA, size_t(r), p.dA_pitch, c), d1 = ld8(p.dA, size_t(r + lanes), p.dA_pitch, c);
         float zf[8], d[8];
-        unpack8(z0, zf); unpack8(d0, d); accum(zf, d);
-        unpack8(z1, zf); unpack8(d1, d); accum(zf, d);
+        unpack8(z0, zf); unpack8(d0, d); accum(zf, d, r);
+        unpack8(z1, zf); unpack8(d1, d); accum(zf, d, r + lanes);
       }
     }
     for (; r < r1; r += lanes) {
       float zf[8], d[8];
       unpack8(ld8(p.z, size_t(r), p.z_pitch, c), zf);
       load_dA(p.dA, p.dA_pitch, g, r, c, p.up2x, d);
-      accum(zf, d);
+      accum(zf, d, r);
     }
   }
   block_channel_reduce(s, q, g.groups, lanes, active, g.C, red, sums);
@@ -370,7 +375,8 @@ __global__ void k_bias_finalize(const double* __restrict__ sums, int C, float* _
   if (c < C) dbias[c] = float(sums[2 * c]);
 }
 
-// Pass 2: dz = scale*dy + c1*z + c0; optional zero-stuffed copy at 2x resolution (value at (2i, 2j))
+// Pass 2: dz = scale*dy + c1*z + c0, in place over the dy that pass 1 left in the dz buffer; optional zero-stuffed
+// copy at 2x resolution (value at (2i, 2j))
 __global__ void __launch_bounds__(TR_THREADS, 4) k_bn_act_bwd_apply(const BnBwdParams p, const float* __restrict__ c1,
                                                                     const float* __restrict__ c0, __nv_bfloat16* __restrict__ dz,
                                                                     int dz_pitch, __nv_bfloat16* __restrict__ stuffed,
@@ -382,18 +388,12 @@ __global__ void __launch_bounds__(TR_THREADS, 4) k_bn_act_bwd_apply(const BnBwdP
   const int c = int(idx - r * unsigned(g.groups)) * 8;
   float zf[8], d[8], o[8];
   unpack8(ld8(p.z, size_t(r), p.z_pitch, c), zf);
-  load_dA(p.dA, p.dA_pitch, g, r, c, p.up2x, d);
+  unpack8(*reinterpret_cast<const uint4*>(dz + size_t(r) * dz_pitch + c), d);   // dy, left here by pass 1
   {
-    float sc[8], bi[8];
-    ld8f(p.scale + c, sc); ld8f(p.bias + c, bi);
+    float sc[8], a1[8], a0[8];
+    ld8f(p.scale + c, sc); ld8f(c1 + c, a1); ld8f(c0 + c, a0);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = sc[k] * d[k] * act_grad(fmaf(zf[k], sc[k], bi[k]), p.act);
-  }
-  {
-    float a1[8], a0[8];
-    ld8f(c1 + c, a1); ld8f(c0 + c, a0);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] += fmaf(a1[k], zf[k], a0[k]);
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(sc[k], d[k], fmaf(a1[k], zf[k], a0[k]));
   }
   const uint4 u = pack8(o);
   *reinterpret_cast<uint4*>(dz + size_t(r) * dz_pitch + c) = u;
@@ -630,7 +630,8 @@ extern "C" int yolo_bn_act_bwd(const void* dA, int dA_pitch, int up2x, const voi
   p.scale = scale; p.bias = bias; p.mean = mean; p.rstd = rstd; p.act = act;
   p.g = RowGeom{P, C, C / 8, h, w};
   const BnBwdFinalize f{P, dgamma, dbeta, c1c0, c1c0 + C};
-  k_bn_act_bwd_reduce<<<reduce_grid(P, p.g.groups), TR_THREADS, 0, stream>>>(p, sums2c, counter, f);
+  k_bn_act_bwd_reduce<<<reduce_grid(P, p.g.groups), TR_THREADS, 0, stream>>>(p, sums2c, counter, f,
+                                                                             static_cast<__nv_bfloat16*>(dz), dz_pitch);
   YB_CHECK_LAUNCH();
   const long long n = P * p.g.groups;
   k_bn_act_bwd_apply<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, stream>>>(
