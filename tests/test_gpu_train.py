@@ -186,3 +186,29 @@ def test_frozen_parameters_stay_put():
         else:
             moved += int(not torch.equal(p.detach(), before[k]))
     assert moved == len(named) - len(frozen)
+
+
+def test_multi_scale_steps_rebuild_plans():
+    """Multi-scale training (config.py:43-45, dataset.py:113-117 change the image size every 10 batches): plans are
+    cached per size (at most `max_plans`), evicted plans are rebuilt, and every step keeps training the same weights."""
+    from oracle import yolo_oracle as orc
+    from yolo_for_turbines_b200.dataset import encode_targets
+    from yolo_for_turbines_b200.train import Trainer
+
+    m, sd, x, tg = _setup(2, "mish", 64, 2, 41)
+    m = m.cuda().train()
+    tr = Trainer(m, orc.TURBINE_ANCHORS, lr=1e-3, momentum=0.9, weight_decay=5e-4, max_plans=2)
+    g = torch.Generator().manual_seed(0)
+    prev = {k: p.detach().clone() for k, p in m.named_parameters()}
+    for size in (64, 96, 128, 64, 96):
+        xb = torch.rand(2, 3, size, size, generator=g).cuda()
+        boxes = [[[0.3, 0.4, 0.2, 0.3, 1.0], [0.7, 0.6, 0.4, 0.2, 0.0]], [[0.5, 0.5, 0.6, 0.5, 1.0]]]
+        tb = encode_targets(boxes, orc.TURBINE_ANCHORS, image_size=size)
+        losses = tr.step(xb, tb)
+        torch.cuda.synchronize()
+        assert torch.isfinite(losses).all(), (size, losses)
+        k = "layers.29.pred_block.1.conv.bias"
+        now = dict(m.named_parameters())[k].detach()
+        assert not torch.equal(now, prev[k]), size
+        prev[k] = now.clone()
+    assert len(tr.plans) <= 2 and tr.steps_done == 5
