@@ -151,6 +151,7 @@ class TrainPlan:
         self.loss_sums = torch.zeros(18, dtype=torch.float64, device=dev)
         self.counters = torch.zeros(2 * len(self.ops), dtype=torch.int32, device=dev)   # last-block tickets (self-resetting)
         self.ev_dz = [torch.cuda.Event() for _ in self.ops]
+        self.ev_branch = [torch.cuda.Event() for _ in self.ops]
         self.stuffed = None   # stride-2 data gradients run as row-parity sub-convolutions over dz: no zero-stuffed copy
 
         # gradient records
@@ -289,12 +290,10 @@ class TrainPlan:
         fused_stats = tr.fused_stats
         pending = tr._packs_pending
         main = torch.cuda.current_stream(dev)
-        for op in self.ops:
-            if pending:
-                main.wait_event(tr.ev_pack[id(op.block)])   # this layer's operand packs (side stream) are ready
+        def run_op(op, st):
             if op.head:
                 lib.yolo_conv_fwd(op.fwd_plan[1], sp, st)
-                continue
+                return
             pc, bn, blk = op.pc, op.bn, op.block.batch_norm
             C_ = pc.c_out
             mom = float(blk.momentum if blk.momentum is not None else 0.1)
@@ -316,6 +315,25 @@ class TrainPlan:
                 res_ptr, res_pitch = _p(rroot.buf, 2 * roff), rroot.C
             lib.yolo_bn_act_fwd(ptr(op.z), op.P, C_, pc.c_out_pad, ptr(bn["scale"]), ptr(bn["bias"]), ACT_CODES[pc.act],
                                 res_ptr, res_pitch, _p(droot.buf, 2 * doff), droot.C, int(op.upsample), op.ho, op.wo, st)
+
+        # The scale heads (ScalePredictionBlock, model.py:123-148) branch off the trunk and only the loss reads them:
+        # they run on the side stream, beside the trunk layers that follow (small 13x13 / 26x26 kernels either way).
+        side = tr.wgrad_stream
+        branched = False
+        for op in self.ops:
+            if pending:
+                main.wait_event(tr.ev_pack[id(op.block)])   # this layer's operand packs (side stream) are ready
+            if side is not None and ".pred_block." in op.name:
+                if op.name.endswith(".pred_block.0"):
+                    self.ev_branch[op.index].record(main)   # the trunk tensor the head reads is complete
+                    side.wait_event(self.ev_branch[op.index])
+                with torch.cuda.stream(side):
+                    run_op(op, stream_ptr(dev))
+                branched = True
+            else:
+                run_op(op, st)
+        if branched:
+            main.wait_stream(side)
         tr._packs_pending = False
         torch._foreach_add_(tr.bn_counters, 1)   # nn.BatchNorm2d.num_batches_tracked (state_dict parity)
 
