@@ -55,7 +55,7 @@ class _Grad:
 
 class _TrainOp:
     __slots__ = ("pc", "block", "src", "dst", "res", "upsample", "head", "name", "z", "P", "ho", "wo", "fwd_plan",
-                 "dgrad_plan", "wgrad_plan", "wT", "dz", "bn", "dw_off", "g_w", "g_b", "g_gamma", "g_beta", "stuffed", "index")
+                 "dgrad_plan", "wgrad_plan", "dz", "bn", "g_w", "g_b", "g_gamma", "g_beta", "stuffed", "index")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -184,7 +184,6 @@ class TrainPlan:
                 g.buf = alloc(B * op.src.H * op.src.W * op.src.C, torch.bfloat16)
 
         # ---- plans ------------------------------------------------------------------------------------
-        descs = []
         for i, op in enumerate(self.ops):
             pc = op.pc
             sroot, soff = op.src.resolve()
@@ -206,7 +205,6 @@ class TrainPlan:
             lib.yolo_wgrad_plan_init(blob, lib.yolo_wgrad_plan_bytes(), C.byref(d), x_ptr, ptr(op.dz), pc.c_out_pad,
                                      _p(trainer.dw_packed, 4 * trainer.dw_off[id(op.block)]), 0)
             op.wgrad_plan = (raw, blob)
-            descs.append(d)
         # data gradients, in EXECUTION order (reverse): the first launch that targets a tensor's gradient writes it
         # (absorbing the skip / route contribution through the residual operand), later ones accumulate in place
         for i in range(len(self.ops) - 1, 0, -1):
