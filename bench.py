@@ -212,19 +212,39 @@ def run_train_workload(args, dev, dist, rank, world, local):
     e1.record()
     barrier()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
-    # end to end: pinned host images + targets uploaded every step, the four loss terms read back every step
+    # end to end: pinned host images + targets uploaded every step, the four loss terms read back every step.
+    # Software-pipelined like any training input pipeline: batch i+1 is uploaded on a copy stream (double-buffered)
+    # while step i computes; the loss read-back of step i is asynchronous into pinned memory.
     dx = [torch.empty_like(xs[0]) for _ in range(2)]
     dt = [[torch.empty_like(t, device=dev) for t in htg[0]] for _ in range(2)]
-    host_loss = torch.empty(4, dtype=torch.float32).pin_memory()
+    host_loss = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    up_done = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        j = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[j])       # the step that read this buffer pair has finished
+            dx[j].copy_(hx[j], non_blocking=True)
+            for a, b in zip(dt[j], htg[j]):
+                a.copy_(b, non_blocking=True)
+            up_done[j].record(copy_stream)
+
     barrier()
+    for ev in consumed:
+        ev.record(main_stream)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
+    upload(0)
     for i in range(args.steps):
         j = i % 2
-        dx[j].copy_(hx[j], non_blocking=True)
-        for a, b in zip(dt[j], htg[j]):
-            a.copy_(b, non_blocking=True)
-        host_loss.copy_(tr.step(dx[j], dt[j]), non_blocking=True)
+        if i + 1 < args.steps:
+            upload(i + 1)
+        main_stream.wait_event(up_done[j])
+        host_loss[j].copy_(tr.step(dx[j], dt[j]), non_blocking=True)
+        consumed[j].record(main_stream)
     t1.record()
     barrier()
     ms_e2e = max_over_ranks(t0.elapsed_time(t1))
