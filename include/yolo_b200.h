@@ -116,8 +116,20 @@ int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yolo_conv_desc
 int yolo_conv_fwd(const void* plan_host, uint32_t* status, yb_stream_t stream);
 /* Same launch, plus per-channel statistics of the STORED bf16 output accumulated into sums2c (device doubles,
  * [2*c] += sum, [2*c+1] += sum of squares; caller zeroes): the BatchNorm batch statistics of the training
- * forward (model.py:61 under model.train()) without a second pass over the tensor.  bf16, non-upsampled plans. */
-int yolo_conv_fwd_stats(const void* plan_host, uint32_t* status, double* sums2c, yb_stream_t stream);
+ * forward (model.py:61 under model.train()) without a second pass over the tensor.  bf16, non-upsampled plans.
+ * fin != NULL: the CTA that finishes last also does what yolo_bn_finalize does (all pointers device pointers;
+ * counter: a zero uint32 that is zero again on exit), so no finalize launch sits between the conv and
+ * yolo_bn_act_fwd.                                                                                              */
+typedef struct yolo_bn_finalize_desc {
+  long long P;                              /* rows (batch * h_out * w_out)                                   */
+  const float *gamma, *beta;
+  float eps, momentum;
+  float *running_mean, *running_var;        /* may be NULL                                                     */
+  float *mean, *rstd, *scale, *bias;        /* outputs, as yolo_bn_finalize                                    */
+  unsigned int* counter;
+} yolo_bn_finalize_desc;
+int yolo_conv_fwd_stats(const void* plan_host, uint32_t* status, double* sums2c, const yolo_bn_finalize_desc* fin,
+                        yb_stream_t stream);
 /* Fused stem launch: x_nchw = (B,3,H,W) fp32; also ORs YB_STATUS_NAN_INPUT (model.py:175).               */
 int yolo_conv_fwd_stem(const void* plan_host, const float* x_nchw, uint32_t* status, yb_stream_t stream);
 /* tile configuration chosen by plan_init: info8 = block_n, block_k, stages, tiles_n, tiles_m,

@@ -281,11 +281,31 @@ def test_conv_epilogue_statistics(B, H, cin, cout, k, stride):
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     plan = make_conv_plan(d, ptr(x), ptr(wpk), ptr(ones), ptr(zeros), None, ptr(z))
     sums = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
-    lib.yolo_conv_fwd_stats(plan[1], ptr(status), ptr(sums), st)
+    lib.yolo_conv_fwd_stats(plan[1], ptr(status), ptr(sums), None, st)
     torch.cuda.synchronize()
     zd = z.double()
     ref = torch.stack([zd.sum(0), (zd * zd).sum(0)], dim=1).reshape(-1)
     assert torch.allclose(sums, ref, rtol=1e-5, atol=1e-4 * float(ref.abs().max())), float((sums - ref).abs().max())
+    # with a finalize descriptor the conv's last CTA also produces what yolo_bn_finalize produces
+    from yolo_for_turbines_b200._lib import BnFinalizeDesc
+    gamma, beta = (0.5 + torch.rand(cout, generator=g)).to(dev), (0.2 * torch.randn(cout, generator=g)).to(dev)
+    outs = {k: torch.empty(cout, device=dev) for k in ("mean", "rstd", "scale", "bias")}
+    refs = {k: torch.empty(cout, device=dev) for k in ("mean", "rstd", "scale", "bias")}
+    rm, rv, rm2, rv2 = (torch.zeros(cout, device=dev), torch.ones(cout, device=dev), torch.zeros(cout, device=dev),
+                        torch.ones(cout, device=dev))
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    P = B * Ho * Ho
+    fin = BnFinalizeDesc(P, gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(), outs["mean"].data_ptr(),
+                         outs["rstd"].data_ptr(), outs["scale"].data_ptr(), outs["bias"].data_ptr(), counter.data_ptr())
+    sums2 = torch.zeros_like(sums)
+    lib.yolo_conv_fwd_stats(plan[1], ptr(status), ptr(sums2), C.byref(fin), st)
+    lib.yolo_bn_finalize(ptr(sums), P, cout, ptr(gamma), ptr(beta), 1e-5, 0.1, ptr(rm2), ptr(rv2), ptr(refs["mean"]),
+                         ptr(refs["rstd"]), ptr(refs["scale"]), ptr(refs["bias"]), st)
+    torch.cuda.synchronize()
+    assert int(counter) == 0
+    for k in outs:
+        assert torch.allclose(outs[k], refs[k], rtol=1e-4, atol=1e-5), k
+    assert torch.allclose(rm, rm2, rtol=1e-4, atol=1e-6) and torch.allclose(rv, rv2, rtol=1e-4, atol=1e-6)
 
 
 @pytest.mark.parametrize("cout,cin,k", [(64, 32, 3), (255, 1024, 1), (21, 256, 1), (1024, 512, 3), (128, 384, 1)])

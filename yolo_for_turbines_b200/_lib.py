@@ -34,6 +34,13 @@ class ConvDesc(C.Structure):
         "stages_hint", "impl_hint", "cta_pair_hint", "ksize_w", "stride_w", "pad_w_hi_plus1", "stem_c", "want_stats", "pad_h_hi_plus1", "s2_parity", "s2_cin")]
 
 
+class BnFinalizeDesc(C.Structure):
+    """Mirror of `yolo_bn_finalize_desc` (include/yolo_b200.h)."""
+    _fields_ = [("P", C.c_longlong), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("momentum", C.c_float),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+                ("scale", C.c_void_p), ("bias", C.c_void_p), ("counter", C.c_void_p)]
+
+
 _P, _I, _F, _D, _SZ, _LL = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_longlong
 
 # name -> (restype, argtypes); every int-returning entry is error-checked by _Lib.__getattr__
@@ -44,7 +51,7 @@ SIGNATURES = {
     "yolo_conv_plan_bytes": (_SZ, []),
     "yolo_conv_plan_init": (_I, [_P, _SZ, C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "yolo_conv_fwd": (_I, [_P, _P, _P]),
-    "yolo_conv_fwd_stats": (_I, [_P, _P, _P, _P]),
+    "yolo_conv_fwd_stats": (_I, [_P, _P, _P, C.POINTER(BnFinalizeDesc), _P]),
     "yolo_conv_fwd_stem": (_I, [_P, _P, _P, _P]),
     "yolo_conv_plan_info": (_I, [_P, C.POINTER(C.c_int32)]),
     "yolo_conv_fwd_simt": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),

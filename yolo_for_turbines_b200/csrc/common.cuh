@@ -120,3 +120,30 @@ __device__ __forceinline__ uint32_t yb_float_key_asc(float f) {
   uint32_t b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+
+// nn.BatchNorm2d training-mode finalize of one channel from its batch sums (shared by csrc/train.cu and by the conv
+// kernel's last-CTA epilogue, csrc/conv2.cu): biased variance for the normalisation, momentum update of the running
+// statistics with the UNBIASED variance.
+struct BnFinalize {
+  long long P;
+  const float *gamma, *beta;
+  float eps, momentum;
+  float *running_mean, *running_var, *mean, *rstd, *scale, *bias;
+};
+__device__ __forceinline__ void bn_finalize_channel(const BnFinalize& f, int c, double s, double q) {
+  const double n = double(f.P);
+  const double mean = s / n;
+  double var = q / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = float(1.0 / sqrt(var + double(f.eps)));
+  const float sc = f.gamma[c] * rstd;
+  f.mean[c] = float(mean);
+  f.rstd[c] = rstd;
+  f.scale[c] = sc;
+  f.bias[c] = f.beta[c] - float(mean) * sc;
+  if (f.running_mean) {
+    const double unbiased = f.P > 1 ? var * n / (n - 1.0) : var;
+    f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * float(mean);
+    f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * float(unbiased);
+  }
+}

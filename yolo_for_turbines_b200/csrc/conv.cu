@@ -463,12 +463,18 @@ extern "C" int yolo_conv_fwd(const void* plan_host, uint32_t* status, yb_stream_
   return YB_ERR_UNSUPPORTED;
 }
 
-extern "C" int yolo_conv_fwd_stats(const void* plan_host, uint32_t* status, double* sums2c, yb_stream_t stream_) {
+extern "C" int yolo_conv_fwd_stats(const void* plan_host, uint32_t* status, double* sums2c, const yolo_bn_finalize_desc* fin,
+                                   yb_stream_t stream_) {
   const ConvPlan* pl = static_cast<const ConvPlan*>(plan_host);
   YB_REQUIRE(pl && pl->magic == PLAN_MAGIC, "conv fwd: plan not initialised");
   YB_REQUIRE(pl->impl == 2 && sums2c, "conv fwd stats: needs the persistent kernel and a sums buffer");
   YB_REQUIRE(status || !pl->kp.check_nan, "conv fwd: status word required when check_nan is set");
-  return conv2_launch(pl, status, (cudaStream_t)stream_, sums2c);
+  if (!fin) return conv2_launch(pl, status, (cudaStream_t)stream_, sums2c);
+  YB_REQUIRE(fin->P >= 1 && fin->gamma && fin->beta && fin->mean && fin->rstd && fin->scale && fin->bias && fin->counter,
+             "conv fwd stats: incomplete finalize descriptor");
+  const BnFinalize f{fin->P, fin->gamma, fin->beta, fin->eps, fin->momentum, fin->running_mean, fin->running_var,
+                     fin->mean, fin->rstd, fin->scale, fin->bias};
+  return conv2_launch(pl, status, (cudaStream_t)stream_, sums2c, &f, fin->counter);
 }
 
 extern "C" int yolo_conv_fwd_stem(const void* plan_host, const float* x_nchw, uint32_t* status, yb_stream_t stream) {

@@ -472,6 +472,24 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stats_base + 4u * i));
       if (v != 0.f) atomicAdd(p.stats + i, double(v));
     }
+    if (p.fin_counter != nullptr) {
+      // the CTA that takes the last ticket sees every CTA's sums: it turns them into the layer's BatchNorm
+      // mean / rstd / scale / bias (and running statistics) -- no separate finalize launch on the critical path
+      __shared__ bool is_last;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(p.fin_counter, 1u);
+        is_last = ticket == gridDim.x - 1;
+        if (is_last) *p.fin_counter = 0u;
+      }
+      __syncthreads();
+      if (is_last) {
+        __threadfence();
+        for (int c = threadIdx.x; c < p.c_out_pad; c += blockDim.x)
+          bn_finalize_channel(p.fin, c, __ldcg(p.stats + 2 * c), __ldcg(p.stats + 2 * c + 1));
+      }
+    }
   }
 }
 
@@ -583,7 +601,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   kp.act = d->act; kp.has_residual = d->has_residual; kp.upsample2x = d->upsample2x;
   kp.out_fp32 = d->out_fp32; kp.check_nan = d->check_nan; kp.a_im2col = im2col;
   kp.stem_x = nullptr; kp.stem_h = d->h_in; kp.stem_w = d->w_in * 2;
-  kp.stats = nullptr; kp.c_out_pad = d->c_out_pad;
+  kp.stats = nullptr; kp.c_out_pad = d->c_out_pad; kp.fin_counter = nullptr;
   kp.s2_parity = d->s2_parity; kp.s2_cin = d->s2_cin;
   pl->stem_direct = stem ? 1 : 0;
   if (stem) {
@@ -616,13 +634,15 @@ int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status,
   return launch2<64, 64, 1, true>(pl, kp, stream);
 }
 
-int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats) {
+int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats, const BnFinalize* fin,
+                 unsigned int* fin_counter) {
   YB_REQUIRE(!pl->stem_direct, "conv fwd: stem plans are launched with yolo_conv_fwd_stem");
   YB_REQUIRE(!stats || (pl->d.want_stats && !(pl->d.upsample2x || pl->d.out_fp32)),
              "conv fwd: statistics need a plan built with want_stats and the staged bf16 output path");
   ConvKParams2 kp = pl->kp2;
   kp.status = status;
   kp.stats = stats;
+  if (stats && fin && fin_counter) { kp.fin = *fin; kp.fin_counter = fin_counter; }
 #define YB_L2(BN, KC)                                                        \
   if (pl->block_n == BN && pl->kc == KC)                                     \
     return pl->ncta == 2 ? launch2<BN, KC, 2>(pl, kp, stream) : launch2<BN, KC, 1>(pl, kp, stream);

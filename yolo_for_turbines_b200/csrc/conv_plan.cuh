@@ -50,6 +50,8 @@ struct ConvKParams2 {
   int stem_h, stem_w;
   int c_out_pad;
   int s2_parity, s2_cin;  // stride-2 data-gradient sub-convolution (yolo_conv_desc.s2_parity)
+  BnFinalize fin;       // training forward: finalize by the CTA that finishes last (fin_counter != nullptr)
+  unsigned int* fin_counter;
   double* stats;        // training forward: per-channel [sum, sum of squares] of the stored bf16 output (set per launch)
 };
 
@@ -75,5 +77,6 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
 // conv2.cu
 int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out, int im2col, PFN_encodeTiled encTiled,
                      const void* residual, void* y);
-int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats = nullptr);
+int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats = nullptr,
+                 const BnFinalize* fin = nullptr, unsigned int* fin_counter = nullptr);
 int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status, cudaStream_t stream);

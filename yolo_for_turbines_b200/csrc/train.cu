@@ -140,29 +140,6 @@ __global__ void __launch_bounds__(TR_THREADS) k_bn_stats(const __nv_bfloat16* __
 
 // nn.BatchNorm2d training semantics: normalise with the biased batch variance, update the running
 // statistics with momentum and the UNBIASED variance.
-struct BnFinalize {
-  long long P;
-  const float *gamma, *beta;
-  float eps, momentum;
-  float *running_mean, *running_var, *mean, *rstd, *scale, *bias;
-};
-__device__ __forceinline__ void bn_finalize_channel(const BnFinalize& f, int c, double s, double q) {
-  const double n = double(f.P);
-  const double mean = s / n;
-  double var = q / n - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const float rstd = float(1.0 / sqrt(var + double(f.eps)));
-  const float sc = f.gamma[c] * rstd;
-  f.mean[c] = float(mean);
-  f.rstd[c] = rstd;
-  f.scale[c] = sc;
-  f.bias[c] = f.beta[c] - float(mean) * sc;
-  if (f.running_mean) {
-    const double unbiased = f.P > 1 ? var * n / (n - 1.0) : var;
-    f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * float(mean);
-    f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * float(unbiased);
-  }
-}
 __global__ void k_bn_finalize(const double* __restrict__ sums, int C, const BnFinalize f) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) bn_finalize_channel(f, c, sums[2 * c], sums[2 * c + 1]);

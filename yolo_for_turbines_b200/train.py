@@ -36,7 +36,7 @@ import torch
 import torch.nn as nn
 
 from . import engine as E
-from ._lib import ACT_CODES, ConvDesc, YoloB200Error, lib, ptr, require_cuda, stream_ptr
+from ._lib import ACT_CODES, BnFinalizeDesc, ConvDesc, YoloB200Error, lib, ptr, require_cuda, stream_ptr
 
 
 def _p(t: torch.Tensor, byte_off: int = 0) -> C.c_void_p:
@@ -295,11 +295,12 @@ class TrainPlan:
             pc, bn, blk = op.pc, op.bn, op.block.batch_norm
             C_ = pc.c_out
             mom = float(blk.momentum if blk.momentum is not None else 0.1)
-            if fused_stats:   # batch statistics accumulated by the conv epilogue itself
-                lib.yolo_conv_fwd_stats(op.fwd_plan[1], sp, ptr(bn["sums"]), st)
-                lib.yolo_bn_finalize(ptr(bn["sums"]), op.P, C_, ptr(blk.weight), ptr(blk.bias), float(blk.eps), mom,
-                                     ptr(blk.running_mean), ptr(blk.running_var), ptr(bn["mean"]), ptr(bn["rstd"]),
-                                     ptr(bn["scale"]), ptr(bn["bias"]), st)
+            if fused_stats:   # batch statistics accumulated by the conv epilogue itself; its last CTA finalises them
+                fin = BnFinalizeDesc(op.P, blk.weight.data_ptr(), blk.bias.data_ptr(), float(blk.eps), mom,
+                                     blk.running_mean.data_ptr(), blk.running_var.data_ptr(), bn["mean"].data_ptr(),
+                                     bn["rstd"].data_ptr(), bn["scale"].data_ptr(), bn["bias"].data_ptr(),
+                                     self.counters.data_ptr() + 8 * op.index)
+                lib.yolo_conv_fwd_stats(op.fwd_plan[1], sp, ptr(bn["sums"]), C.byref(fin), st)
             else:
                 lib.yolo_conv_fwd(op.fwd_plan[1], sp, st)
                 lib.yolo_bn_stats_finalize(ptr(op.z), op.P, C_, pc.c_out_pad, ptr(bn["sums"]), _p(self.counters, 8 * op.index),
