@@ -212,3 +212,41 @@ def test_multi_scale_steps_rebuild_plans():
         assert not torch.equal(now, prev[k]), size
         prev[k] = now.clone()
     assert len(tr.plans) <= 2 and tr.steps_done == 5
+
+
+def test_full_size_step_properties():
+    """BASELINE configs[3] at full size (batch 32, 416x416, 2 classes, Mish), through properties that need no CPU
+    reference: (1) a fixed batch is over-fitted -- the summed loss falls over 6 SGD steps; (2) every parameter,
+    gradient, running statistic and loss term stays finite; (3) the data-gradient chain reaches the stem (its
+    weight gradient is non-zero); (4) BatchNorm running statistics move towards the batch statistics."""
+    import numpy as np
+
+    from yolo_for_turbines_b200 import config as cfg
+    from yolo_for_turbines_b200.dataset import encode_targets
+    from yolo_for_turbines_b200.model import YOLOv3
+    from yolo_for_turbines_b200.train import Trainer
+
+    torch.manual_seed(0)
+    B, S = 32, 416
+    m = YOLOv3(num_classes=2, activation="mish").cuda().train()
+    rm0 = m.layers[0].batch_norm.running_mean.clone()
+    tr = Trainer(m, cfg.TURBINE_ANCHORS, lr=1e-3, momentum=0.9, weight_decay=5e-4)
+    x = torch.rand(B, 3, S, S, device="cuda")
+    rng = np.random.default_rng(0)
+    boxes = []
+    for _ in range(B):
+        wh = rng.uniform(0.05, 0.5, (6, 2))
+        xy = rng.uniform(wh / 2, 1 - wh / 2)
+        boxes.append(np.concatenate([xy, wh, rng.integers(0, 2, (6, 1)).astype(np.float64)], axis=1))
+    tg = encode_targets(boxes, cfg.TURBINE_ANCHORS, image_size=S)
+    hist = []
+    for _ in range(6):
+        hist.append(float(tr.step(x, tg).sum()))
+    torch.cuda.synchronize()
+    assert all(np.isfinite(hist)) and hist[-1] < 0.9 * hist[0], hist
+    assert all(bool(torch.isfinite(p).all()) and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+    assert float(m.layers[0].conv.weight.grad.abs().max()) > 0
+    sd = m.state_dict()
+    assert all(bool(torch.isfinite(v).all()) for v in sd.values())
+    assert not torch.equal(m.layers[0].batch_norm.running_mean, rm0)
+    assert int(sd["layers.0.batch_norm.num_batches_tracked"]) == 6
