@@ -280,7 +280,9 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     const int ew = warp - 2;
     const uint32_t acc = uint32_t(ew >> 2);
     const int quad = warp & 3;
-    const bool direct = p.upsample2x || p.out_fp32 || p.s2_parity != 0;
+    // fp32 outputs (the scale heads) are staged too: 32-column fp32 boxes (128-byte rows) leave through TMA stores
+    const bool f32_staged = p.out_fp32 && !p.upsample2x && p.s2_parity == 0;
+    const bool direct = p.upsample2x || p.s2_parity != 0;
     const uint32_t wslot_base = epi_base + uint32_t(ew) * WSLOTS * C::WBOX_BYTES;
     const uint32_t swz = (C::BOX_ROW_BYTES == 128) ? (lane & 7) : ((lane >> 1) & 3);
     uint32_t tl = 0, wbox = 0;
@@ -323,7 +325,8 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         const int nb = n0 + b * C::BOXC;
         if (staged) {
           if (lane == 0) {
-            bulk_wait_group_read<WSLOTS - 1>();  // the TMA store that last used this slot has read it out
+            if (f32_staged) bulk_wait_group_read<0>();   // an fp32 box pair uses both slots: all earlier stores have read
+            else bulk_wait_group_read<WSLOTS - 1>();  // the TMA store that last used this slot has read it out
             if (p.has_residual) {
               mbar_expect_tx(res_bar(ew, slot), C::WBOX_BYTES);
               tma_load_2d(&p.tmR, res_bar(ew, slot), slot_addr, nb, m0w);
@@ -385,7 +388,15 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) saw_nan |= (o[j] != o[j]);
           }
-          if (!direct) {
+          if (f32_staged) {
+            // half h of the box -> its own 4 KB slot: 32 rows x 32 fp32 (128-byte rows, 128B swizzle)
+            const uint32_t fa = wslot_base + uint32_t(h) * 4096u + uint32_t(lane) * 128u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(fa + ((uint32_t(j) ^ uint32_t(lane & 7)) << 4)),
+                           "r"(__float_as_uint(o[4 * j])), "r"(__float_as_uint(o[4 * j + 1])),
+                           "r"(__float_as_uint(o[4 * j + 2])), "r"(__float_as_uint(o[4 * j + 3])) : "memory");
+          } else if (!direct) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t a = row_addr + (((h * 4 + j) ^ swz) << 4);
@@ -426,7 +437,12 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&p.tmY, slot_addr, nb, m0w);  // rows >= M are clipped by the tensor map
+            if (f32_staged) {
+              tma_store_2d(&p.tmY, wslot_base, nb, m0w);
+              if constexpr (C::BOXC == 64) tma_store_2d(&p.tmY, wslot_base + 4096u, nb + 32, m0w);
+            } else {
+              tma_store_2d(&p.tmY, slot_addr, nb, m0w);  // rows >= M are clipped by the tensor map
+            }
             bulk_commit_group();
           }
           if (p.stats != nullptr) {
@@ -567,10 +583,19 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: tensor map B encode failed (%d)", (int)cr);
   }
-  const int direct = d->upsample2x || d->out_fp32 || d->s2_parity;
+  const int direct = d->upsample2x || d->s2_parity;
   const int boxc = bn < 64 ? bn : 64;
   const CUtensorMapSwizzle bswz = boxc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  if (!direct) {
+  if (d->out_fp32 && !direct) {   // scale heads: fp32 boxes of 32 columns x 32 rows
+    cuuint64_t dims[2] = {(cuuint64_t)d->c_out_pad, (cuuint64_t)M};
+    cuuint32_t box[2] = {32u, 32u};
+    cuuint32_t estr[2] = {1, 1};
+    cuuint64_t ystr[1] = {(cuuint64_t)d->out_pitch * 4};
+    CUresult cr = encTiled(&kp.tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, y, dims, ystr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: fp32 tensor map Y encode failed (%d)", (int)cr);
+    kp.tmR = kp.tmY;
+  } else if (!direct) {
     cuuint64_t dims[2] = {(cuuint64_t)d->c_out_pad, (cuuint64_t)M};
     cuuint32_t box[2] = {(cuuint32_t)boxc, 32u};  // one epilogue warp's 32 rows
     cuuint32_t estr[2] = {1, 1};
