@@ -130,3 +130,54 @@ def test_product_package_never_imports_the_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("CPU oracle", ""), fn
+
+
+def test_letterbox_geometry_host_rule_equals_oracle():
+    """preprocess.letterbox_geometry (host side of yolo_letterbox_u8) against the oracle's restatement of
+    albumentations' LongestMaxSize / PadIfNeeded integer rules, over many shapes."""
+    import numpy as np
+
+    from oracle import preprocess_oracle as po
+    from yolo_for_turbines_b200.preprocess import letterbox_geometry
+
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        h, w = int(rng.integers(1, 3000)), int(rng.integers(1, 3000))
+        for size in (320, 416, 608):
+            assert letterbox_geometry(h, w, size) == po.letterbox_geometry(h, w, size), (h, w, size)
+
+
+def test_gradient_buckets_cover_the_flat_buffer():
+    from yolo_for_turbines_b200.train import make_buckets
+
+    import random
+    rnd = random.Random(1)
+    for _ in range(50):
+        sizes = [rnd.choice([4, 64, 512, 4096, 100000]) for _ in range(rnd.randint(1, 80))]
+        offs, n = [], 0
+        for s_ in sizes:
+            offs.append(n)
+            n += s_
+        bk = make_buckets([(o, i) for i, o in enumerate(offs)], n, rnd.choice([1, 1000, 50000, 10 ** 9]))
+        spans = sorted((lo, hi) for _, lo, hi in bk)
+        assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        firsts = [f for f, _, _ in bk]
+        assert firsts == sorted(firsts, reverse=True)            # fired in backward (descending op) order
+        for first_op, lo, hi in bk:                               # every op whose parameters lie in the slice is >= first_op
+            assert all(i >= first_op for i, o in enumerate(offs) if lo <= o < hi)
+
+
+def test_new_entry_points_refuse_cpu_tensors():
+    import torch
+
+    from yolo_for_turbines_b200._lib import YoloB200Error
+    from yolo_for_turbines_b200.dataset import encode_targets
+    from yolo_for_turbines_b200.loss import YOLOLoss
+    from yolo_for_turbines_b200.preprocess import letterbox_batch
+
+    with pytest.raises(YoloB200Error, match="no CPU fallback"):
+        letterbox_batch([torch.zeros(4, 4, 3, dtype=torch.uint8)], 32, device="cpu")
+    with pytest.raises(YoloB200Error, match="no CPU fallback"):
+        encode_targets([[[0.5, 0.5, 0.1, 0.1, 0]]], [[(0.1, 0.1)] * 3] * 3, image_size=64, device="cpu")
+    with pytest.raises(YoloB200Error, match="no CPU fallback"):
+        YOLOLoss()(torch.zeros(1, 3, 2, 2, 7), torch.zeros(1, 3, 2, 2, 6), [[1, 1]] * 3)
