@@ -11,7 +11,6 @@
 
 namespace {
 
-constexpr int NMS_THREADS = 512;
 
 __device__ __forceinline__ int find_image(const int32_t* __restrict__ off, int batch, int i) {
   int lo = 0, hi = batch;  // largest b with off[b] <= i
@@ -162,9 +161,7 @@ __device__ __forceinline__ bool nms_pair(const float4 e, const float ae, const f
 //       global memory).  A later box is only tested against survivors that share an x-bin AND a y-bin
 //       with it -- disjoint extents cannot suppress (iou == 0 < thr) -- so the usual cost per (box,
 //       chunk) is a few shared-memory words instead of up to 32 IoU tests.
-constexpr int NMS_WARPS = NMS_THREADS / 32;
-constexpr int NMS_QPT = 48;  // owned boxes per thread: 48 x 512 = 24 576 boxes per segment take the fast path
-constexpr int NMS_REG_CAP = NMS_THREADS * NMS_QPT;
+constexpr int NMS_QPT = 48;  // owned boxes per thread: 48 x 512 = 24 576 boxes per segment take the fast path (NT = 512)
 
 __device__ __forceinline__ int nms_bin(float v) {  // monotone and clamped => overlapping extents share a bin
   return (int)fminf(fmaxf(v * 32.f, 0.f), 31.f);
@@ -182,7 +179,10 @@ __device__ __forceinline__ uint32_t nms_candidates(uint32_t bins, const uint32_t
   return mx & my;
 }
 
-__global__ void __launch_bounds__(NMS_THREADS)
+// NT threads per segment CTA: 512 suits few long segments, 128 many short ones (4x the resident CTAs per SM: 24 KB of
+// bins and a quarter of the threads each) -- the host picks by the average segment length it can expect.
+template <int NT>
+__global__ void __launch_bounds__(NT)
 k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
                const uint64_t* __restrict__ key2, const int32_t* __restrict__ val2,
                const int32_t* __restrict__ seg_starts, const int32_t* __restrict__ nseg_dev,
@@ -195,6 +195,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
   extern __shared__ uint32_t s_bins[];  // [NMS_QPT][NMS_THREADS] packed spatial bins, 96 KB (dynamic)
   __shared__ int s_cpos[32];
   __shared__ int s_end;
+  constexpr int NMS_THREADS = NT, NMS_WARPS = NT / 32, NMS_REG_CAP = NT * NMS_QPT;
   const bool thr_pos = thr > 0.f;
   const int n = *n_dev, nseg = *nseg_dev;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -293,8 +294,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
           const uint32_t pb = nms_pack_bins(bj);
           const int xl = pb & 31, xh = (pb >> 8) & 31, yl = (pb >> 16) & 31, yh = (pb >> 24) & 31;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int i = warp + h * NMS_WARPS;
+          for (int i = warp; i < 32; i += NMS_WARPS) {
             bool sup = false;
             if (lane > i && vj)
               sup = nms_pair(s_cbox[i], s_carea[i], bj, aj, ((cgen >> i) | (cgen >> lane)) & 1u, thr, thr_pos);
@@ -373,8 +373,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
         const uint32_t pb = nms_pack_bins(bj);
         const int xl = pb & 31, xh = (pb >> 8) & 31, yl = (pb >> 16) & 31, yh = (pb >> 24) & 31;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int i = warp + h * NMS_WARPS;
+        for (int i = warp; i < 32; i += NMS_WARPS) {
           bool sup = false;
           if (lane > i && vj)
             sup = nms_pair(s_cbox[i], s_carea[i], bj, aj, ((cgen >> i) | (cgen >> lane)) & 1u, thr, thr_pos);
@@ -585,12 +584,27 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   int dev = 0, sms = 148;
   YB_CHECK_CUDA(cudaGetDevice(&dev));
   YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int grid = sms * 3;
+  // CTA size: segments are (image, class) groups; with integer class labels of <= 2^class_bits classes the average
+  // segment is total / (batch * classes) boxes long at most -- short segments want many small CTAs
+  // Measured on random-init YOLOv3 heads (class-skewed segments, profiles/r1_nms_cta_size.txt): 128 / 256 / 512 threads
+  // give 0.99 / 0.71 / 0.61 ms at 416 (conf 0.5) and 4.6 / 3.1 / 1.9 ms at 608 (conf 0.01), 1024 threads 0.94 / 2.8 ms.
+  int nt = 512;
+  if (const char* e = getenv("YOLO_B200_NMS_THREADS")) {
+    const int v = atoi(e);
+    if (v == 128 || v == 256 || v == 512 || v == 1024) nt = v;
+  }
+  const size_t nms_smem = size_t(NMS_QPT) * nt * sizeof(uint32_t);
+  int grid = sms * (nt == 1024 ? 1 : (nt == 512 ? 3 : (nt == 256 ? 6 : 12)));
   if (grid > total) grid = total;
-  const size_t nms_smem = size_t(NMS_QPT) * NMS_THREADS * sizeof(uint32_t);
-  YB_CHECK_CUDA(cudaFuncSetAttribute(k_nms_segments, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
-  k_nms_segments<<<grid, NMS_THREADS, nms_smem, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts,
-                                                   nseg, n_valid, iou_thr, w.suppressed, w.keep, class_bits > 0);
+#define YB_NMS_LAUNCH(NTV)                                                                                              \
+  do {                                                                                                                  \
+    YB_CHECK_CUDA(cudaFuncSetAttribute(k_nms_segments<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem)); \
+    k_nms_segments<NTV><<<grid, NTV, nms_smem, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts, nseg, n_valid,    \
+                                                       iou_thr, w.suppressed, w.keep, class_bits > 0);                  \
+  } while (0)
+  if (nt == 128) YB_NMS_LAUNCH(128); else if (nt == 256) YB_NMS_LAUNCH(256); else if (nt == 1024) YB_NMS_LAUNCH(1024);
+  else YB_NMS_LAUNCH(512);
+#undef YB_NMS_LAUNCH
   YB_CHECK_LAUNCH();
 
   // survivors, in the reference's order, + per-image offsets
