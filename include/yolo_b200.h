@@ -104,6 +104,11 @@ typedef struct yolo_conv_desc {
    * Weights: yolo_pack_weights_dgrad_s2.                                                                        */
   int32_t pad_h_hi_plus1;             /* 0: bottom pad = pad; else bottom pad = value - 1           */
   int32_t s2_parity, s2_cin;
+  /* tuning switches of the persistent kernel, 0 = library default (on), 1 = off:
+   * pdl_hint         launch with programmatic stream serialization (the prologue of layer i+1 overlaps the tail
+   *                  of layer i; griddepcontrol.wait orders every global access after the previous launch);
+   * tail_split_hint  cut the tiles of a last round that is at most half full into two half-width tiles.        */
+  int32_t pdl_hint, tail_split_hint;
 } yolo_conv_desc;
 
 /* Size of the opaque, caller-owned plan blob (64-byte aligned storage).       */
@@ -135,6 +140,11 @@ int yolo_conv_fwd_stem(const void* plan_host, const float* x_nchw, uint32_t* sta
 /* tile configuration chosen by plan_init: info8 = block_n, block_k, stages, tiles_n, tiles_m,
  * impl (1|2), CTAs per cluster, launched CTAs */
 int yolo_conv_plan_info(const void* plan_host, int32_t* info8);
+/* DEV TOOL (scripts/conv_trace.py): yolo_conv_fwd with 16 x uint64 %globaltimer stamps per launched CTA written to
+ * trace_dev: [0] entry, [1] prologue done, [2] griddepcontrol.wait returned, [3] first TMA load issued,
+ * [4] first operand stage landed, [5] last MMA committed, [6] first accumulator ready, [7] epilogue drained,
+ * [8] exit, [9] tiles of this CTA (whole + half).  Never used by the product path.                            */
+int yolo_conv_fwd_trace(const void* plan_host, uint32_t* status, unsigned long long* trace_dev, yb_stream_t stream);
 
 /* TEST-ONLY reference: the same math on CUDA cores (direct convolution, one
  * thread per output element).  Never called by the product path.              */

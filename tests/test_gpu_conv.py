@@ -16,7 +16,8 @@ REL = 2.0 ** -7
 
 
 def _run_case(B, H, cin, cout, k, stride, act="leaky_relu", residual=False, upsample=False, fp32=False,
-              a_mode=0, block_n=0, stages=0, in_pitch=None, out_pitch=None, seed=0, also_simt=True, impl=0, pair=0):
+              a_mode=0, block_n=0, stages=0, in_pitch=None, out_pitch=None, seed=0, also_simt=True, impl=0, pair=0,
+              pdl=0, split=0, launches=1):
     from yolo_for_turbines_b200._lib import ACT_CODES, ConvDesc, lib, ptr, stream_ptr
     from yolo_for_turbines_b200.engine import make_conv_plan
 
@@ -64,11 +65,13 @@ def _run_case(B, H, cin, cout, k, stride, act="leaky_relu", residual=False, upsa
     d.upsample2x, d.out_fp32, d.check_nan = int(upsample), int(fp32), 1
     d.a_mode, d.block_n_hint, d.stages_hint = a_mode, block_n, stages
     d.impl_hint, d.cta_pair_hint = impl, pair
+    d.pdl_hint, d.tail_split_hint = pdl, split
 
     outs = {}
     yd = torch.full((B, Hy, Hy, out_pitch), 7.0, dtype=odt, device=dev)
     plan = make_conv_plan(d, ptr(xd), ptr(wd), ptr(sd), ptr(bd), ptr(rd), ptr(yd))
-    lib.yolo_conv_fwd(plan[1], ptr(status), stream_ptr())
+    for _ in range(launches):   # back-to-back launches of one plan: the programmatic-dependent-launch chain
+        lib.yolo_conv_fwd(plan[1], ptr(status), stream_ptr())
     torch.cuda.synchronize()
     outs["tcgen05"] = yd.float().cpu()
     if also_simt:
@@ -148,6 +151,18 @@ def test_conv_darknet_shapes_batch4():
     for cin, cout, k, s, h in shapes:
         _run_case(B=4, H=h, cin=cin, cout=cout, k=k, stride=s, act="none" if cout == 255 else "leaky_relu",
                   fp32=(cout == 255), also_simt=False, seed=cin + cout)
+
+
+def test_tail_split_and_pdl_switches():
+    """Tail splitting (half-width tiles in a last round that is at most half full) and programmatic dependent
+    launch, each on and off, on tile counts with whole rounds plus a remainder: 86 tiles on 74 CTA pairs
+    (74 whole + 12 split), 170 tiles on 148 single CTAs, and a 3x3 layer with a residual."""
+    for pdl, split in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        _run_case(B=64, H=13, cin=128, cout=512, k=1, stride=1, pdl=pdl, split=split, also_simt=False, launches=3)
+        _run_case(B=64, H=13, cin=64, cout=256, k=1, stride=1, pair=1, pdl=pdl, split=split, also_simt=False)
+    _run_case(B=40, H=13, cin=64, cout=512, k=3, stride=1, residual=True, also_simt=False, launches=2)
+    _run_case(B=40, H=13, cin=64, cout=512, k=3, stride=1, residual=True, also_simt=False, split=1)
+    _run_case(B=24, H=26, cin=64, cout=128, k=3, stride=1, act="mish", also_simt=False)   # bn 128 -> 64-wide halves
 
 
 def test_nan_layer_flag():

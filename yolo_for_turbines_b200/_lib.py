@@ -31,7 +31,8 @@ class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "h_in", "w_in", "c_in", "in_pitch", "c_out", "c_out_pad", "out_pitch", "ksize", "stride", "pad",
         "act", "has_residual", "res_pitch", "upsample2x", "out_fp32", "check_nan", "a_mode", "block_n_hint",
-        "stages_hint", "impl_hint", "cta_pair_hint", "ksize_w", "stride_w", "pad_w_hi_plus1", "stem_c", "want_stats", "pad_h_hi_plus1", "s2_parity", "s2_cin")]
+        "stages_hint", "impl_hint", "cta_pair_hint", "ksize_w", "stride_w", "pad_w_hi_plus1", "stem_c", "want_stats", "pad_h_hi_plus1", "s2_parity", "s2_cin",
+        "pdl_hint", "tail_split_hint")]
 
 
 class BnFinalizeDesc(C.Structure):
@@ -54,6 +55,7 @@ SIGNATURES = {
     "yolo_conv_fwd_stats": (_I, [_P, _P, _P, C.POINTER(BnFinalizeDesc), _P]),
     "yolo_conv_fwd_stem": (_I, [_P, _P, _P, _P]),
     "yolo_conv_plan_info": (_I, [_P, C.POINTER(C.c_int32)]),
+    "yolo_conv_fwd_trace": (_I, [_P, _P, _P, _P]),
     "yolo_conv_fwd_simt": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "yolo_pack_weights": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "yolo_pack_stem_weights": (_I, [_P, _I, _I, _I, _P, _P]),

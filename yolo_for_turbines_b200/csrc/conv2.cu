@@ -38,11 +38,12 @@ struct Cfg {
   static constexpr int BOXC = BLOCK_N < 64 ? BLOCK_N : 64;   // channels per epilogue box
   static constexpr int BOX_ROW_BYTES = BOXC * 2;             // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   static constexpr uint32_t WBOX_BYTES = 32 * BOX_ROW_BYTES; // one warp's 32 rows of a box
-  static constexpr int NBOXES = BLOCK_N / BOXC;
   static constexpr uint32_t EPI_BYTES = EPI_WARPS * WSLOTS * WBOX_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) |
                                     (uint32_t((BLOCK_M * NCTA) >> 4) << 24);
+  static constexpr uint32_t IDESC_HALF = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 4) << 17) |
+                                         (uint32_t((BLOCK_M * NCTA) >> 4) << 24);   // tail-split tiles: N = BLOCK_N / 2
   __host__ __device__ static constexpr int NUM_BARS(int stages) { return 2 * stages + 4 + EPI_WARPS * WSLOTS; }
   static int smem_bytes(int stages, int extra) { return stages * STAGE_BYTES + EPI_BYTES + NUM_BARS(stages) * 8 + 16 + 1024 + extra; }
 };
@@ -84,6 +85,28 @@ __device__ __forceinline__ void bn_act32(const uint32_t (&v)[32], float (&o)[32]
   }
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// virtual tile v -> (M tile, first column, width); see ConvKParams2::t_full
+template <int BLOCK_N>
+__device__ __forceinline__ void decode_tile(const ConvKParams2& p, int v, int& mt, int& n0, int& nw) {
+  int t = v, half = 0;
+  nw = BLOCK_N;
+  if (v >= p.t_full) {
+    const int u = v - p.t_full;
+    t = p.t_full + (u >> 1);
+    half = u & 1;
+    nw = BLOCK_N >> 1;
+  }
+  const int nt = t % p.tiles_n;
+  mt = t / p.tiles_n;
+  n0 = nt * BLOCK_N + half * nw;
+}
+
 constexpr int STEM_GATHER_WARPS = 4;  // STEM mode: warps 10..13 build the A tile from the fp32 NCHW image
 
 // STEM = true: the network's first conv (Cin = 3, 3x3/s1/p1) without the patch-matrix round trip through HBM.
@@ -108,6 +131,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   const uint32_t stats_base = tmem_slot + 16;  // training forward: [2 * c_out_pad] fp32 channel sums of this CTA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.trace && threadIdx.x == 0) p.trace[16 * size_t(blockIdx.x)] = gtimer();
   if (p.stats != nullptr) {
     for (int i = threadIdx.x; i < 2 * p.c_out_pad; i += blockDim.x)
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(stats_base + 4u * i), "r"(0u) : "memory");
@@ -140,16 +164,31 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  unsigned long long* const trace = p.trace ? p.trace + 16 * size_t(blockIdx.x) : nullptr;
+  if (trace && threadIdx.x == 0) trace[1] = gtimer();
+  if (p.pdl) {
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped
+    // the tail of the previous launch in the stream.  The next launch may start its own prologue now; every access
+    // to global memory below is ordered after the COMPLETION of the previous launch (and, through its own wait, of
+    // all earlier ones), so reads of its output and the reuse of older buffers are both safe.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+  if (trace && threadIdx.x == 0) trace[2] = gtimer();
 
   if (warp == 0) {
     // ===== TMA producer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
-    int s = 0;
+    int s = 0, ntiles = 0;
     uint32_t ph = 0;
-    for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
-      const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+    for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++ntiles) {
+      int mt, n0, nw;
+      decode_tile<BLOCK_N>(p, v, mt, n0, nw);
       int m0 = (mt * NCTA + (int)rank) * BLOCK_M;
       if (m0 >= p.M) m0 = 0;  // peer CTA of a ragged last pair: load valid rows, results are discarded
-      const int nb0 = nt * BLOCK_N + (int)rank * C::B_ROWS;
+      const bool whole = nw == BLOCK_N;
+      const int nb0 = n0 + (int)rank * (whole ? C::B_ROWS : C::B_ROWS / 2);   // this CTA's rows of the weight tile
+      const uint32_t b_bytes = whole ? C::B_BYTES : C::B_BYTES / 2;
+      const bool b_second = whole && p.b_half;  // half-height weight boxes: a whole tile takes two
       int cw = 0, ch = 0, img = 0;
       if (p.a_im2col) {
         const int hw = p.h_out * p.w_out;
@@ -163,7 +202,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         if (elect_one()) {
-          if (leader) mbar_expect_tx(full_bar(s), (STEM ? C::B_BYTES : C::STAGE_BYTES) * NCTA);
+          if (leader) mbar_expect_tx(full_bar(s), (STEM ? C::B_BYTES : C::A_BYTES + b_bytes) * NCTA);
           const uint32_t sa = smem_base + s * C::STAGE_BYTES, sb = sa + C::A_BYTES;
           if constexpr (STEM) {
             tma_load_2d(&p.tmB, full_bar(s), sb, kb * KC, nb0);
@@ -171,17 +210,21 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             if (p.a_im2col) tma_load_im2col_4d(&p.tmA, full_bar(s), sa, cc * KC, cw, ch, img, (uint16_t)tq, (uint16_t)tr);
             else tma_load_2d(&p.tmA, full_bar(s), sa, cc * KC, m0);
             tma_load_2d(&p.tmB, full_bar(s), sb, kb * KC, nb0);
+            if (b_second) tma_load_2d(&p.tmB, full_bar(s), sb + C::B_BYTES / 2, kb * KC, nb0 + C::B_ROWS / 2);
           } else {
             if (p.a_im2col) tma_load_im2col_4d_2sm(&p.tmA, full_bar(s), sa, cc * KC, cw, ch, img, (uint16_t)tq, (uint16_t)tr);
             else tma_load_2d_2sm(&p.tmA, full_bar(s), sa, cc * KC, m0);
             tma_load_2d_2sm(&p.tmB, full_bar(s), sb, kb * KC, nb0);
+            if (b_second) tma_load_2d_2sm(&p.tmB, full_bar(s), sb + C::B_BYTES / 2, kb * KC, nb0 + C::B_ROWS / 2);
           }
+          if (trace && ntiles == 0 && kb == 0) trace[3] = gtimer();
         }
         __syncwarp();
         if (++cc == p.cchunks) { cc = 0; if (++tq == p.ksize_w) { tq = 0; ++tr; } }
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
+    if (trace && lane == 0) trace[9] = (unsigned long long)ntiles;
   } else if (warp == 1) {
     if (leader) {
       // ===== MMA issuer: warp-uniform loop, tcgen05.mma / commit from one elected lane =====
@@ -189,19 +232,21 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       uint32_t ph = 0, tl = 0;
       const uint64_t adesc0 = make_kmajor_desc<C::ROW_BYTES>(smem_base);
       const uint64_t bdesc0 = make_kmajor_desc<C::ROW_BYTES>(smem_base + C::A_BYTES);
-      for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++tl) {
+      for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
         const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+        const uint32_t idesc = v < p.t_full ? C::IDESC : C::IDESC_HALF;
         mbar_wait(tempty_bar(acc), aph ^ 1u);  // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
+          if (trace && tl == 0 && kb == 0 && lane == 0) trace[4] = gtimer();
           if (elect_one()) {
             const uint64_t soff = uint64_t((uint32_t(s) * C::STAGE_BYTES) >> 4);  // stage offset in descriptor units
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k)
-              umma_bf16_n<NCTA>(d_tmem, adesc0 + soff + uint64_t(2 * k), bdesc0 + soff + uint64_t(2 * k), C::IDESC,
+              umma_bf16_n<NCTA>(d_tmem, adesc0 + soff + uint64_t(2 * k), bdesc0 + soff + uint64_t(2 * k), idesc,
                                 (kb | k) != 0 ? 1u : 0u);
             umma_commit_n<NCTA>(empty_bar(s));
             if (kb == p.num_kb - 1) umma_commit_n<NCTA>(tfull_bar(acc));
@@ -210,6 +255,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
       }
+      if (trace && lane == 0) trace[5] = gtimer();
     }
   } else if (STEM && warp >= 2 + EPI_WARPS) {
     // ===== STEM gather warps: one thread per A row = one output pixel pair =====
@@ -287,12 +333,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     const uint32_t swz = (C::BOX_ROW_BYTES == 128) ? (lane & 7) : ((lane >> 1) & 3);
     uint32_t tl = 0, wbox = 0;
     bool saw_nan = false;
-    for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++tl) {
+    for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
       if ((tl & 1u) != acc) continue;
       const uint32_t aph = (tl >> 1) & 1u;
-      const int nt = t % p.tiles_n, mt = t / p.tiles_n;
+      int mt, n0, nw;
+      decode_tile<BLOCK_N>(p, v, mt, n0, nw);
+      const int nboxes = nw / C::BOXC;
       const int m0w = (mt * NCTA + (int)rank) * BLOCK_M + quad * 32;
-      const int n0 = nt * BLOCK_N;
       const int m = m0w + lane;
       const bool valid = m < p.M;
       const bool wvalid = m0w < p.M;
@@ -319,7 +366,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       const bool staged = !direct && wvalid;
       bool acc_ready = false;
 #pragma unroll 1
-      for (int b = 0; b < C::NBOXES; ++b) {
+      for (int b = 0; b < nboxes; ++b) {
         const uint32_t slot = wbox % WSLOTS, sph = (wbox / WSLOTS) & 1u;
         const uint32_t slot_addr = wslot_base + slot * C::WBOX_BYTES;
         const int nb = n0 + b * C::BOXC;
@@ -338,13 +385,14 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           mbar_wait(tfull_bar(acc), aph);
           tc_fence_after();
           acc_ready = true;
+          if (trace && tl == 0 && ew == 0 && lane == 0) trace[6] = gtimer();
         }
         const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + b * C::BOXC;
         uint32_t v0[32], v1[32];
         tmem_ld32_nowait(taddr, v0);
         if constexpr (C::BOXC == 64) tmem_ld32_nowait(taddr + 32, v1);
         tmem_wait_ld();
-        if (b == C::NBOXES - 1) {
+        if (b == nboxes - 1) {
           // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -477,11 +525,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     }
     if (saw_nan) atomicOr(p.status, YB_STATUS_NAN_LAYER);
     if (lane == 0) bulk_wait_group_all();
+    if (trace && lane == 0) atomicMax(trace + 7, gtimer());
   }
 
   tc_fence_before();
   if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) tmem_dealloc_n<NCTA>(tmem_base, C::TMEM_COLS);
+  if (trace && threadIdx.x == 0) trace[8] = gtimer();
   if (p.stats != nullptr) {  // one double atomic per channel statistic per CTA
     for (int i = threadIdx.x; i < 2 * p.c_out_pad; i += blockDim.x) {
       float v;
@@ -518,13 +568,15 @@ int launch2(const ConvPlan* pl, const ConvKParams2& kp, cudaStream_t stream) {
   cfg.blockDim = dim3(CONV2_THREADS + (STEM ? STEM_GATHER_WARPS * 32 : 0));
   cfg.dynamicSmemBytes = (size_t)pl->smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NCTA;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = kp.pdl ? 2 : 1;
   YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
   return YB_OK;
 }
@@ -569,21 +621,38 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   const int smem = smem_bytes_v2(bn, kc, ncta, stages, extra);
   YB_REQUIRE(smem <= 227 * 1024, "conv v2: %d stages do not fit shared memory (block_n %d)", stages, bn);
 
+  int dev = 0, sms = 148;
+  YB_CHECK_CUDA(cudaGetDevice(&dev));
+  YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int max_clusters = sms / ncta;
+  const int direct = d->upsample2x || d->s2_parity;
+  // Tail splitting (ConvKParams2::t_full): the last round of a persistent launch holds num_tiles % clusters tiles.
+  // When at most half of the CTA pairs would get one, every such tile is cut into two half-width tiles: the round
+  // then costs about half a tile time (13x13 3x3 layers: 2.5 instead of 3 rounds).
+  int t_full = tiles_m * tiles_n, num_vtiles = t_full, b_half = 0;
+  if (d->tail_split_hint != 1 && bn >= 128 && !d->out_fp32 && !direct && !d->want_stats && !stem) {
+    const int rem = t_full % max_clusters;
+    if (rem > 0 && 2 * rem <= max_clusters) {
+      t_full -= rem;
+      num_vtiles = t_full + 2 * rem;
+      b_half = 1;
+    }
+  }
+
   ConvKParams2& kp = pl->kp2;
   kp.tmA = pl->kp.tmA;  // same A geometry as v1 (128-row boxes of KC channels); unused by the stem
-  // weight tile: BLOCK_N / NCTA rows per CTA
+  // weight tile: BLOCK_N / NCTA rows per CTA (two half-height boxes when the tail is split)
   {
     const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     cuuint64_t dims[2] = {(cuuint64_t)taps * d->c_in, (cuuint64_t)d->c_out_pad};
     cuuint64_t strides[1] = {(cuuint64_t)taps * d->c_in * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(bn / ncta)};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)(bn / ncta / (b_half ? 2 : 1))};
     cuuint32_t estr[2] = {1, 1};
     CUresult cr = encTiled(&kp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(pl->w), dims, strides, box,
                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: tensor map B encode failed (%d)", (int)cr);
   }
-  const int direct = d->upsample2x || d->s2_parity;
   const int boxc = bn < 64 ? bn : 64;
   const CUtensorMapSwizzle bswz = boxc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   if (d->out_fp32 && !direct) {   // scale heads: fp32 boxes of 32 columns x 32 rows
@@ -628,6 +697,9 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   kp.stem_x = nullptr; kp.stem_h = d->h_in; kp.stem_w = d->w_in * 2;
   kp.stats = nullptr; kp.c_out_pad = d->c_out_pad; kp.fin_counter = nullptr;
   kp.s2_parity = d->s2_parity; kp.s2_cin = d->s2_cin;
+  kp.t_full = t_full; kp.num_vtiles = num_vtiles; kp.b_half = b_half;
+  kp.pdl = d->pdl_hint == 1 ? 0 : 1;
+  kp.trace = nullptr;
   pl->stem_direct = stem ? 1 : 0;
   if (stem) {
     YB_REQUIRE(bn == 64 && kc == 64 && d->stem_c == 3 && d->ksize == 1 && tiles_n == 1 && !d->has_residual && !direct,
@@ -636,11 +708,8 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
     kp.stages = stages;
   }
 
-  int dev = 0, sms = 148;
-  YB_CHECK_CUDA(cudaGetDevice(&dev));
-  YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int clusters = sms / ncta;
-  if (clusters > kp.num_tiles) clusters = kp.num_tiles;
+  int clusters = max_clusters;
+  if (clusters > kp.num_vtiles) clusters = kp.num_vtiles;
   pl->grid2 = clusters * ncta;
   pl->ncta = ncta;
   pl->block_n = bn;
@@ -660,13 +729,14 @@ int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status,
 }
 
 int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats, const BnFinalize* fin,
-                 unsigned int* fin_counter) {
+                 unsigned int* fin_counter, unsigned long long* trace) {
   YB_REQUIRE(!pl->stem_direct, "conv fwd: stem plans are launched with yolo_conv_fwd_stem");
   YB_REQUIRE(!stats || (pl->d.want_stats && !(pl->d.upsample2x || pl->d.out_fp32)),
              "conv fwd: statistics need a plan built with want_stats and the staged bf16 output path");
   ConvKParams2 kp = pl->kp2;
   kp.status = status;
   kp.stats = stats;
+  kp.trace = trace;
   if (stats && fin && fin_counter) { kp.fin = *fin; kp.fin_counter = fin_counter; }
 #define YB_L2(BN, KC)                                                        \
   if (pl->block_n == BN && pl->kc == KC)                                     \

@@ -53,6 +53,13 @@ struct ConvKParams2 {
   BnFinalize fin;       // training forward: finalize by the CTA that finishes last (fin_counter != nullptr)
   unsigned int* fin_counter;
   double* stats;        // training forward: per-channel [sum, sum of squares] of the stored bf16 output (set per launch)
+  // Tail splitting: virtual tiles [0, t_full) are whole (128*NCTA x BLOCK_N) tiles; every later pair of virtual
+  // tiles is one tile of the last, partially filled round cut into two BLOCK_N/2-wide halves, so that the round
+  // costs half a tile time when at most half of the CTA pairs would have had work (b_half: the weight tensor map
+  // then holds half-height boxes and a whole tile issues two of them).
+  int t_full, num_vtiles, b_half;
+  int pdl;              // launched with programmatic stream serialization: griddepcontrol.* brackets the prologue
+  unsigned long long* trace;  // dev tool (yolo_conv_fwd_trace): 16 globaltimer stamps per CTA, nullptr otherwise
 };
 
 struct ConvPlan {
@@ -78,5 +85,6 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
 int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out, int im2col, PFN_encodeTiled encTiled,
                      const void* residual, void* y);
 int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats = nullptr,
-                 const BnFinalize* fin = nullptr, unsigned int* fin_counter = nullptr);
+                 const BnFinalize* fin = nullptr, unsigned int* fin_counter = nullptr,
+                 unsigned long long* trace = nullptr);
 int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status, cudaStream_t stream);
