@@ -1,8 +1,10 @@
-"""Imports the UNMODIFIED reference (code/model.py, utils.py, loss.py, config.py) in THIS container.
+"""Imports the UNMODIFIED reference (code/model.py, utils.py, loss.py, config.py).
 
-Test infrastructure only.  /root/reference does not exist on the GPU box, so nothing that runs
-there may call this; it is used by oracle/gen_golden.py (fixture generation) and by the
-container-only differential tests (skipped when the reference checkout is absent).
+Test infrastructure only.  Search order: baseline/_ref/code -- the offline install made by
+scripts/install_reference.sh (git-ignored; travels to the GPU box with the snapshot) -- then /root/reference/code (this
+container only).  Used by oracle/gen_golden*.py (fixture generation), by the container-only differential tests
+(skipped when no copy is found) and by `bench.py --impl reference` / its cpu_baseline leg.  The product path never
+imports this module.
 
 The reference imports matplotlib and albumentations at module scope (utils.py:1-4,13-15,
 model.py:4, config.py:1-2); neither is installed and neither is used on the hot path, so inert
@@ -13,7 +15,10 @@ import os
 import sys
 import types
 
-REF_CODE_DIRS = ["/root/reference/code"]
+import torch  # noqa: F401  (before the stubs go in: torch's own import machinery inspects sys.modules)
+
+REF_CODE_DIRS = [os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "code"),
+                 "/root/reference/code"]
 
 
 class _Inert:
@@ -29,7 +34,13 @@ class _Inert:
 
 def _stub(name):
     m = types.ModuleType(name)
-    m.__getattr__ = lambda attr: _Inert  # any attribute -> inert callable/class
+
+    def _attr(attr):  # any public attribute -> inert callable/class; dunders stay missing (inspect looks at __file__)
+        if attr.startswith("__"):
+            raise AttributeError(attr)
+        return _Inert
+
+    m.__getattr__ = _attr
     sys.modules.setdefault(name, m)
     return sys.modules[name]
 
@@ -42,7 +53,7 @@ def load():
     """Returns (model, utils, loss, config) modules of the reference."""
     code_dir = next((d for d in REF_CODE_DIRS if os.path.isfile(os.path.join(d, "utils.py"))), None)
     if code_dir is None:
-        raise RuntimeError("reference checkout not found (expected /root/reference/code)")
+        raise RuntimeError("reference not found (looked in baseline/_ref/code and /root/reference/code)")
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "albumentations",
                  "albumentations.pytorch"):
         try:

@@ -46,7 +46,10 @@ for i, op in enumerate(ops):
     lead = t[t[:, 5] > 0]
     med = lambda v: float(v.double().median()) / 1e3  # noqa: E731
     span = (int(t[:, 8].max()) - int(t[:, 0].min())) / 1e3
+    e = lead[lead[:, 14] > 0]
+    epi = (f" | epi box0: tmem {med(e[:, 10] - e[:, 6]):5.2f} res {med(e[:, 11] - e[:, 10]):5.2f} math+st {med(e[:, 12] - e[:, 11]):5.2f} "
+           f"store {med(e[:, 13] - e[:, 12]):5.2f} tile {med(e[:, 14] - e[:, 6]):5.2f}") if e.shape[0] else ""
     print(f"{op.name:30s} {t.shape[0]:4d} {int(t[:, 9].max()):5d} | {med(t[:, 1] - t[:, 0]):6.2f} {med(t[:, 2] - t[:, 1]):6.2f} "
           f"{med(lead[:, 4] - lead[:, 3]):6.2f} {med(lead[:, 5] - lead[:, 4]):7.2f} {med(lead[:, 7] - lead[:, 5]):6.2f} "
           f"{med(t[:, 8] - t[:, 7]):6.2f} | {span:7.2f}  entry spread {(int(t[:, 0].max()) - int(t[:, 0].min())) / 1e3:6.2f} "
-          f"exit spread {(int(t[:, 8].max()) - int(t[:, 8].min())) / 1e3:6.2f}")
+          f"exit spread {(int(t[:, 8].max()) - int(t[:, 8].min())) / 1e3:6.2f}{epi}")

@@ -333,6 +333,35 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     const uint32_t swz = (C::BOX_ROW_BYTES == 128) ? (lane & 7) : ((lane >> 1) & 3);
     uint32_t tl = 0, wbox = 0;
     bool saw_nan = false;
+    // Residual prefetch cursor.  The residual box of output box k lands in slot k % WSLOTS and is overwritten in
+    // place by the output box, so its load may be issued as soon as the TMA store of box k - WSLOTS has read the
+    // slot.  The cursor runs up to one box ahead of the box being computed -- across tile boundaries, where the
+    // loads of the next tile's first two boxes fly while this group waits for its accumulator -- instead of
+    // starting every load right before its data is needed (one exposed L2 round trip per box).
+    const bool res_staged = p.has_residual && !direct;
+    int pv = cluster_id + int(acc) * num_clusters, pb = 0;   // (virtual tile, box) the cursor points at
+    uint32_t pk = 0;                                         // boxes whose residual load has been issued
+    auto res_cursor_settle = [&]() {   // skip tiles in which this warp has no valid rows (they use no slots)
+      while (pv < p.num_vtiles) {
+        int cmt, cn0, cnw;
+        decode_tile<BLOCK_N>(p, pv, cmt, cn0, cnw);
+        if ((cmt * NCTA + (int)rank) * BLOCK_M + quad * 32 < p.M) break;
+        pv += 2 * num_clusters;
+      }
+    };
+    auto res_issue_next = [&]() {      // warp-uniform; the caller guarantees the slot is free
+      int cmt, cn0, cnw;
+      decode_tile<BLOCK_N>(p, pv, cmt, cn0, cnw);
+      const int cm0w = (cmt * NCTA + (int)rank) * BLOCK_M + quad * 32;
+      const uint32_t cslot = pk % WSLOTS;
+      if (lane == 0) {
+        mbar_expect_tx(res_bar(ew, cslot), C::WBOX_BYTES);
+        tma_load_2d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, cn0 + pb * C::BOXC, cm0w);
+      }
+      ++pk;
+      if (++pb == cnw / C::BOXC) { pb = 0; pv += 2 * num_clusters; res_cursor_settle(); }
+    };
+    if (res_staged) res_cursor_settle();
     for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
       if ((tl & 1u) != acc) continue;
       const uint32_t aph = (tl >> 1) & 1u;
@@ -343,6 +372,16 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       const int m = m0w + lane;
       const bool valid = m < p.M;
       const bool wvalid = m0w < p.M;
+      const bool tr0 = trace != nullptr && ew == 0 && tl == 0 && lane == 0;
+      // warm the L1 lines of this tile's scale / bias vectors while the accumulator is still being produced
+      if (lane < nw / 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.scale + n0 + 32 * lane));
+      else if (lane >= 16 && lane - 16 < nw / 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + n0 + 32 * (lane - 16)));
+      if (res_staged && wvalid) {
+        // tile boundary: every earlier store of this warp was committed long ago -- take both slots
+        if (lane == 0) bulk_wait_group_read<0>();
+        __syncwarp();
+        while (pk < wbox + WSLOTS && pv < p.num_vtiles) res_issue_next();
+      }
       size_t out_row[4];
       int n_out_rows = 1;
       out_row[0] = size_t(m);
@@ -370,14 +409,10 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         const uint32_t slot = wbox % WSLOTS, sph = (wbox / WSLOTS) & 1u;
         const uint32_t slot_addr = wslot_base + slot * C::WBOX_BYTES;
         const int nb = n0 + b * C::BOXC;
-        if (staged) {
+        if (staged && !res_staged) {
           if (lane == 0) {
             if (f32_staged) bulk_wait_group_read<0>();   // an fp32 box pair uses both slots: all earlier stores have read
             else bulk_wait_group_read<WSLOTS - 1>();  // the TMA store that last used this slot has read it out
-            if (p.has_residual) {
-              mbar_expect_tx(res_bar(ew, slot), C::WBOX_BYTES);
-              tma_load_2d(&p.tmR, res_bar(ew, slot), slot_addr, nb, m0w);
-            }
           }
           __syncwarp();
         }
@@ -400,7 +435,17 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             if constexpr (NCTA == 1) mbar_arrive_local(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc));
           }
         }
-        if (staged && p.has_residual) mbar_wait(res_bar(ew, slot), sph);
+        if (tr0 && b == 0) trace[10] = gtimer();
+        if (staged && res_staged) {
+          // one box ahead: the store of the previous box (committed a TMEM round trip ago) has read its slot
+          if (pk < wbox + WSLOTS && pv < p.num_vtiles) {
+            if (lane == 0) bulk_wait_group_read<0>();
+            __syncwarp();
+            res_issue_next();
+          }
+          mbar_wait(res_bar(ew, slot), sph);
+        }
+        if (tr0 && b == 0) trace[11] = gtimer();
         const uint32_t row_addr = slot_addr + lane * C::BOX_ROW_BYTES;
         auto process_half = [&](const uint32_t (&v)[32], const int h) {
           const int n = nb + h * 32;
@@ -484,6 +529,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         if (staged) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
+          if (tr0 && b == 0) trace[12] = gtimer();
           if (lane == 0) {
             if (f32_staged) {
               tma_store_2d(&p.tmY, wslot_base, nb, m0w);
@@ -520,6 +566,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             }
           }
           ++wbox;
+          if (tr0) trace[b == 0 ? 13 : 14] = gtimer();
         }
       }
     }
