@@ -461,6 +461,31 @@ def read_darknet_weights(path: str, sd: Dict[str, torch.Tensor]) -> Dict[str, in
 
 
 # --- end-to-end detection as the reference's callers do it (utils.py:296-321, demo.py:30-55) ----
+def get_eval_boxes(batches, anchors, iou_threshold, obj_threshold, box_format="center"):
+    """utils.py:276-332 restated on precomputed head tensors: `batches` yields (heads[3], targets[3]) per batch, i.e.
+    what `model(x)` and the loader hand the reference.  Per image: the three scales' decoded boxes concatenated in
+    scale order (:300-309), NMS (:317-321), image index prepended (:323-324); true boxes are the rows of the LAST
+    scale's targets (anchors of the last scale, :313-315) whose objectness exceeds obj_threshold (:326-328)."""
+    data_idx, preds, trues = 0, [], []
+    for heads, targets in batches:
+        bsz = heads[0].shape[0]
+        per_image = [[] for _ in range(bsz)]
+        for i, o in enumerate(heads):
+            s = o.shape[2]
+            a = torch.tensor([*anchors[i]]) * s
+            for b, rows in enumerate(cells_to_boxes(o.clone(), a, s, is_pred=True)):
+                per_image[b] += rows
+        true_rows = cells_to_boxes(targets[2].clone(), a, s, is_pred=False)
+        for b in range(bsz):
+            for row in non_max_suppression(per_image[b], iou_threshold, obj_threshold, box_format):
+                preds.append([data_idx] + row)
+            for row in true_rows[b]:
+                if row[4] > obj_threshold:
+                    trues.append([data_idx] + row)
+            data_idx += 1
+    return preds, trues
+
+
 def detect(sd, x, anchors=ANCHORS, iou_threshold=NMS_IOU_THRESHOLD, obj_threshold=CONF_THRESHOLD,
            num_classes=80, activation="leaky_relu", box_format="center"):
     with torch.no_grad():

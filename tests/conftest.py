@@ -40,6 +40,7 @@ def gold():
         loader = json.load(open(os.path.join(GOLD, "loader.json")))
         accuracy = np.load(os.path.join(GOLD, "accuracy.npz"))
         loss = np.load(os.path.join(GOLD, "loss.npz"))
+        eval_boxes = np.load(os.path.join(GOLD, "eval_boxes.npz"))
     return G
 
 

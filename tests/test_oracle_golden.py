@@ -138,3 +138,14 @@ def test_yolo_loss_matches_reference(gold):
         out = orc.yolo_loss(p, t, torch.from_numpy(d[name + "/anchors"]))
         assert [float(v) for v in out] == list(d[name + "/loss"]), name
         assert np.array_equal(p.numpy(), d[name + "/pred_after"]) and np.array_equal(t.numpy(), d[name + "/tgt_after"]), name
+
+
+def test_get_eval_boxes_oracle_matches_reference(gold):
+    """oracle.get_eval_boxes vs the lists the UNMODIFIED reference returned (utils.py:276-332, oracle/gen_golden_eval.py)."""
+    e = gold.eval_boxes
+    batches = [([torch.from_numpy(e[f"b{bi}_head{si}"]) for si in range(3)], [torch.from_numpy(e[f"b{bi}_tgt{si}"]) for si in range(3)])
+               for bi in range(2)]
+    preds, trues = orc.get_eval_boxes(batches, e["anchors"].tolist(), float(e["iou_thr"]), float(e["obj_thr"]), "center")
+    assert np.array_equal(np.asarray(preds, dtype=np.float64).reshape(-1, 7), e["preds"])
+    assert np.array_equal(np.asarray(trues, dtype=np.float64).reshape(-1, 7), e["trues"])
+    assert e["calls"].tolist() == ["eval", "train"]   # utils.py:295 and the unconditional :331

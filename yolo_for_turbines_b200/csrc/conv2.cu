@@ -25,6 +25,7 @@ using namespace convptx;
 constexpr int CONV2_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 = two epilogue groups
 constexpr int WSLOTS = 2;           // per-warp ring of 32-row output/residual boxes in shared memory
 constexpr int EPI_WARPS = 8;
+constexpr int SCRATCH_BYTES = 256;  // per epilogue warp: scale[32] | bias[32] of the 32 columns being processed
 
 template <int BLOCK_N, int KC, int NCTA>
 struct Cfg {
@@ -45,7 +46,11 @@ struct Cfg {
   static constexpr uint32_t IDESC_HALF = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 4) << 17) |
                                          (uint32_t((BLOCK_M * NCTA) >> 4) << 24);   // tail-split tiles: N = BLOCK_N / 2
   __host__ __device__ static constexpr int NUM_BARS(int stages) { return 2 * stages + 4 + EPI_WARPS * WSLOTS; }
-  static int smem_bytes(int stages, int extra) { return stages * STAGE_BYTES + EPI_BYTES + NUM_BARS(stages) * 8 + 16 + 1024 + extra; }
+  // ring | epilogue slots | barriers | TMEM slot + last-CTA flag (16 B) | per-warp scale/bias scratch | channel sums.
+  // The dynamic segment is 1024-byte aligned (no static shared memory in this kernel; checked at entry).
+  static int smem_bytes(int stages, int extra) {
+    return stages * STAGE_BYTES + EPI_BYTES + NUM_BARS(stages) * 8 + 16 + EPI_WARPS * SCRATCH_BYTES + extra;
+  }
 };
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
@@ -63,14 +68,16 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// scale/bias + activation on 32 accumulator columns.  LeakyReLU(0.1) is branch-free: max(v, 0.1 v).
-__device__ __forceinline__ void bn_act32(const uint32_t (&v)[32], float (&o)[32], const float* __restrict__ scale,
-                                         const float* __restrict__ bias, int n, int act) {
-  const float4* sp = reinterpret_cast<const float4*>(scale + n);
-  const float4* bp = reinterpret_cast<const float4*>(bias + n);
+// scale/bias + activation on 32 accumulator columns.  The per-column factors come from the warp's shared-memory
+// scratch (scale[32] | bias[32], broadcast reads): with ~224 KB of the SM carved out as shared memory there is no L1
+// left, and per-box global loads of scale / bias cost an L2 round trip each (1.5-3.5 us per box under load, measured
+// with yolo_conv_fwd_trace) -- they were the epilogue's critical path.  LeakyReLU(0.1) is branch-free: max(v, 0.1 v).
+__device__ __forceinline__ void bn_act32(const uint32_t (&v)[32], float (&o)[32], uint32_t scratch, int act) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 s4 = __ldg(sp + j), b4 = __ldg(bp + j);
+    float4 s4, b4;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w) : "r"(scratch + 16u * j));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(scratch + 128u + 16u * j));
     o[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), s4.x, b4.x);
     o[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), s4.y, b4.y);
     o[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), s4.z, b4.z);
@@ -117,8 +124,9 @@ template <int BLOCK_N, int KC, int NCTA, bool STEM = false>
 __global__ void __launch_bounds__(CONV2_THREADS + (STEM ? STEM_GATHER_WARPS * 32 : 0), 1)
 k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   using C = Cfg<BLOCK_N, KC, NCTA>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0u) __trap();  // the 128B-swizzled stages need 1024-byte aligned bases
   const int stages = p.stages;
   const uint32_t epi_base = smem_base + stages * C::STAGE_BYTES;
   const uint32_t bar_base = epi_base + C::EPI_BYTES;
@@ -128,7 +136,8 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   auto tempty_bar = [&](int a) { return bar_base + (2 * stages + 2 + a) * 8; };
   auto res_bar = [&](int w, int sl) { return bar_base + (2 * stages + 4 + w * WSLOTS + sl) * 8; };
   const uint32_t tmem_slot = bar_base + C::NUM_BARS(stages) * 8;
-  const uint32_t stats_base = tmem_slot + 16;  // training forward: [2 * c_out_pad] fp32 channel sums of this CTA
+  const uint32_t scratch_base = tmem_slot + 16;
+  const uint32_t stats_base = scratch_base + EPI_WARPS * SCRATCH_BYTES;  // training forward: [2 * c_out_pad] fp32 channel sums of this CTA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.trace && threadIdx.x == 0) p.trace[16 * size_t(blockIdx.x)] = gtimer();
@@ -330,6 +339,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     const bool f32_staged = p.out_fp32 && !p.upsample2x && p.s2_parity == 0;
     const bool direct = p.upsample2x || p.s2_parity != 0;
     const uint32_t wslot_base = epi_base + uint32_t(ew) * WSLOTS * C::WBOX_BYTES;
+    const uint32_t scratch = scratch_base + uint32_t(ew) * SCRATCH_BYTES;
     const uint32_t swz = (C::BOX_ROW_BYTES == 128) ? (lane & 7) : ((lane >> 1) & 3);
     uint32_t tl = 0, wbox = 0;
     bool saw_nan = false;
@@ -373,9 +383,15 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       const bool valid = m < p.M;
       const bool wvalid = m0w < p.M;
       const bool tr0 = trace != nullptr && ew == 0 && tl == 0 && lane == 0;
-      // warm the L1 lines of this tile's scale / bias vectors while the accumulator is still being produced
-      if (lane < nw / 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.scale + n0 + 32 * lane));
-      else if (lane >= 16 && lane - 16 < nw / 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + n0 + 32 * (lane - 16)));
+      // this tile's per-column scale / bias, fetched while the accumulator is still being produced: lane l holds
+      // columns n0 + 32 i + l; chunk 0 is handed to the scratch per 32-column step and the registers rotate
+      float r_sc[BLOCK_N / 32], r_bi[BLOCK_N / 32];
+#pragma unroll
+      for (int i = 0; i < BLOCK_N / 32; ++i) {
+        const bool in = 32 * i < nw;
+        r_sc[i] = in ? __ldg(p.scale + n0 + 32 * i + lane) : 0.f;
+        r_bi[i] = in ? __ldg(p.bias + n0 + 32 * i + lane) : 0.f;
+      }
       if (res_staged && wvalid) {
         // tile boundary: every earlier store of this warp was committed long ago -- take both slots
         if (lane == 0) bulk_wait_group_read<0>();
@@ -450,7 +466,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         auto process_half = [&](const uint32_t (&v)[32], const int h) {
           const int n = nb + h * 32;
           float o[32];
-          bn_act32(v, o, p.scale, p.bias, n, p.act);
+          __syncwarp();  // the previous step's broadcast reads are done
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + 4u * lane), "f"(r_sc[0]) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + 128u + 4u * lane), "f"(r_bi[0]) : "memory");
+#pragma unroll
+          for (int i = 0; i + 1 < BLOCK_N / 32; ++i) { r_sc[i] = r_sc[i + 1]; r_bi[i] = r_bi[i + 1]; }
+          __syncwarp();
+          bn_act32(v, o, scratch, p.act);
           size_t drow = size_t(m);   // direct-path addressing: (row, column) of the residual / output element
           int dcol = n;
           if (p.s2_parity) {
@@ -588,15 +610,17 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     if (p.fin_counter != nullptr) {
       // the CTA that takes the last ticket sees every CTA's sums: it turns them into the layer's BatchNorm
       // mean / rstd / scale / bias (and running statistics) -- no separate finalize launch on the critical path
-      __shared__ bool is_last;
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) {
         const unsigned int ticket = atomicAdd(p.fin_counter, 1u);
-        is_last = ticket == gridDim.x - 1;
-        if (is_last) *p.fin_counter = 0u;
+        const uint32_t last = ticket == gridDim.x - 1 ? 1u : 0u;
+        if (last) *p.fin_counter = 0u;
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(tmem_slot + 8), "r"(last) : "memory");
       }
       __syncthreads();
+      uint32_t is_last;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(is_last) : "r"(tmem_slot + 8));
       if (is_last) {
         __threadfence();
         for (int c = threadIdx.x; c < p.c_out_pad; c += blockDim.x)

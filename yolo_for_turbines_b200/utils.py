@@ -389,23 +389,49 @@ def detect(model, x, anchors=None, iou_threshold=config.NMS_IOU_THRESHOLD, obj_t
     return out
 
 
+def detect_from_heads(heads, anchors, iou_threshold, obj_threshold, box_format="center") -> NmsResult:
+    """decode x3 + batched NMS on head tensors produced by ANY model: (B,3,S,S,5+nc) per scale, CUDA, any strides.
+    The three scales are concatenated per image in the caller's order, as utils.py:300-309 does."""
+    heads = [h if h.dtype == torch.float32 else h.float() for h in heads]
+    dev, B = heads[0].device, heads[0].shape[0]
+    n = sum(3 * h.shape[2] * h.shape[2] for h in heads)
+    cand = torch.empty(B, n, 6, dtype=torch.float32, device=dev)
+    off = 0
+    for i, h in enumerate(heads):
+        s = h.shape[2]
+        decode_boxes(h, _scaled_anchors(anchors, i, s), s, True, out=cand, out_offset=off)
+        off += 3 * s * s
+    img_off = (torch.arange(B + 1, dtype=torch.int32, device=dev) * n).contiguous()
+    return batched_nms(cand.view(-1, 6), img_off, iou_threshold, obj_threshold, box_format)
+
+
 def get_eval_boxes(loader, model, iou_threshold, anchors, obj_threshold, box_format="center", device=None):
     """utils.py:276-332 on the fused device pipeline: returns (all_box_predictions, all_true_boxes)
-    as lists of [image_idx, cx, cy, w, h, obj, cls], image indices counted across batches."""
+    as lists of [image_idx, cx, cy, w, h, obj, cls], image indices counted across batches.
+    Like the reference it calls model.eval() first (:295) and model.train() at the end UNCONDITIONALLY (:331).
+    A model of this package runs through the planned Detector (no head tensor leaves the device pipeline); any other
+    callable returning the three head tensors is evaluated with the same decode + NMS kernels on its outputs."""
     device = _device(device)
-    was_training = model.training
     model.eval()
-    det = Detector(model, anchors, iou_threshold, obj_threshold, box_format)
+    native = hasattr(model, "_prepare")
+    det = Detector(model, anchors, iou_threshold, obj_threshold, box_format) if native else None
     preds, trues, data_idx = [], [], 0
     for x, targets in loader:
         x = x.to(device)
-        res, plan = det(x)
+        plan = None
+        if native:
+            res, plan = det(x)
+        else:
+            with torch.no_grad():
+                heads = [h.to(device) for h in model(x)]
+            res = detect_from_heads(heads, anchors, iou_threshold, obj_threshold, box_format)
         t2 = targets[2].to(device=device, dtype=torch.float32)
         s = t2.shape[2]
         anc = _scaled_anchors(anchors, 2, s)
         true_rows = decode_boxes(t2, anc, s, is_pred=False)  # utils.py:313-315
         kept = res.kept_rows()
-        plan.check_status()
+        if plan is not None:
+            plan.check_status()
         for b in range(x.shape[0]):
             for row in kept[b].tolist():
                 preds.append([data_idx] + row)
@@ -413,8 +439,7 @@ def get_eval_boxes(loader, model, iou_threshold, anchors, obj_threshold, box_for
             for row in tb[(tb[:, 4].double() > obj_threshold)].tolist():  # utils.py:326-328
                 trues.append([data_idx] + row)
             data_idx += 1
-    if was_training:
-        model.train()
+    model.train()
     return preds, trues
 
 
@@ -438,16 +463,23 @@ def accuracy_counts(outs, targets, object_threshold) -> torch.Tensor:
 
 
 def check_model_accuracy(model, loader, object_threshold):
-    """utils.py:334-381: class / no-object / object accuracy over a loader; same prints, same return order."""
-    was_training = model.training
+    """utils.py:334-381: class / no-object / object accuracy over a loader; same prints, same return order, and the
+    same mode changes: model.eval() first (:344), model.train() at the end unconditionally (:380)."""
     model.eval()
-    dev = next(model.parameters()).device
+    native = hasattr(model, "forward_async")
+    params = list(model.parameters()) if hasattr(model, "parameters") else []
+    dev = params[0].device if params and params[0].is_cuda else _device()
     total = torch.zeros(6, dtype=torch.int64, device=dev)
     for x, target in loader:
         x = x.to(dev)
-        plan, heads = model.forward_async(x)
+        if native:
+            plan, heads = model.forward_async(x)
+        else:
+            with torch.no_grad():
+                plan, heads = None, [h.to(dev) for h in model(x)]
         total += accuracy_counts(heads, target, object_threshold)
-        plan.check_status()
+        if plan is not None:
+            plan.check_status()
     c = total.to(torch.float32).cpu()
     class_accuracy = c[0] / (c[1] + 1e-16)
     noobj_accuracy = c[4] / (c[5] + 1e-16)
@@ -455,8 +487,7 @@ def check_model_accuracy(model, loader, object_threshold):
     print(f"Class accuracy is: {(class_accuracy)*100:2f}%")
     print(f"No obj accuracy is: {(noobj_accuracy)*100:2f}%")
     print(f"Obj accuracy is: {(obj_accuracy)*100:2f}%")
-    if was_training:
-        model.train()
+    model.train()
     return class_accuracy, noobj_accuracy, obj_accuracy
 
 
