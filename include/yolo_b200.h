@@ -140,11 +140,12 @@ int yolo_conv_fwd_stem(const void* plan_host, const float* x_nchw, uint32_t* sta
 /* tile configuration chosen by plan_init: info8 = block_n, block_k, stages, tiles_n, tiles_m,
  * impl (1|2), CTAs per cluster, launched CTAs */
 int yolo_conv_plan_info(const void* plan_host, int32_t* info8);
-/* DEV TOOL (scripts/conv_trace.py): yolo_conv_fwd with 16 x uint64 %globaltimer stamps per launched CTA written to
+/* DEV TOOL (scripts/conv_trace.py): yolo_conv_fwd with 32 x uint64 %globaltimer stamps / counters per launched CTA written to
  * trace_dev: [0] entry, [1] prologue done, [2] griddepcontrol.wait returned, [3] first TMA load issued,
  * [4] first operand stage landed, [5] last MMA committed, [6] first accumulator ready, [7] epilogue drained,
- * [8] exit, [9] tiles of this CTA (whole + half).  Never used by the product path.                            */
-int yolo_conv_fwd_trace(const void* plan_host, uint32_t* status, unsigned long long* trace_dev, yb_stream_t stream);
+ * [8] exit, [9] tiles of this CTA (whole + half), [10..14], [19..22] epilogue box `box` of the first tile, [16..18] ns the MMA warp
+ * waited for operands / for a free accumulator and the producer for a free ring stage.  Never used by the product path.                            */
+int yolo_conv_fwd_trace(const void* plan_host, uint32_t* status, unsigned long long* trace_dev, int box, yb_stream_t stream);
 
 /* TEST-ONLY reference: the same math on CUDA cores (direct convolution, one
  * thread per output element).  Never called by the product path.              */

@@ -182,3 +182,79 @@ def test_detector_lanes_give_identical_results():
             got = r.kept_rows()
             assert all(torch.equal(a, b) for a, b in zip(got, ref[j])), (rounds, j)
     multi.join()
+
+
+def test_forward_608_matches_oracle():
+    """BASELINE configs[2] geometry (19 / 38 / 76 grids: different tile tails and tail splits than 416)."""
+    m, sd = _model(80, "leaky_relu", 5)
+    x = torch.rand(1, 3, 608, 608, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        refs = orc.forward(sd, x, 80)
+        outs = m(x.cuda())
+    assert [tuple(o.shape) for o in outs] == [(1, 3, 19, 19, 85), (1, 3, 38, 38, 85), (1, 3, 76, 76, 85)]
+    _compare(outs, refs, "608")
+
+
+def test_config2_608_low_conf_pipeline_and_map(oracle_c):
+    """BASELINE configs[2] end to end: 608^2, conf 0.01 (22 743 candidates per image, nearly all pass), IoU 0.45 ->
+    kept rows bit-exact against the C oracle on the device's decoded boxes; then calc_mAP(num_classes=80) against the
+    oracle on synthetic ground truth (20 boxes per image, seed 7)."""
+    from yolo_for_turbines_b200.utils import Detector, calc_mAP
+
+    m, sd = _model(80, "leaky_relu", 6)
+    B = 2
+    x = torch.rand(B, 3, 608, 608, generator=torch.Generator().manual_seed(13)).cuda()
+    det = Detector(m, orc.ANCHORS, 0.45, 0.01, "center")
+    res, plan = det(x)
+    plan.check_status()
+    cand = res.boxes.view(B, -1, 6).cpu()
+    assert cand.shape[1] == 22743
+    kept = res.kept_rows()
+    preds = []
+    for b in range(B):
+        exp = oracle_c(cand[b], 0.45, 0.01, "center")
+        assert np.array_equal(kept[b].cpu().numpy(), cand[b][exp].numpy()), b
+        preds += [[float(b)] + r for r in kept[b].tolist()]
+    g = torch.Generator().manual_seed(7)
+    gts = []
+    for b in range(B):
+        cxy = torch.rand(20, 2, generator=g)
+        wh = 0.05 + 0.35 * torch.rand(20, 2, generator=g)
+        cls = torch.randint(0, 80, (20,), generator=g).float()
+        gts += [[float(b), float(cxy[i, 0]), float(cxy[i, 1]), float(wh[i, 0]), float(wh[i, 1]), 1.0, float(cls[i])] for i in range(20)]
+    # the oracle is pure Python, O(D * G): evaluate the 4 000 best-scored detections of each image
+    sub = []
+    for b in range(B):
+        rows = [p for p in preds if p[0] == b]
+        sub += sorted(rows, key=lambda r: -r[5])[:4000]
+    ref = float(orc.calc_mAP(sub, gts, 0.5, "center", 80))
+    got = float(calc_mAP(sub, gts, 0.5, "center", 80))
+    print(f"config 2: kept {len(preds)} of {B * 22743}, mAP {got:.6f} (oracle {ref:.6f})")
+    assert abs(got - ref) <= 1e-6
+
+
+def test_standalone_blocks_in_train_mode_use_batch_statistics():
+    """The reference's own unit tests call the blocks in default (train) mode (model_tests.py:16-45): BatchNorm then
+    normalises with batch statistics and updates the running ones (nn.BatchNorm2d, model.py:61)."""
+    from yolo_for_turbines_b200.model import CNNBlock, ResidualBlock, ScalePredictionBlock
+
+    torch.manual_seed(1)
+    blk = CNNBlock(3, 32, kernel_size=1).cuda()
+    assert blk.training
+    x = torch.randn(5, 3, 64, 64)
+    y = blk(x.cuda())
+    assert y.shape == (5, 32, 64, 64)
+    z = F.conv2d(x.bfloat16().float(), blk.conv.weight.detach().cpu().bfloat16().float())
+    ref = F.leaky_relu(F.batch_norm(z, None, None, blk.batch_norm.weight.detach().cpu(), blk.batch_norm.bias.detach().cpu(),
+                                    True, 0.1, 1e-5), 0.1)
+    assert float((y.detach().cpu() - ref).abs().max()) <= 2.0 ** -6 * max(1.0, float(ref.abs().max()))
+    assert int(blk.batch_norm.num_batches_tracked) == 1
+    exp_mean = 0.1 * z.mean((0, 2, 3))
+    exp_var = 0.9 + 0.1 * z.var((0, 2, 3), unbiased=True)
+    assert torch.allclose(blk.batch_norm.running_mean.cpu(), exp_mean, atol=2e-3)
+    assert torch.allclose(blk.batch_norm.running_var.cpu(), exp_var, rtol=1e-2, atol=1e-3)
+    rb = ResidualBlock(128, num_blocks=2).cuda()
+    assert rb(torch.randn(5, 128, 64, 64).cuda()).shape == (5, 128, 64, 64)
+    sp = ScalePredictionBlock(512, num_classes=2).cuda()
+    out = sp(torch.randn(5, 512, 13, 13).cuda())
+    assert out.shape == (5, 3, 13, 13, 7) and bool(torch.isfinite(out).all())

@@ -21,7 +21,12 @@ pytestmark = pytest.mark.gpu
 
 BOUNDS = {  # activation -> (min cosine per tensor, min mean cosine, allowed norm ratio range)
     "mish": (0.93, 0.965, (0.85, 1.15)),
-    "leaky_relu": (0.0, 0.55, (0.4, 2.5)),   # per tensor only "not anti-correlated": observed worst 0.22-0.45, it varies run to run
+    # End to end the LeakyReLU gradient is chaotic under bf16 storage (the CPU bf16-sim of the reference itself only
+    # reaches cosine 0.35-0.45 per tensor / 0.67 on average against fp32, on synthetic AND default-init weights), so
+    # this bound can only say "not anti-correlated".  What pins the LeakyReLU backward is the teacher-forced test
+    # below (test_teacher_forced_layer_backward): every layer's dz / dgamma / dbeta / dW against fp32 arithmetic on
+    # the SAME saved tensors, cosine >= 0.995.
+    "leaky_relu": (0.0, 0.55, (0.4, 2.5)),
 }
 
 
@@ -250,3 +255,175 @@ def test_full_size_step_properties():
     assert all(bool(torch.isfinite(v).all()) for v in sd.values())
     assert not torch.equal(m.layers[0].batch_norm.running_mean, rm0)
     assert int(sd["layers.0.batch_norm.num_batches_tracked"]) == 6
+
+
+@pytest.mark.parametrize("act", ["leaky_relu", "mish"])
+def test_teacher_forced_layer_backward(act):
+    """Every layer of the backward pass, teacher-forced: after one Trainer.step the plan still holds each layer's
+    raw conv output z, batch statistics, input activation, the complete gradient dA of its output and the dz it
+    produced.  For every batch-normalised layer the fp32 arithmetic of nn.BatchNorm2d + activation backward is applied
+    to the CUDA path's OWN saved z / dA, and the weight gradient is recomputed from its own input and dz -- so bf16
+    noise cannot accumulate across layers and the bound bites: cosine >= 0.995 for dz, dgamma, dbeta and dW of all
+    72 layers (a wrong negative slope, a mis-scaled BatchNorm backward or a mis-indexed layer fails it)."""
+    import torch.nn.functional as F
+    from oracle import yolo_oracle as orc
+    from yolo_for_turbines_b200.train import Trainer
+
+    m, sd, x, tg = _setup(2, act, 64, 4, 21)
+    m = m.cuda().train()
+    tr = Trainer(m, orc.TURBINE_ANCHORS, lr=0.0, momentum=0.0, weight_decay=0.0)   # lr 0: parameters stay put
+    tr.step(x.cuda(), [t.cuda() for t in tg])
+    torch.cuda.synchronize()
+    plan = tr.plan(4, 64, 64)
+    B, checked, worst = plan.B, 0, (2.0, None)
+
+    def cos(a, b):
+        return float(F.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0))
+
+    for op in plan.ops:
+        if op.head or op.upsample:
+            continue
+        pc, blk = op.pc, op.block
+        C_, cp, P = pc.c_out, pc.c_out_pad, op.P
+        z = op.z.view(P, cp)[:, :C_].float()
+        gbuf, goff, gpitch = plan._final_grad(op.dst)
+        dA = gbuf.view(-1, gpitch)[:P, goff:goff + C_].float()
+        mean, rstd = op.bn["mean"][:C_].float(), op.bn["rstd"][:C_].float()
+        gamma, beta = blk.batch_norm.weight.detach().float(), blk.batch_norm.bias.detach().float()
+        xhat = (z - mean) * rstd
+        y = (xhat * gamma + beta).requires_grad_(True)
+        out = F.leaky_relu(y, 0.1) if act == "leaky_relu" else F.mish(y)
+        (dy,) = torch.autograd.grad(out, y, dA)
+        dbeta, dgamma = dy.sum(0), (dy * xhat).sum(0)
+        dz_ref = gamma * rstd * (dy - dbeta / P - xhat * (dgamma / P))
+        got_dz = op.dz.view(P, cp)[:, :C_].float()
+        res = {"dz": cos(got_dz, dz_ref), "dgamma": cos(blk.batch_norm.weight.grad, dgamma),
+               "dbeta": cos(blk.batch_norm.bias.grad, dbeta)}
+        if op.index > 0:   # weight gradient from the layer's own input and its own dz (the stem reads a patch matrix)
+            sroot, soff = op.src.resolve()
+            a = sroot.buf.view(B, op.src.H, op.src.W, sroot.C)[..., soff:soff + pc.c_in].float().permute(0, 3, 1, 2)
+            go = got_dz.view(B, op.ho, op.wo, C_).permute(0, 3, 1, 2)
+            dw_ref = torch.nn.grad.conv2d_weight(a, blk.conv.weight.shape, go, stride=pc.stride, padding=pc.pad)
+            res["dW"] = cos(blk.conv.weight.grad, dw_ref)
+        for k, v in res.items():
+            if v < worst[0]:
+                worst = (v, f"{op.name}.{k}")
+            assert v >= 0.995, (op.name, k, v)
+        checked += 1
+    print(f"teacher-forced backward ({act}): {checked} layers, worst cosine {worst}")
+    assert checked >= 68
+
+
+def test_load_weights_after_first_forward_and_after_trainer(tmp_path):
+    """Darknet weights loaded AFTER the packs were built (first forward / Trainer construction -- the
+    reference's order is model -> optimizer -> load) must reach the kernels: load_weights() writes through the
+    tensors (version bump), invalidates both caches, and Trainer.step re-validates its packs."""
+    import numpy as np
+    from oracle import yolo_oracle as orc
+    from yolo_for_turbines_b200.model import YOLOv3
+    from yolo_for_turbines_b200.train import Trainer
+
+    import torch.nn as nn
+
+    torch.manual_seed(3)
+    ref = YOLOv3(num_classes=2)
+    path = str(tmp_path / "synthetic.weights")
+    rng = np.random.default_rng(5)
+    chunks = []
+    for mod in ref._darknet_modules():   # the file order: per block beta, gamma, mean, var, then the conv weights
+        if isinstance(mod, nn.BatchNorm2d):
+            c = mod.num_features
+            chunks += [0.1 * rng.standard_normal(c), 1.0 + 0.1 * rng.standard_normal(c), 0.1 * rng.standard_normal(c),
+                       1.0 + 0.2 * rng.random(c)]
+        elif isinstance(mod, nn.Conv2d):
+            if mod.bias is not None:
+                chunks.append(0.1 * rng.standard_normal(mod.out_channels))
+            fan_in = mod.in_channels * mod.kernel_size[0] * mod.kernel_size[1]
+            chunks.append(rng.standard_normal(mod.weight.numel()) * (2.0 / fan_in) ** 0.5)
+    with open(path, "wb") as f:
+        np.zeros(5, dtype=np.int32).tofile(f)
+        np.concatenate(chunks).astype(np.float32).tofile(f)
+    x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(1)).cuda()
+
+    a = YOLOv3(num_classes=2, weights_path=path)
+    a.load_weights()
+    a = a.cuda().eval()
+    want = [o.clone() for o in a(x)]
+
+    b = YOLOv3(num_classes=2, weights_path=path).cuda().eval()
+    first = [o.clone() for o in b(x)]                  # packs built from the random init
+    b.load_weights()                                   # ... then the file is loaded
+    got = b(x)
+    assert any(not torch.equal(u, v) for u, v in zip(first, got))
+    for u, v in zip(want, got):
+        assert torch.equal(u, v)
+
+    tg = [t.cuda() for t in orc.synth_targets(2, 64, 2, 9)]
+    c = YOLOv3(num_classes=2, weights_path=path).cuda().train()
+    tr_c = Trainer(c, orc.TURBINE_ANCHORS, lr=0.0)     # packs built from the random init
+    c.load_weights()
+    d = YOLOv3(num_classes=2, weights_path=path)
+    d.load_weights()
+    d = d.cuda().train()
+    tr_d = Trainer(d, orc.TURBINE_ANCHORS, lr=0.0)     # packs built from the loaded weights
+    lc, ld = tr_c.step(x, tg).cpu(), tr_d.step(x, tg).cpu()
+    assert torch.allclose(lc, ld, rtol=2e-2, atol=1e-4), (lc, ld)
+    for u, v in zip(tr_c.plan(2, 64, 64).head_views(), tr_d.plan(2, 64, 64).head_views()):   # stale packs: cosine ~ 0
+        assert float(torch.nn.functional.cosine_similarity(u.flatten(), v.flatten(), dim=0)) > 0.999
+
+
+def test_autograd_forward_keeps_one_outstanding_graph():
+    """the autograd wrapper keeps its activations in the plan's static buffers; backward() through a
+    graph whose buffers a later forward has reused must raise instead of returning wrong gradients."""
+    from oracle import yolo_oracle as orc
+    from yolo_for_turbines_b200.loss import YOLOLoss
+
+    m, sd, x, tg = _setup(2, "mish", 64, 2, 4)
+    m = m.cuda().train()
+    xs, ts = x.cuda(), [t.cuda() for t in tg]
+    crit = YOLOLoss()
+
+    def loss_of(outs):
+        return sum(sum(crit(o, t.clone(), torch.tensor(orc.TURBINE_ANCHORS[i]) * o.shape[2])) for i, (o, t) in enumerate(zip(outs, ts)))
+
+    l1 = loss_of(m(xs))
+    l2 = loss_of(m(xs))                # same shape: overwrites the buffers l1's graph points at
+    with pytest.raises(RuntimeError, match="ONE outstanding"):
+        l1.backward()
+    l2.backward()                      # the latest graph is intact
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters() if p.requires_grad)
+
+
+def test_trainer_state_dict_round_trip():
+    """the fused trainer's optimizer state (momentum buffers, step count) survives save / restore in the
+    torch.optim.SGD layout utils.save_checkpoint stores: a restored run continues on the same trajectory."""
+    from oracle import yolo_oracle as orc
+    from yolo_for_turbines_b200.model import YOLOv3
+    from yolo_for_turbines_b200.train import Trainer
+
+    m, sd, x, tg = _setup(2, "mish", 64, 2, 8)
+    xs, ts = x.cuda(), [t.cuda() for t in tg]
+    a = m.cuda().train()
+    tr_a = Trainer(a, orc.TURBINE_ANCHORS, lr=1e-3, momentum=0.9, weight_decay=5e-4)
+    tr_a.step(xs, ts)
+    tr_a.step(xs, ts)
+    torch.cuda.synchronize()
+    model_sd = {k: v.detach().clone() for k, v in a.state_dict().items()}
+    opt_sd = tr_a.state_dict()
+    ref_opt = torch.optim.SGD([p for p in a.parameters() if p.requires_grad], lr=1e-3, momentum=0.9, weight_decay=5e-4)
+    assert set(opt_sd["param_groups"][0]) >= set(ref_opt.state_dict()["param_groups"][0])   # torch.optim.SGD layout
+    ref_opt.load_state_dict({k: v for k, v in opt_sd.items() if k != "steps_done"})         # torch accepts it
+    tr_a.step(xs, ts)
+    torch.cuda.synchronize()
+    want = {k: p.detach().clone() for k, p in a.named_parameters()}
+
+    b = YOLOv3(num_classes=2, activation="mish")
+    b.load_state_dict(model_sd)
+    b = b.cuda().train()
+    tr_b = Trainer(b, orc.TURBINE_ANCHORS, lr=0.5, momentum=0.0)     # wrong hyper-parameters: the state dict fixes them
+    tr_b.load_state_dict(opt_sd)
+    assert tr_b.steps_done == 2 and tr_b.momentum == 0.9 and tr_b.lr == 1e-3
+    tr_b.step(xs, ts)
+    torch.cuda.synchronize()
+    for k, p in b.named_parameters():   # same kernels, same inputs; only fp32 atomics order differs
+        assert torch.allclose(p.detach(), want[k], rtol=2e-3, atol=2e-5), k

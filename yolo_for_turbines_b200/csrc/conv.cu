@@ -463,11 +463,11 @@ extern "C" int yolo_conv_fwd(const void* plan_host, uint32_t* status, yb_stream_
   return YB_ERR_UNSUPPORTED;
 }
 
-extern "C" int yolo_conv_fwd_trace(const void* plan_host, uint32_t* status, unsigned long long* trace_dev,
+extern "C" int yolo_conv_fwd_trace(const void* plan_host, uint32_t* status, unsigned long long* trace_dev, int box,
                                    yb_stream_t stream_) {
   const ConvPlan* pl = static_cast<const ConvPlan*>(plan_host);
   YB_REQUIRE(pl && pl->magic == PLAN_MAGIC && pl->impl == 2 && trace_dev, "conv trace: needs a persistent-kernel plan");
-  return conv2_launch(pl, status, (cudaStream_t)stream_, nullptr, nullptr, nullptr, trace_dev);
+  return conv2_launch(pl, status, (cudaStream_t)stream_, nullptr, nullptr, nullptr, trace_dev, box);
 }
 
 extern "C" int yolo_conv_fwd_stats(const void* plan_host, uint32_t* status, double* sums2c, const yolo_bn_finalize_desc* fin,

@@ -140,7 +140,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   const uint32_t stats_base = scratch_base + EPI_WARPS * SCRATCH_BYTES;  // training forward: [2 * c_out_pad] fp32 channel sums of this CTA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (p.trace && threadIdx.x == 0) p.trace[16 * size_t(blockIdx.x)] = gtimer();
+  if (p.trace && threadIdx.x == 0) p.trace[32 * size_t(blockIdx.x)] = gtimer();
   if (p.stats != nullptr) {
     for (int i = threadIdx.x; i < 2 * p.c_out_pad; i += blockDim.x)
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(stats_base + 4u * i), "r"(0u) : "memory");
@@ -173,7 +173,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  unsigned long long* const trace = p.trace ? p.trace + 16 * size_t(blockIdx.x) : nullptr;
+  unsigned long long* const trace = p.trace ? p.trace + 32 * size_t(blockIdx.x) : nullptr;
   if (trace && threadIdx.x == 0) trace[1] = gtimer();
   if (p.pdl) {
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped
@@ -189,6 +189,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     // ===== TMA producer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
     int s = 0, ntiles = 0;
     uint32_t ph = 0;
+    unsigned long long wait_ns = 0;
     for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++ntiles) {
       int mt, n0, nw;
       decode_tile<BLOCK_N>(p, v, mt, n0, nw);
@@ -209,7 +210,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       }
       int tr = 0, tq = 0, cc = 0;  // filter tap (row, col) and channel chunk of the current k-block
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (trace) {
+          const unsigned long long w0 = gtimer();
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          wait_ns += gtimer() - w0;
+        } else {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+        }
         if (elect_one()) {
           if (leader) mbar_expect_tx(full_bar(s), (STEM ? C::B_BYTES : C::A_BYTES + b_bytes) * NCTA);
           const uint32_t sa = smem_base + s * C::STAGE_BYTES, sb = sa + C::A_BYTES;
@@ -233,22 +240,35 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
-    if (trace && lane == 0) trace[9] = (unsigned long long)ntiles;
+    if (trace && lane == 0) { trace[9] = (unsigned long long)ntiles; trace[18] = wait_ns; }
   } else if (warp == 1) {
     if (leader) {
       // ===== MMA issuer: warp-uniform loop, tcgen05.mma / commit from one elected lane =====
       int s = 0;
       uint32_t ph = 0, tl = 0;
+      unsigned long long wfull_ns = 0, wacc_ns = 0;
       const uint64_t adesc0 = make_kmajor_desc<C::ROW_BYTES>(smem_base);
       const uint64_t bdesc0 = make_kmajor_desc<C::ROW_BYTES>(smem_base + C::A_BYTES);
       for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
         const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
         const uint32_t idesc = v < p.t_full ? C::IDESC : C::IDESC_HALF;
-        mbar_wait(tempty_bar(acc), aph ^ 1u);  // the epilogue has drained this accumulator
+        if (trace) {
+          const unsigned long long w0 = gtimer();
+          mbar_wait(tempty_bar(acc), aph ^ 1u);
+          wacc_ns += gtimer() - w0;
+        } else {
+          mbar_wait(tempty_bar(acc), aph ^ 1u);  // the epilogue has drained this accumulator
+        }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(full_bar(s), ph);
+          if (trace) {
+            const unsigned long long w0 = gtimer();
+            mbar_wait(full_bar(s), ph);
+            wfull_ns += gtimer() - w0;
+          } else {
+            mbar_wait(full_bar(s), ph);
+          }
           tc_fence_after();
           if (trace && tl == 0 && kb == 0 && lane == 0) trace[4] = gtimer();
           if (elect_one()) {
@@ -264,7 +284,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
       }
-      if (trace && lane == 0) trace[5] = gtimer();
+      if (trace && lane == 0) { trace[5] = gtimer(); trace[16] = wfull_ns; trace[17] = wacc_ns; }
     }
   } else if (STEM && warp >= 2 + EPI_WARPS) {
     // ===== STEM gather warps: one thread per A row = one output pixel pair =====
@@ -451,7 +471,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             if constexpr (NCTA == 1) mbar_arrive_local(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc));
           }
         }
-        if (tr0 && b == 0) trace[10] = gtimer();
+        if (tr0 && b == p.trace_box) trace[10] = gtimer();
         if (staged && res_staged) {
           // one box ahead: the store of the previous box (committed a TMEM round trip ago) has read its slot
           if (pk < wbox + WSLOTS && pv < p.num_vtiles) {
@@ -461,7 +481,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           }
           mbar_wait(res_bar(ew, slot), sph);
         }
-        if (tr0 && b == 0) trace[11] = gtimer();
+        if (tr0 && b == p.trace_box) trace[11] = gtimer();
         const uint32_t row_addr = slot_addr + lane * C::BOX_ROW_BYTES;
         auto process_half = [&](const uint32_t (&v)[32], const int h) {
           const int n = nb + h * 32;
@@ -473,6 +493,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           for (int i = 0; i + 1 < BLOCK_N / 32; ++i) { r_sc[i] = r_sc[i + 1]; r_bi[i] = r_bi[i + 1]; }
           __syncwarp();
           bn_act32(v, o, scratch, p.act);
+          if (tr0 && b == p.trace_box && h == 0) trace[19] = gtimer();
           size_t drow = size_t(m);   // direct-path addressing: (row, column) of the residual / output element
           int dcol = n;
           if (p.s2_parity) {
@@ -499,6 +520,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
               o[8 * j + 6] += bf16_lo(r.w); o[8 * j + 7] += bf16_hi(r.w);
             }
           }
+          if (tr0 && b == p.trace_box && h == 0) trace[20] = gtimer();
           if (p.check_nan && valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) saw_nan |= (o[j] != o[j]);
@@ -547,11 +569,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           }
         };
         process_half(v0, 0);
+        if (tr0 && b == p.trace_box) trace[21] = gtimer();
         if constexpr (C::BOXC == 64) process_half(v1, 1);
+        if (tr0 && b == p.trace_box) trace[22] = gtimer();
         if (staged) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
-          if (tr0 && b == 0) trace[12] = gtimer();
+          if (tr0 && b == p.trace_box) trace[12] = gtimer();
           if (lane == 0) {
             if (f32_staged) {
               tma_store_2d(&p.tmY, wslot_base, nb, m0w);
@@ -588,7 +612,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             }
           }
           ++wbox;
-          if (tr0) trace[b == 0 ? 13 : 14] = gtimer();
+          if (tr0) { if (b == p.trace_box) trace[13] = gtimer(); if (b == nboxes - 1) trace[14] = gtimer(); }
         }
       }
     }
@@ -770,7 +794,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   kp.s2_parity = d->s2_parity; kp.s2_cin = d->s2_cin;
   kp.t_full = t_full; kp.num_vtiles = num_vtiles; kp.b_half = b_half;
   kp.pdl = d->pdl_hint == 1 ? 0 : 1;
-  kp.trace = nullptr;
+  kp.trace = nullptr; kp.trace_box = 0;
   pl->stem_direct = stem ? 1 : 0;
   if (stem) {
     YB_REQUIRE(bn == 64 && kc == 64 && d->stem_c == 3 && d->ksize == 1 && tiles_n == 1 && !d->has_residual && !direct,
@@ -800,7 +824,7 @@ int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status,
 }
 
 int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats, const BnFinalize* fin,
-                 unsigned int* fin_counter, unsigned long long* trace) {
+                 unsigned int* fin_counter, unsigned long long* trace, int trace_box) {
   YB_REQUIRE(!pl->stem_direct, "conv fwd: stem plans are launched with yolo_conv_fwd_stem");
   YB_REQUIRE(!stats || (pl->d.want_stats && !(pl->d.upsample2x || pl->d.out_fp32)),
              "conv fwd: statistics need a plan built with want_stats and the staged bf16 output path");
@@ -808,6 +832,7 @@ int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, doub
   kp.status = status;
   kp.stats = stats;
   kp.trace = trace;
+  kp.trace_box = trace_box;
   if (stats && fin && fin_counter) { kp.fin = *fin; kp.fin_counter = fin_counter; }
 #define YB_L2(BN, KC)                                                        \
   if (pl->block_n == BN && pl->kc == KC)                                     \

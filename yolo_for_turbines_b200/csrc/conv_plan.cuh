@@ -59,7 +59,8 @@ struct ConvKParams2 {
   // then holds half-height boxes and a whole tile issues two of them).
   int t_full, num_vtiles, b_half;
   int pdl;              // launched with programmatic stream serialization: griddepcontrol.* brackets the prologue
-  unsigned long long* trace;  // dev tool (yolo_conv_fwd_trace): 16 globaltimer stamps per CTA, nullptr otherwise
+  unsigned long long* trace;  // dev tool (yolo_conv_fwd_trace): 32 globaltimer stamps / counters per CTA, nullptr otherwise
+  int trace_box;              // which epilogue box of the first tile gets the fine-grained stamps
 };
 
 struct ConvPlan {
@@ -86,5 +87,5 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
                      const void* residual, void* y);
 int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats = nullptr,
                  const BnFinalize* fin = nullptr, unsigned int* fin_counter = nullptr,
-                 unsigned long long* trace = nullptr);
+                 unsigned long long* trace = nullptr, int trace_box = 0);
 int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status, cudaStream_t stream);

@@ -9,7 +9,10 @@ not on a CUDA device or libyolo_b200.so is missing.
 
 Deviations, all deliberate:
   * train mode (`model.train()`): the whole network is one autograd node (train._TrainForwardFn) running the
-    batch-statistics forward and the hand-written backward; standalone blocks still need .eval().
+    batch-statistics forward and the hand-written backward.  Standalone blocks called in train mode (the
+    reference's own unit tests do, model_tests.py:16-45) normalise with batch statistics and update the running
+    ones like nn.BatchNorm2d, but their output carries no autograd graph: the training entry points are
+    YOLOv3.forward and train.Trainer.
   * the reference's 28 per-layer NaN syncs (model.py:175,183) are one device status word checked
     once per forward; the same AssertionError / ValueError("Nan in layer") are raised.
   * compute is bf16 with fp32 accumulation; head outputs are returned as fp32.
@@ -43,8 +46,6 @@ def _run_blocks_standalone(owner: nn.Module, x: torch.Tensor, program):
     from . import engine as E
 
     require_cuda(x, f"{type(owner).__name__} input")
-    if owner.training and any(isinstance(m, nn.BatchNorm2d) for m in owner.modules()):
-        raise YoloB200Error("train-mode BatchNorm (batch statistics) is not built on this path yet: call .eval()")
     eng = getattr(owner, "_yb_engine", None)
     if eng is None or eng.device != x.device:
         eng = E.Engine(owner, x.device)
@@ -70,17 +71,46 @@ def _run_blocks_standalone(owner: nn.Module, x: torch.Tensor, program):
         ho = (h + 2 * pc.pad_eff - pc.k_eff) // pc.stride_eff + 1
         wo = (w + 2 * pc.pad_eff - pc.k_eff) // pc.stride_eff + 1
         y = torch.empty(B * ho * wo * pc.c_out_pad, dtype=torch.float32 if fp32 else torch.bfloat16, device=x.device)
+        bn_train = bool(block.batch_norm_act and block.batch_norm.training)
         d = E.ConvDesc()
         d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch = B, h, w, pc.c_in_eff, C_
         d.c_out, d.c_out_pad, d.out_pitch = pc.c_out, pc.c_out_pad, pc.c_out_pad
         d.ksize, d.stride, d.pad, d.act = pc.k_eff, pc.stride_eff, pc.pad_eff, E.ACT_CODES[pc.act]
         d.out_fp32, d.check_nan = int(fp32), 0
-        if residual is not None:
+        if residual is not None and not bn_train:
             d.has_residual, d.res_pitch = 1, residual[1]
-        plan = E.make_conv_plan(d, ptr(t), ptr(pc.w), ptr(pc.scale), ptr(pc.bias),
-                                ptr(residual[0]) if residual is not None else None, ptr(y))
+        if not bn_train:
+            plan = E.make_conv_plan(d, ptr(t), ptr(pc.w), ptr(pc.scale), ptr(pc.bias),
+                                    ptr(residual[0]) if residual is not None else None, ptr(y))
+            lib.yolo_conv_fwd(plan[1], ptr(status), st)
+            keep.append((plan, pc, t, y))
+            return (y, pc.c_out_pad, ho, wo), pc.c_out
+        # train mode (nn.BatchNorm2d with batch statistics, model.py:61 under .train()): raw conv output z, its batch
+        # statistics (running ones updated with the module's momentum), then BN + activation (+ residual)
+        bn, Cp, P = block.batch_norm, pc.c_out_pad, B * ho * wo
+        d.act = 0
+        dev = x.device
+        ones, zeros = torch.ones(Cp, device=dev), torch.zeros(Cp, device=dev)
+        z = torch.empty(P * Cp, dtype=torch.bfloat16, device=dev)
+        plan = E.make_conv_plan(d, ptr(t), ptr(pc.w), ptr(ones), ptr(zeros), None, ptr(z))
         lib.yolo_conv_fwd(plan[1], ptr(status), st)
-        keep.append((plan, pc, t, y))
+        sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        f32 = lambda v: v.detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        gamma, beta = f32(bn.weight), f32(bn.bias)
+        mean, rstd, sc, bi = (torch.empty(Cp, device=dev) for _ in range(4))
+        momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+        track = bn.track_running_stats and bn.running_mean is not None
+        rm = bn.running_mean if track else None
+        rv = bn.running_var if track else None
+        lib.yolo_bn_stats_finalize(ptr(z), P, pc.c_out, Cp, ptr(sums), ptr(counter), ptr(gamma), ptr(beta), float(bn.eps),
+                                   momentum, ptr(rm), ptr(rv), ptr(mean), ptr(rstd), ptr(sc), ptr(bi), st)
+        if track:
+            bn.num_batches_tracked += 1
+        lib.yolo_bn_act_fwd(ptr(z), P, pc.c_out, Cp, ptr(sc), ptr(bi), E.ACT_CODES[pc.act],
+                            ptr(residual[0]) if residual is not None else None, residual[1] if residual is not None else 0,
+                            ptr(y), Cp, 0, ho, wo, st)
+        keep.append((plan, pc, t, y, z, sums, counter, gamma, beta, mean, rstd, sc, bi, ones, zeros))
         return (y, pc.c_out_pad, ho, wo), pc.c_out
 
     (y, cp, ho, wo), c_out, fp32 = program(conv, (a0, cpad, H, W))
@@ -238,8 +268,8 @@ class YOLOv3(_EngineHolder, nn.Module):
         """Input checks + (cached) plan lookup shared by forward_async and utils.Detector."""
         require_cuda(x, "YOLOv3 input")
         if self.training:
-            raise YoloB200Error("train-mode forward (batch-statistics BatchNorm + autograd) is not built on this "
-                                "path yet: call model.eval()")
+            raise YoloB200Error("the planned inference pipeline (forward_async / utils.Detector) needs model.eval(); "
+                                "in train mode call model(x) (autograd) or train.Trainer.step")
         if x.dim() != 4 or x.shape[1] != self.in_channels:
             raise YoloB200Error(f"expected (B,{self.in_channels},H,W) input, got {tuple(x.shape)}")
         eng = self._engine(x.device)
@@ -308,9 +338,22 @@ class YOLOv3(_EngineHolder, nn.Module):
             for t in slots:
                 n = t.numel()
                 if not skip:
-                    t.data.copy_(torch.from_numpy(flat[self.param_idx:self.param_idx + n]).view_as(t))
+                    with torch.no_grad():  # an in-place copy THROUGH the tensor: bumps its version counter, which
+                        # is what Engine.refresh_if_needed / Trainer.repack_if_changed watch (t.data.copy_ does not)
+                        t.copy_(torch.from_numpy(flat[self.param_idx:self.param_idx + n]).view_as(t))
                     if self.freeze:
                         t.requires_grad = False
                 self.param_idx += n
             self.layer_id += 1
+        self.invalidate_packed_weights()
         print(f"Weights from {self.weights_path} loaded successfully.")
+
+    def invalidate_packed_weights(self):
+        """Forces the bf16 weight packs / folded BatchNorm vectors (inference engine and training session) to be
+        rebuilt on the next forward.  Needed after writes that bypass the tensors' version counters (`p.data...`)."""
+        eng = self.__dict__.get("_yb_engine")
+        if eng is not None:
+            eng._sig = None
+        sess = self.__dict__.get("_yb_train")
+        if sess is not None and hasattr(sess, "_packed_sig"):
+            sess._packed_sig = None

@@ -414,6 +414,11 @@ class _TrainForwardFn(torch.autograd.Function):
             trainer.repack_if_changed()
             plan = trainer.plan(x.shape[0], x.shape[2], x.shape[3])
             plan.forward(x)
+        # The activations the backward pass needs live in the plan's static buffers (11 GB at batch 32, 416^2), not
+        # in this node: ONE forward of a given shape may be outstanding.  Every forward / backward that touches the
+        # buffers bumps the plan's generation; backward() refuses to run on buffers a later forward has overwritten.
+        plan.generation = getattr(plan, "generation", 0) + 1
+        ctx.generation = plan.generation
         ctx.trainer, ctx.plan = trainer, plan
         ctx.n_params = len(params)
         eng = trainer.model.__dict__.get("_yb_engine")
@@ -424,6 +429,13 @@ class _TrainForwardFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *gheads):
         tr, plan = ctx.trainer, ctx.plan
+        if ctx.generation != getattr(plan, "generation", 0):
+            raise RuntimeError(
+                "backward() of a train-mode forward whose saved activations are gone: this path keeps ONE outstanding "
+                f"forward per input shape ({plan.B}x{plan.H}x{plan.W}) in static buffers, and a later forward (or an earlier "
+                "backward through the same graph) has reused them.  Call backward() before the next model(x) of this "
+                "shape; for gradient accumulation run forward+backward per micro-batch.")
+        plan.generation += 1   # this backward consumes the buffers (dz is rewritten in place): no second backward
         with torch.cuda.device(tr.device):
             tr.dw_packed.zero_()
             plan.sums[plan.sums.numel() // 2:].zero_()
@@ -533,6 +545,7 @@ class Trainer:
         self._ev_sgd = torch.cuda.Event()
         self._packs_pending = False
         self.repack(full=True)
+        self._packed_sig = self._param_sig()
 
     # ------------------------------------------------------------------------------------------------------
     def repack_async(self):
@@ -578,6 +591,22 @@ class Trainer:
                                      ptr(pc.bias), st)
                 if events:
                     self.ev_pack[id(b)].record(torch.cuda.current_stream(dev))
+
+    def _param_sig(self):
+        return tuple((p._version, p.data_ptr()) for p in self.all_params)
+
+    def _repack_if_written_externally(self):
+        """Fused mode: the SGD kernel updates the flat buffer directly (no version bump) and repacks itself, so the
+        version counters only move when someone ELSE wrote the parameters -- load_weights(), load_state_dict(),
+        load_checkpoint() after the Trainer was built (the reference's order: model -> optimizer -> load).  Then the
+        bf16 packs are rebuilt before the forward uses them."""
+        sig = self._param_sig()
+        if sig != self._packed_sig:
+            if self._packs_pending and self.wgrad_stream is not None:
+                torch.cuda.current_stream(self.device).wait_stream(self.wgrad_stream)
+            self.repack()
+            self._packs_pending = False
+            self._packed_sig = sig
 
     def repack_if_changed(self):
         """Autograd mode: the caller's optimizer updates the parameters in place between forwards."""
@@ -671,8 +700,10 @@ class Trainer:
         plan = self.plan(x.shape[0], x.shape[2], x.shape[3])
         with torch.cuda.device(dev):
             st = stream_ptr(dev)
+            self._repack_if_written_externally()
             self.dw_packed.zero_()
             plan.forward(x)
+            plan.generation = getattr(plan, "generation", 0) + 1
             self.losses = self._loss_and_head_grads(plan, targets)
             if self.world > 1:
                 main = torch.cuda.current_stream(dev)
@@ -705,6 +736,53 @@ class Trainer:
         if eng is not None:
             eng._sig = None  # the inference engine's packed weights are stale now
         return self.losses
+
+    # ---- optimizer state (utils.py:383-416 save_checkpoint / load_checkpoint store {state_dict, optimizer}) --------
+    def state_dict(self) -> dict:
+        """A torch.optim.SGD-compatible state dict: one param group over the trainable parameters in module order,
+        per-parameter `momentum_buffer` copies of the flat momentum buffer (absent before the first step, as in
+        torch.optim.SGD)."""
+        trainable = [p for p in self.all_params if p.requires_grad]
+        state = {}
+        if self.steps_done > 0 and self.momentum != 0.0:
+            for i, p in enumerate(trainable):
+                o = self.param_off[id(p)]
+                state[i] = {"momentum_buffer": self.flat_m[o:o + p.numel()].view_as(p).clone()}
+        group = {"lr": self.lr, "momentum": self.momentum, "dampening": 0, "weight_decay": self.weight_decay,
+                 "nesterov": False, "maximize": False, "foreach": None, "differentiable": False, "fused": None,
+                 "params": list(range(len(trainable)))}
+        return {"state": state, "param_groups": [group], "steps_done": self.steps_done}
+
+    def load_state_dict(self, sd: dict):
+        """Accepts what state_dict() emits or a torch.optim.SGD state dict of the same parameters (same order)."""
+        if not self.own_params:
+            raise YoloB200Error("load_state_dict needs own_params=True (the fused trainer owns the optimizer state)")
+        trainable = [p for p in self.all_params if p.requires_grad]
+        groups = sd.get("param_groups", [])
+        idx = [i for g in groups for i in g["params"]]
+        if len(idx) != len(trainable):
+            raise YoloB200Error(f"optimizer state holds {len(idx)} parameters, the model has {len(trainable)} trainable ones")
+        if groups:
+            g = groups[0]
+            self.lr, self.momentum = float(g.get("lr", self.lr)), float(g.get("momentum", self.momentum))
+            self.weight_decay = float(g.get("weight_decay", self.weight_decay))
+        state = sd.get("state", {})
+        have = 0
+        self.flat_m.zero_()
+        for pos, (key, p) in enumerate(zip(idx, trainable)):
+            ent = state.get(key, state.get(str(key)))
+            buf = None if ent is None else ent.get("momentum_buffer")
+            if buf is None:
+                continue
+            if tuple(buf.shape) != tuple(p.shape):
+                raise YoloB200Error(f"momentum buffer {pos}: shape {tuple(buf.shape)} does not match {tuple(p.shape)}")
+            o = self.param_off[id(p)]
+            self.flat_m[o:o + p.numel()].view_as(p).copy_(buf.to(device=self.device, dtype=torch.float32))
+            have += 1
+        # torch.optim.SGD seeds the buffer with the first gradient; after a restore with buffers the next step must NOT
+        self.steps_done = int(sd.get("steps_done", 1 if have else 0))
+        if have and self.steps_done == 0:
+            self.steps_done = 1
 
     def launches_per_step(self, plan: TrainPlan) -> int:
         n_bn = sum(1 for op in plan.ops if not op.head)
