@@ -366,10 +366,16 @@ def test_load_weights_after_first_forward_and_after_trainer(tmp_path):
     d.load_weights()
     d = d.cuda().train()
     tr_d = Trainer(d, orc.TURBINE_ANCHORS, lr=0.0)     # packs built from the loaded weights
-    lc, ld = tr_c.step(x, tg).cpu(), tr_d.step(x, tg).cpu()
-    assert torch.allclose(lc, ld, rtol=2e-2, atol=1e-4), (lc, ld)
-    for u, v in zip(tr_c.plan(2, 64, 64).head_views(), tr_d.plan(2, 64, 64).head_views()):   # stale packs: cosine ~ 0
-        assert float(torch.nn.functional.cosine_similarity(u.flatten(), v.flatten(), dim=0)) > 0.999
+    lc, ld = tr_c.step(x, tg).cpu(), tr_d.step(x, tg).cpu()   # step() re-validates the packs before its forward
+    torch.cuda.synchronize()
+    assert torch.isfinite(lc).all() and torch.isfinite(ld).all()
+    # lr = 0: the parameters did not move, so both trainers must now hold bit-identical bf16 operand packs
+    for bc, bd in zip(tr_c.blocks, tr_d.blocks):
+        assert torch.equal(tr_c.engine.packed[id(bc)].w, tr_d.engine.packed[id(bd)].w)
+        if id(bc) in tr_c.wT:
+            assert torch.equal(tr_c.wT[id(bc)], tr_d.wT[id(bd)])
+    # (the loss terms themselves only agree loosely: batch-2 BatchNorm over a 2x2 grid amplifies the order of fp32 atomics)
+    assert torch.allclose(lc, ld, rtol=0.3, atol=1e-3), (lc, ld)
 
 
 def test_autograd_forward_keeps_one_outstanding_graph():

@@ -88,7 +88,7 @@ __device__ __forceinline__ void bn_act32(const uint32_t (&v)[32], float (&o)[32]
     for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.1f * o[j]);  // NaN stays NaN (both operands NaN)
   } else if (act == YB_ACT_MISH) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = apply_act(o[j], YB_ACT_MISH);
+    for (int j = 0; j < 32; ++j) o[j] = mish_fast(o[j]);
   }
 }
 
@@ -161,7 +161,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4 * NCTA);  // one arrive per warp of the owning epilogue group, per CTA
+      mbar_init(tempty_bar(a), EPI_WARPS * NCTA);  // one arrive per epilogue warp, per CTA
     }
     for (int w = 0; w < EPI_WARPS; ++w)
       for (int sl = 0; sl < WSLOTS; ++sl) mbar_init(res_bar(w, sl), 1);
@@ -350,10 +350,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       if (saw_nan) atomicOr(p.status, YB_STATUS_NAN_INPUT);
     }
   } else {
-    // ===== epilogue: group g = (warp-2)/4 owns TMEM accumulator g and every second tile; each warp works
-    // alone on its 32 rows (TMEM lane quadrant = warp % 4): own smem slots, own TMA loads/stores, no CTA barrier.
+    // ===== epilogue: all eight warps work on EVERY tile.  Warp w reads TMEM lane quadrant w % 4 (its 32 rows) and
+    // column half (w - 2) / 4 of the tile, so two warps per scheduler share the tile's epilogue and its latency is
+    // half of what one group of four needs -- that latency is the tail of every launch and, on the short-K 1x1
+    // layers, the critical path (accumulator double buffering only hides it when the main loop is longer).
+    // Each warp works alone: own smem slots, own TMA loads/stores, no CTA barrier.
     const int ew = warp - 2;
-    const uint32_t acc = uint32_t(ew >> 2);
+    const int chalf = ew >> 2;          // which half of the tile's boxes this warp owns
     const int quad = warp & 3;
     // fp32 outputs (the scale heads) are staged too: 32-column fp32 boxes (128-byte rows) leave through TMA stores
     const bool f32_staged = p.out_fp32 && !p.upsample2x && p.s2_parity == 0;
@@ -369,14 +372,21 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     // loads of the next tile's first two boxes fly while this group waits for its accumulator -- instead of
     // starting every load right before its data is needed (one exposed L2 round trip per box).
     const bool res_staged = p.has_residual && !direct;
-    int pv = cluster_id + int(acc) * num_clusters, pb = 0;   // (virtual tile, box) the cursor points at
+    int pv = cluster_id, pb = -1;   // (virtual tile, box) the cursor points at; pb < 0: not yet placed in the tile
     uint32_t pk = 0;                                         // boxes whose residual load has been issued
-    auto res_cursor_settle = [&]() {   // skip tiles in which this warp has no valid rows (they use no slots)
+    // boxes [box_lo, box_hi) of a tile of width w belong to this warp (a one-box tile goes to column half 0)
+    auto box_lo = [&](int w) { const int nb = w / C::BOXC; return nb >= 2 ? chalf * (nb / 2) : 0; };
+    auto box_hi = [&](int w) { const int nb = w / C::BOXC; return nb >= 2 ? (chalf + 1) * (nb / 2) : (chalf == 0 ? nb : 0); };
+    auto res_cursor_settle = [&]() {   // skip tiles in which this warp has no rows or no boxes (they use no slots)
       while (pv < p.num_vtiles) {
         int cmt, cn0, cnw;
         decode_tile<BLOCK_N>(p, pv, cmt, cn0, cnw);
-        if ((cmt * NCTA + (int)rank) * BLOCK_M + quad * 32 < p.M) break;
-        pv += 2 * num_clusters;
+        if ((cmt * NCTA + (int)rank) * BLOCK_M + quad * 32 < p.M && box_lo(cnw) < box_hi(cnw)) {
+          if (pb < 0) pb = box_lo(cnw);
+          break;
+        }
+        pv += num_clusters;
+        pb = -1;
       }
     };
     auto res_issue_next = [&]() {      // warp-uniform; the caller guarantees the slot is free
@@ -389,15 +399,14 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         tma_load_2d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, cn0 + pb * C::BOXC, cm0w);
       }
       ++pk;
-      if (++pb == cnw / C::BOXC) { pb = 0; pv += 2 * num_clusters; res_cursor_settle(); }
+      if (++pb == box_hi(cnw)) { pb = -1; pv += num_clusters; res_cursor_settle(); }
     };
     if (res_staged) res_cursor_settle();
     for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
-      if ((tl & 1u) != acc) continue;
-      const uint32_t aph = (tl >> 1) & 1u;
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       int mt, n0, nw;
       decode_tile<BLOCK_N>(p, v, mt, n0, nw);
-      const int nboxes = nw / C::BOXC;
+      const int b_lo = box_lo(nw), b_hi = box_hi(nw);
       const int m0w = (mt * NCTA + (int)rank) * BLOCK_M + quad * 32;
       const int m = m0w + lane;
       const bool valid = m < p.M;
@@ -405,14 +414,16 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       const bool tr0 = trace != nullptr && ew == 0 && tl == 0 && lane == 0;
       // this tile's per-column scale / bias, fetched while the accumulator is still being produced: lane l holds
       // columns n0 + 32 i + l; chunk 0 is handed to the scratch per 32-column step and the registers rotate
-      float r_sc[BLOCK_N / 32], r_bi[BLOCK_N / 32];
+      constexpr int NCH = (BLOCK_N / 64 > C::BOXC / 32) ? BLOCK_N / 64 : C::BOXC / 32;   // 32-column chunks one warp can own: half a tile, or a whole one-box tile
+      float r_sc[NCH], r_bi[NCH];
+      const int c_lo = n0 + b_lo * C::BOXC, c_hi = n0 + b_hi * C::BOXC;
 #pragma unroll
-      for (int i = 0; i < BLOCK_N / 32; ++i) {
-        const bool in = 32 * i < nw;
-        r_sc[i] = in ? __ldg(p.scale + n0 + 32 * i + lane) : 0.f;
-        r_bi[i] = in ? __ldg(p.bias + n0 + 32 * i + lane) : 0.f;
+      for (int i = 0; i < NCH; ++i) {
+        const bool in = c_lo + 32 * i < c_hi;
+        r_sc[i] = in ? __ldg(p.scale + c_lo + 32 * i + lane) : 0.f;
+        r_bi[i] = in ? __ldg(p.bias + c_lo + 32 * i + lane) : 0.f;
       }
-      if (res_staged && wvalid) {
+      if (res_staged && wvalid && b_lo < b_hi) {
         // tile boundary: every earlier store of this warp was committed long ago -- take both slots
         if (lane == 0) bulk_wait_group_read<0>();
         __syncwarp();
@@ -439,9 +450,19 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         out_row[0] = (size_t(img) * (2 * p.h_out) + 2 * po + (p.s2_parity - 1)) * size_t(2 * p.w_out) + 2 * qo;
       }
       const bool staged = !direct && wvalid;
-      bool acc_ready = false;
+      // every warp waits for the accumulator and hands it back, also when it owns no box of this tile
+      mbar_wait(tfull_bar(acc), aph);
+      tc_fence_after();
+      if (trace && tl == 0 && ew == 0 && lane == 0) trace[6] = gtimer();
+      if (b_lo >= b_hi) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (NCTA == 1) mbar_arrive_local(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc));
+        }
+      }
 #pragma unroll 1
-      for (int b = 0; b < nboxes; ++b) {
+      for (int b = b_lo; b < b_hi; ++b) {
         const uint32_t slot = wbox % WSLOTS, sph = (wbox / WSLOTS) & 1u;
         const uint32_t slot_addr = wslot_base + slot * C::WBOX_BYTES;
         const int nb = n0 + b * C::BOXC;
@@ -452,18 +473,12 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           }
           __syncwarp();
         }
-        if (!acc_ready) {
-          mbar_wait(tfull_bar(acc), aph);
-          tc_fence_after();
-          acc_ready = true;
-          if (trace && tl == 0 && ew == 0 && lane == 0) trace[6] = gtimer();
-        }
         const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + b * C::BOXC;
         uint32_t v0[32], v1[32];
         tmem_ld32_nowait(taddr, v0);
         if constexpr (C::BOXC == 64) tmem_ld32_nowait(taddr + 32, v1);
         tmem_wait_ld();
-        if (b == nboxes - 1) {
+        if (b == b_hi - 1) {
           // every tcgen05.ld of this accumulator has completed: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -471,7 +486,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             if constexpr (NCTA == 1) mbar_arrive_local(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc));
           }
         }
-        if (tr0 && b == p.trace_box) trace[10] = gtimer();
+        if (tr0 && b == b_lo + p.trace_box) trace[10] = gtimer();
         if (staged && res_staged) {
           // one box ahead: the store of the previous box (committed a TMEM round trip ago) has read its slot
           if (pk < wbox + WSLOTS && pv < p.num_vtiles) {
@@ -481,7 +496,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           }
           mbar_wait(res_bar(ew, slot), sph);
         }
-        if (tr0 && b == p.trace_box) trace[11] = gtimer();
+        if (tr0 && b == b_lo + p.trace_box) trace[11] = gtimer();
         const uint32_t row_addr = slot_addr + lane * C::BOX_ROW_BYTES;
         auto process_half = [&](const uint32_t (&v)[32], const int h) {
           const int n = nb + h * 32;
@@ -490,10 +505,10 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + 4u * lane), "f"(r_sc[0]) : "memory");
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + 128u + 4u * lane), "f"(r_bi[0]) : "memory");
 #pragma unroll
-          for (int i = 0; i + 1 < BLOCK_N / 32; ++i) { r_sc[i] = r_sc[i + 1]; r_bi[i] = r_bi[i + 1]; }
+          for (int i = 0; i + 1 < NCH; ++i) { r_sc[i] = r_sc[i + 1]; r_bi[i] = r_bi[i + 1]; }
           __syncwarp();
           bn_act32(v, o, scratch, p.act);
-          if (tr0 && b == p.trace_box && h == 0) trace[19] = gtimer();
+          if (tr0 && b == b_lo + p.trace_box && h == 0) trace[19] = gtimer();
           size_t drow = size_t(m);   // direct-path addressing: (row, column) of the residual / output element
           int dcol = n;
           if (p.s2_parity) {
@@ -520,7 +535,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
               o[8 * j + 6] += bf16_lo(r.w); o[8 * j + 7] += bf16_hi(r.w);
             }
           }
-          if (tr0 && b == p.trace_box && h == 0) trace[20] = gtimer();
+          if (tr0 && b == b_lo + p.trace_box && h == 0) trace[20] = gtimer();
           if (p.check_nan && valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) saw_nan |= (o[j] != o[j]);
@@ -569,13 +584,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           }
         };
         process_half(v0, 0);
-        if (tr0 && b == p.trace_box) trace[21] = gtimer();
+        if (tr0 && b == b_lo + p.trace_box) trace[21] = gtimer();
         if constexpr (C::BOXC == 64) process_half(v1, 1);
-        if (tr0 && b == p.trace_box) trace[22] = gtimer();
+        if (tr0 && b == b_lo + p.trace_box) trace[22] = gtimer();
         if (staged) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
-          if (tr0 && b == p.trace_box) trace[12] = gtimer();
+          if (tr0 && b == b_lo + p.trace_box) trace[12] = gtimer();
           if (lane == 0) {
             if (f32_staged) {
               tma_store_2d(&p.tmY, wslot_base, nb, m0w);
@@ -612,7 +627,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             }
           }
           ++wbox;
-          if (tr0) { if (b == p.trace_box) trace[13] = gtimer(); if (b == nboxes - 1) trace[14] = gtimer(); }
+          if (tr0) { if (b == b_lo + p.trace_box) trace[13] = gtimer(); if (b == b_hi - 1) trace[14] = gtimer(); }
         }
       }
     }

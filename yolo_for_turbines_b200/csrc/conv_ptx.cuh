@@ -135,6 +135,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
   return v;
 }
+// Mish with one exp and one fast divide (the form the training kernels use, csrc/train.cu): with n = e^v,
+// m = n (n + 2):  tanh(softplus(v)) = m / (m + 2).  Agrees with the libm form far below one bf16 ulp and is ~10
+// instructions instead of ~60 -- the libm form inlined 64 times made up nine tenths of the conv kernel's code.
+__device__ __forceinline__ float mish_fast(float v) {
+  const float n = __expf(fminf(v, 20.f));
+  const float m = n * (n + 2.f);
+  return v > 20.f ? v : v * __fdividef(m, m + 2.f);  // NaN stays NaN
+}
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
