@@ -140,6 +140,8 @@ int yolo_conv_fwd_stem(const void* plan_host, const float* x_nchw, uint32_t* sta
 /* tile configuration chosen by plan_init: info8 = block_n, block_k, stages, tiles_n, tiles_m,
  * impl (1|2), CTAs per cluster, launched CTAs */
 int yolo_conv_plan_info(const void* plan_host, int32_t* info8);
+/* DEV TOOL: co-resident clusters of `cluster_size` CTAs of the 256-wide pair kernel (SM stranding per cluster size). */
+int yolo_conv_max_clusters(int cluster_size, int* max_clusters);
 /* DEV TOOL (scripts/conv_trace.py): yolo_conv_fwd with 32 x uint64 %globaltimer stamps / counters per launched CTA written to
  * trace_dev: [0] entry, [1] prologue done, [2] griddepcontrol.wait returned, [3] first TMA load issued,
  * [4] first operand stage landed, [5] last MMA committed, [6] first accumulator ready, [7] epilogue drained,

@@ -419,6 +419,7 @@ def test_trainer_state_dict_round_trip():
     ref_opt = torch.optim.SGD([p for p in a.parameters() if p.requires_grad], lr=1e-3, momentum=0.9, weight_decay=5e-4)
     assert set(opt_sd["param_groups"][0]) >= set(ref_opt.state_dict()["param_groups"][0])   # torch.optim.SGD layout
     ref_opt.load_state_dict({k: v for k, v in opt_sd.items() if k != "steps_done"})         # torch accepts it
+    m_saved = tr_a.flat_m.clone()
     tr_a.step(xs, ts)
     torch.cuda.synchronize()
     want = {k: p.detach().clone() for k, p in a.named_parameters()}
@@ -428,8 +429,17 @@ def test_trainer_state_dict_round_trip():
     b = b.cuda().train()
     tr_b = Trainer(b, orc.TURBINE_ANCHORS, lr=0.5, momentum=0.0)     # wrong hyper-parameters: the state dict fixes them
     tr_b.load_state_dict(opt_sd)
-    assert tr_b.steps_done == 2 and tr_b.momentum == 0.9 and tr_b.lr == 1e-3
+    assert tr_b.steps_done == 2 and tr_b.momentum == 0.9 and tr_b.lr == 1e-3 and tr_b.weight_decay == 5e-4
+    assert torch.equal(tr_b.flat_m[: tr_b.n_trainable], m_saved[: tr_a.n_trainable])   # momentum restored bit for bit
+    before = {k: p.detach().clone() for k, p in b.named_parameters()}
     tr_b.step(xs, ts)
     torch.cuda.synchronize()
-    for k, p in b.named_parameters():   # same kernels, same inputs; only fp32 atomics order differs
-        assert torch.allclose(p.detach(), want[k], rtol=2e-3, atol=2e-5), k
+    # Same kernels, same inputs: the third step of both runs applies p -= lr (mu buf + g + wd p) with the same buf.
+    # Gradients of a batch-2 / 64x64 step are only reproducible up to the order of fp32 atomics amplified through
+    # batch-statistics BatchNorm, so the comparison is per tensor on the UPDATE, loosely -- a lost momentum buffer
+    # (update = lr g instead of lr (0.9 buf + g)) or a reset step count changes it by far more.
+    for k in ("layers.29.pred_block.1.conv.bias", "layers.22.pred_block.1.conv.bias", "layers.15.pred_block.1.conv.bias"):
+        ub = (dict(b.named_parameters())[k].detach() - before[k]).flatten()
+        ua = (want[k] - before[k]).flatten()
+        cos = float(torch.nn.functional.cosine_similarity(ua, ub, dim=0))
+        assert cos > 0.98 and 0.8 < float(ub.norm() / ua.norm()) < 1.25, (k, cos)

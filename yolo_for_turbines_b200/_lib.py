@@ -55,6 +55,7 @@ SIGNATURES = {
     "yolo_conv_fwd_stats": (_I, [_P, _P, _P, C.POINTER(BnFinalizeDesc), _P]),
     "yolo_conv_fwd_stem": (_I, [_P, _P, _P, _P]),
     "yolo_conv_plan_info": (_I, [_P, C.POINTER(C.c_int32)]),
+    "yolo_conv_max_clusters": (_I, [_I, C.POINTER(_I)]),
     "yolo_conv_fwd_trace": (_I, [_P, _P, _P, _I, _P]),
     "yolo_conv_fwd_simt": (_I, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "yolo_pack_weights": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),

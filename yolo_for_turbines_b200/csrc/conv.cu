@@ -463,6 +463,8 @@ extern "C" int yolo_conv_fwd(const void* plan_host, uint32_t* status, yb_stream_
   return YB_ERR_UNSUPPORTED;
 }
 
+extern "C" int yolo_conv_max_clusters(int cluster_size, int* max_clusters) { return conv2_query_max_clusters(cluster_size, max_clusters); }
+
 extern "C" int yolo_conv_fwd_trace(const void* plan_host, uint32_t* status, unsigned long long* trace_dev, int box,
                                    yb_stream_t stream_) {
   const ConvPlan* pl = static_cast<const ConvPlan*>(plan_host);

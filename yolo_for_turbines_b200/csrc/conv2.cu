@@ -374,18 +374,24 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     const bool res_staged = p.has_residual && !direct;
     int pv = cluster_id, pb = -1;   // (virtual tile, box) the cursor points at; pb < 0: not yet placed in the tile
     uint32_t pk = 0;                                         // boxes whose residual load has been issued
-    // boxes [box_lo, box_hi) of a tile of width w belong to this warp (a one-box tile goes to column half 0)
-    auto box_lo = [&](int w) { const int nb = w / C::BOXC; return nb >= 2 ? chalf * (nb / 2) : 0; };
-    auto box_hi = [&](int w) { const int nb = w / C::BOXC; return nb >= 2 ? (chalf + 1) * (nb / 2) : (chalf == 0 ? nb : 0); };
+    // boxes [box_lo, box_hi) of tile number t (of this CTA) with width w belong to this warp: half of the boxes each;
+    // one-box tiles alternate between the two column-half groups, so that consecutive tiles' epilogues overlap
+    auto box_lo = [&](int w, uint32_t t) { const int nb = w / C::BOXC; return nb >= 2 ? chalf * (nb / 2) : 0; };
+    auto box_hi = [&](int w, uint32_t t) {
+      const int nb = w / C::BOXC;
+      return nb >= 2 ? (chalf + 1) * (nb / 2) : (uint32_t(chalf) == (t & 1u) ? nb : 0);
+    };
+    uint32_t ptl = 0;                  // tile number of the cursor's tile
     auto res_cursor_settle = [&]() {   // skip tiles in which this warp has no rows or no boxes (they use no slots)
       while (pv < p.num_vtiles) {
         int cmt, cn0, cnw;
         decode_tile<BLOCK_N>(p, pv, cmt, cn0, cnw);
-        if ((cmt * NCTA + (int)rank) * BLOCK_M + quad * 32 < p.M && box_lo(cnw) < box_hi(cnw)) {
-          if (pb < 0) pb = box_lo(cnw);
+        if ((cmt * NCTA + (int)rank) * BLOCK_M + quad * 32 < p.M && box_lo(cnw, ptl) < box_hi(cnw, ptl)) {
+          if (pb < 0) pb = box_lo(cnw, ptl);
           break;
         }
         pv += num_clusters;
+        ++ptl;
         pb = -1;
       }
     };
@@ -399,14 +405,14 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         tma_load_2d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, cn0 + pb * C::BOXC, cm0w);
       }
       ++pk;
-      if (++pb == box_hi(cnw)) { pb = -1; pv += num_clusters; res_cursor_settle(); }
+      if (++pb == box_hi(cnw, ptl)) { pb = -1; pv += num_clusters; ++ptl; res_cursor_settle(); }
     };
     if (res_staged) res_cursor_settle();
     for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       int mt, n0, nw;
       decode_tile<BLOCK_N>(p, v, mt, n0, nw);
-      const int b_lo = box_lo(nw), b_hi = box_hi(nw);
+      const int b_lo = box_lo(nw, tl), b_hi = box_hi(nw, tl);
       const int m0w = (mt * NCTA + (int)rank) * BLOCK_M + quad * 32;
       const int m = m0w + lane;
       const bool valid = m < p.M;
@@ -826,6 +832,27 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   pl->smem_bytes = smem;
   pl->grid_x = tiles_n;
   pl->grid_y = tiles_m;
+  return YB_OK;
+}
+
+// DEV: how many clusters of `cluster` CTAs of the 256x64 pair kernel can be co-resident (SM stranding by cluster size)
+int conv2_query_max_clusters(int cluster, int* out) {
+  auto kern = k_conv_v2<256, 64, 2, false>;
+  const int smem = Cfg<256, 64, 2>::smem_bytes(5, 0);
+  YB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (cluster > 8) YB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(cluster * 148));
+  cfg.blockDim = dim3(CONV2_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  YB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(out, kern, &cfg));
   return YB_OK;
 }
 

@@ -88,4 +88,5 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
 int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats = nullptr,
                  const BnFinalize* fin = nullptr, unsigned int* fin_counter = nullptr,
                  unsigned long long* trace = nullptr, int trace_box = 0);
+int conv2_query_max_clusters(int cluster, int* out);
 int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status, cudaStream_t stream);
