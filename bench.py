@@ -95,6 +95,14 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def workload_config(args, world: int) -> dict:
+    """The `config` object of the JSON line: identical for this arm and for `--impl reference` (the reference arm runs
+    a bounded sample of the SAME workload; what the sample was goes into its cpu_baseline.sample)."""
+    which = {(416, 64): "BASELINE configs[1]", (608, 32): "BASELINE configs[2]"}.get((args.size, args.batch), "custom")
+    return {"workload": f"YOLOv3-{args.size} COCO-{args.classes}cls random-init, batch {args.batch}/GPU, conf {args.conf} "
+                        f"iou {args.iou} ({which})", "global_batch": args.batch * world, "parallelism": f"dp{world}"}
+
+
 def nms_launch_count(batch: int) -> int:
     img_passes = 0 if batch <= 1 else ((max(batch - 1, 1).bit_length() + 7) // 8)
     sort = (4 + img_passes) * 3
@@ -102,11 +110,52 @@ def nms_launch_count(batch: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------ CPU
-def cpu_reference_step(sd, x, nc, conf, iou_thr, anchors):
-    """The reference's own path on host cores (oracle port of model.py:172, utils.py:86,150)."""
-    from oracle import yolo_oracle as orc
+_REF = {}
 
-    return orc.detect(sd, x, anchors, iou_thr, conf, nc, "leaky_relu", "center")
+
+def _reference_modules():
+    """The UNMODIFIED reference (baseline/_ref/code, else /root/reference/code) through the oracle loader, or None."""
+    if "mods" not in _REF:
+        _REF["mods"] = None
+        try:
+            from oracle import ref_loader
+
+            if ref_loader.available():
+                _REF["mods"] = ref_loader.load()
+        except Exception as e:  # a broken copy must not take the bench down: fall back to the port and say so
+            _REF["error"] = f"{type(e).__name__}: {e}"
+    return _REF["mods"]
+
+
+def cpu_reference_kind() -> str:
+    return "reference" if _reference_modules() is not None else "port"
+
+
+def cpu_reference_step(sd, x, nc, conf, iou_thr, anchors):
+    """The reference's own path on host cores: YOLOv3.forward (model.py:172), cells_to_boxes x3 (utils.py:86, head
+    tensors cloned first because it mutates them), non_max_suppression per image (utils.py:150) -- the reference's
+    own functions when a copy is present (kind "reference"), else the oracle port of exactly these (kind "port")."""
+    mods = _reference_modules()
+    if mods is None:
+        from oracle import yolo_oracle as orc
+
+        return orc.detect(sd, x, anchors, iou_thr, conf, nc, "leaky_relu", "center")
+    rmodel, rutils = mods[0], mods[1]
+    key = ("model", nc)
+    if key not in _REF:
+        m = rmodel.YOLOv3(num_classes=nc).eval()
+        m.load_state_dict(sd)
+        _REF[key] = m
+    m = _REF[key]
+    with torch.no_grad():
+        outs = m(x)
+        per_image = [[] for _ in range(x.shape[0])]
+        for i, o in enumerate(outs):
+            s_ = o.shape[2]
+            a = torch.tensor([*anchors[i]]) * s_
+            for b, rows in enumerate(rutils.cells_to_boxes(o.clone(), a, s_, is_pred=True)):
+                per_image[b] += rows
+        return [rutils.non_max_suppression(rows, iou_thr, conf, "center") for rows in per_image]
 
 
 def default_init_state_dict(nc: int, seed: int = 0):
@@ -139,14 +188,13 @@ def run_reference_arm(args):
         cpu_reference_step(sd, xs[i % 2], args.classes, args.conf, args.iou, cfg.ANCHORS)
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
-    line = {"impl": "reference", "metric": "yolov3_416_images_per_sec_fwd_decode_nms", "value": val, "unit": "images/s",
+    line = {"impl": "reference", "metric": f"yolov3_{args.size}_images_per_sec_fwd_decode_nms", "value": val, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"YOLOv3-{args.size} nc{args.classes} conf {args.conf} iou {args.iou}: "
-                                   f"{sample}-image sample per step of the batch-{args.batch} workload, CPU"},
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{sample} images/step x {args.steps} steps, torch intra-op threads "
-                                       f"{torch.get_num_threads()} of {os.cpu_count()} cpus"},
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": cpu_reference_kind(),
+                             "sample": f"{sample}-image sample per step of the batch-{args.batch} workload x {args.steps} steps, "
+                                       f"torch intra-op threads {torch.get_num_threads()} of {os.cpu_count()} cpus"},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -278,6 +326,139 @@ def run_train_workload(args, dev, dist, rank, world, local):
         dist.destroy_process_group()
 
 
+def stage_train_step(args, dev, dist, rank, world):
+    """BASELINE configs[3] beside the headline: the turbine model's training step (fwd + YOLOLoss + bwd + gradient
+    all-reduce + SGD), batch 32 per GPU at 416^2, Mish.  At N >= 2 the same steps are timed a second time with the
+    all-reduce disabled: the difference is the communication time the overlap does NOT hide.  Also checks that the
+    replicas hold bit-identical parameters after the exchanged steps (the data-parallel invariant)."""
+    import numpy as np
+
+    from yolo_for_turbines_b200 import config as cfg
+    from yolo_for_turbines_b200.dataset import encode_targets
+    from yolo_for_turbines_b200.model import YOLOv3
+    from yolo_for_turbines_b200.train import Trainer
+
+    B, S, steps = 32, 416, 8
+    torch.manual_seed(0)
+    model = YOLOv3(num_classes=2, activation="mish").to(dev).train()
+    tr = Trainer(model, cfg.TURBINE_ANCHORS, lr=1e-4, momentum=0.9, weight_decay=5e-4)
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    xs = [torch.rand(B, 3, S, S, generator=g, device=dev) for _ in range(2)]
+    rng = np.random.default_rng(100 + rank)
+    tgs = []
+    for _ in range(2):
+        boxes = []
+        for _ in range(B):
+            wh = rng.uniform(0.02, 0.6, (8, 2))
+            xy = rng.uniform(wh / 2, 1 - wh / 2)
+            boxes.append(np.concatenate([np.minimum(xy, 0.999999), wh, rng.integers(0, 2, (8, 1)).astype(np.float64)], axis=1))
+        tgs.append(encode_targets(boxes, cfg.TURBINE_ANCHORS, image_size=S, device=dev))
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(n):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            tr.step(xs[i % 2], tgs[i % 2])
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1) / n
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(4):
+        tr.step(xs[i % 2], tgs[i % 2])
+    ms_with = statistics.median(timed(steps) for _ in range(3))
+    out = {"workload": f"YOLOv3-{S} turbine model (2 classes, mish) training step, batch {B}/GPU (BASELINE configs[3])",
+           "ms_per_step": ms_with, "images_per_sec": B * world / (ms_with / 1e3), "allreduce_bytes": int(tr.n_trainable) * 4 if world > 1 else 0,
+           "launches_per_step": tr.launches_per_step(tr.plan(B, S, S))}
+    if world > 1:
+        ref = tr.flat_p.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([int(torch.equal(ref, tr.flat_p))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        out["replicas_bit_identical"] = bool(int(same.item()))
+        kernels = {}
+        try:   # which NCCL kernel carries the exchange (names only; this pass is outside every timed region)
+            from torch.profiler import ProfilerActivity, profile
+
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                tr.step(xs[0], tgs[0])
+                torch.cuda.synchronize(dev)
+            for ev in prof.key_averages():
+                if "nccl" in ev.key.lower():
+                    kernels[ev.key[:96]] = {"calls": int(ev.count), "device_ms": float(getattr(ev, "device_time_total", getattr(ev, "cuda_time_total", 0.0))) / 1e3}
+        except Exception as e:
+            kernels = {"error": f"{type(e).__name__}: {e}"}
+        out["nccl_kernels_one_step"] = kernels
+        saved = tr.world
+        tr.world = 1                      # same step without the exchange (replicas diverge: measured last)
+        for i in range(2):
+            tr.step(xs[i % 2], tgs[i % 2])
+        ms_without = statistics.median(timed(steps) for _ in range(3))
+        tr.world = saved
+        out["ms_per_step_without_allreduce"] = ms_without
+        out["exposed_comm_ms"] = max(0.0, ms_with - ms_without)
+    del tr, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def stage_map_gather(args, dev, dist, rank, world, model, cfg):
+    """The one exchange of the evaluation path (utils.py:193 consumes the whole data set): every rank detects its
+    shard of a small common image set (conf 0.01), the [img, box, score, cls] rows are all-gathered over NCCL
+    (parallel.gather_rows) and calc_mAP runs on the union.  Checked against calc_mAP over all images computed locally
+    (every rank can: the set is seeded), which must give the identical value."""
+    from yolo_for_turbines_b200.parallel import distributed_mAP, shard_range
+    from yolo_for_turbines_b200.utils import Detector, calc_mAP
+
+    n_img, S = 8 * max(world, 1), 416
+    gen = torch.Generator().manual_seed(2024)
+    imgs = torch.rand(n_img, 3, S, S, generator=gen)
+    gg = torch.Generator().manual_seed(7)
+    gts = torch.cat([torch.cat([torch.full((20, 1), float(i)), torch.rand(20, 2, generator=gg), 0.05 + 0.35 * torch.rand(20, 2, generator=gg),
+                                torch.ones(20, 1), torch.randint(0, args.classes, (20, 1), generator=gg).float()], dim=1) for i in range(n_img)])
+    det = Detector(model, cfg.ANCHORS, args.iou, 0.01, "center")
+
+    def rows_of(lo, hi):
+        out = []
+        for i0 in range(lo, hi, 8):
+            res, plan = det(imgs[i0:min(i0 + 8, hi)].to(dev))
+            for b, r in enumerate(res.kept_rows()):
+                r = r[torch.argsort(r[:, 4], descending=True, stable=True)[:300]]   # 300 best per image keeps the exchange small
+                out.append(torch.cat([torch.full((r.shape[0], 1), float(i0 + b), device=dev), r], dim=1))
+            plan.check_status()
+        return torch.cat(out) if out else torch.zeros(0, 7, device=dev)
+
+    lo, hi = shard_range(n_img, rank, world)
+    local = rows_of(lo, hi)
+    gl = gts[(gts[:, 0] >= lo) & (gts[:, 0] < hi)].to(dev)
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    m_dist = float(distributed_mAP(local, gl, 0.5, "center", args.classes))
+    torch.cuda.synchronize(dev)
+    ms = 1e3 * (time.perf_counter() - t0)
+    full = rows_of(0, n_img)
+    m_one = float(calc_mAP(full, gts.to(dev), 0.5, "center", args.classes))
+    n_rows = torch.tensor([local.shape[0]], device=dev)
+    if dist is not None:
+        dist.all_reduce(n_rows)
+    return {"images": n_img, "detections_gathered": int(n_rows.item()), "bytes_gathered": int(n_rows.item()) * 28,
+            "ms_gather_plus_mAP": ms, "mAP_distributed": m_dist, "mAP_single_process": m_one,
+            "equal": bool(abs(m_dist - m_one) <= 1e-7), "collective": "all_gather (NCCL)" if world > 1 else "none (one rank)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -298,6 +479,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=4,
                     help="independent detector pipelines (buffers + CUDA graph + stream) that consecutive batches alternate "
                          "between, so one batch's input conversion / decode / NMS overlaps the next batch's convs")
+    ap.add_argument("--windows", type=int, default=5, help="timed windows of `steps` steps each; the median is reported")
+    ap.add_argument("--no-extra-stages", action="store_true", help="skip the train-step / mAP-gather stage records")
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--conv-impl", type=int, default=0)
@@ -376,36 +559,45 @@ def main():
     kept_total = int(res.wait().keep_off[-1].item())
     for i in range(40):  # a second of steady load so that clocks / power state are the sustained ones
         res, plan = det(xs[i % nbuf])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        res, plan = det(xs[i % nbuf])
-    det.join(dev)   # the timing stream waits for every lane
-    e1.record()
-    barrier()
-    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    # `--windows` timed windows of EXACTLY `steps` steps each, every one bracketed by barrier + synchronize on both sides
+    # and reduced with MAX over ranks; the reported step time is the MEDIAN window (a 20-step window is ~0.1 s: single
+    # windows move by a few percent with the power state, which round 1's e2e > value inversion showed).
+    win_dev = []
+    for _ in range(max(1, args.windows)):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            res, plan = det(xs[i % nbuf])
+        det.join(dev)   # the timing stream waits for every lane
+        e1.record()
+        barrier()
+        win_dev.append(max_over_ranks(e0.elapsed_time(e1)))
+    ms_dev = statistics.median(win_dev)
     plan.check_status()
 
     # ---- conv-only time (roofline numerator): the plan's 75 conv launches, eager, event-timed ----
     plan._launch_input(xs[0])
     torch.cuda.synchronize(dev)
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     conv_steps = max(3, min(args.steps, 10))
     if plan.graph is not None:
         plan.graph.replay()
     torch.cuda.synchronize(dev)
-    c0.record()
-    for _ in range(conv_steps):
-        if plan.stem_direct:
-            plan._launch_input(xs[0])  # the fused stem conv reads the image itself and lives outside the graph
-        if plan.graph is not None:
-            plan.graph.replay()      # the captured graph holds exactly the remaining conv launches
-        else:
-            plan._launch_convs()
-    c1.record()
-    torch.cuda.synchronize(dev)
-    ms_conv = c0.elapsed_time(c1) / conv_steps
+    win_conv = []
+    for _ in range(max(1, args.windows)):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(conv_steps):
+            if plan.stem_direct:
+                plan._launch_input(xs[0])  # the fused stem conv reads the image itself and lives outside the graph
+            if plan.graph is not None:
+                plan.graph.replay()      # the captured graph holds exactly the remaining conv launches
+            else:
+                plan._launch_convs()
+        c1.record()
+        torch.cuda.synchronize(dev)
+        win_conv.append(c0.elapsed_time(c1) / conv_steps)
+    ms_conv = statistics.median(win_conv)
 
     # ---- stage timings that explain the step: decode (HBM roofline) and the NMS pipeline (boxes/s) -----
     from yolo_for_turbines_b200.utils import batched_nms, decode_boxes, _scaled_anchors
@@ -441,6 +633,13 @@ def main():
 
     ms_decode = timed_graph(run_decode)
     ms_nms = timed_graph(run_nms)
+    cand_all = stt["cand"].view(-1, 6)
+    passing = cand_all[:, 4].double() > args.conf
+    img_of = torch.arange(cand_all.shape[0], device=dev) // n_cand
+    grp = (img_of * max(args.classes, 1) + cand_all[:, 5].long().clamp(0, max(args.classes, 1) - 1))[passing]
+    cnt = torch.bincount(grp, minlength=1).double()
+    n_pass, n_pairs = int(passing.sum().item()), float((cnt * (cnt - 1) / 2).sum().item())
+    n_kept = int(stt["ws"].keep_off[-1].item())
 
     # ---- end to end from pinned host memory through the public API ------------------------------
     # Every step: H2D copy of that step's pinned fp32 batch, model forward + decode + NMS through
@@ -506,15 +705,26 @@ def main():
         return d2h
 
     e2e_run(2 * D + 1)
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    d2h = e2e_run(args.steps)
-    t1.record()
-    barrier()
-    ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+    win_e2e, d2h = [], 0
+    for _ in range(max(1, args.windows)):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        d2h = e2e_run(args.steps)
+        t1.record()
+        barrier()
+        win_e2e.append(max_over_ranks(t0.elapsed_time(t1)))
+    ms_e2e = statistics.median(win_e2e)
     clocks = sampler.finish()
+    extra = {}
+    if not args.no_extra_stages:
+        for name, fn in (("map_gather", lambda: stage_map_gather(args, dev, dist, rank, world, model, cfg)),
+                         ("train_step", lambda: stage_train_step(args, dev, dist, rank, world))):
+            try:
+                extra[name] = fn()
+            except Exception as e:   # a stage record must never take the headline line down
+                extra[name] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         pk = peaks()
@@ -523,31 +733,41 @@ def main():
         gflop = algorithmic_gflop(S, args.classes)
         achieved = gflop * B / ms_conv  # GFLOP/ms == TFLOP/s
         line = {
-            "metric": "yolov3_416_images_per_sec_fwd_decode_nms", "value": value, "unit": "images/s",
+            "metric": f"yolov3_{S}_images_per_sec_fwd_decode_nms", "value": value, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"YOLOv3-{S} COCO-{args.classes}cls random-init, batch {B}/GPU, conf {args.conf} "
-                                   f"iou {args.iou} (BASELINE configs[1])", "global_batch": B * world,
-                       "parallelism": f"dp{world}", "candidates_per_image": n_cand, "kept_last_step": kept_total,
-                       "lanes": args.lanes,
-                       "l2": f"{nbuf} rotating input batches of {B * 3 * S * S * 4 / 1e6:.0f} MB + "
-                             f"{plan.total_bytes / 1e9:.2f} GB of activations per step exceed the 126 MB L2"},
+            "config": workload_config(args, world),
+            "timing": {"windows": len(win_dev), "statistic": "median window of `steps` steps, max over ranks per window",
+                       "ms_per_window": win_dev, "ms_per_window_e2e": win_e2e, "ms_per_conv_pass": win_conv},
+            "workload_facts": {"candidates_per_image": n_cand, "kept_last_step": kept_total, "lanes": args.lanes,
+                               "l2": f"{nbuf} rotating input batches of {B * 3 * S * S * 4 / 1e6:.0f} MB + "
+                                     f"{plan.total_bytes / 1e9:.2f} GB of activations per step exceed the 126 MB L2"},
             "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
                     "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": (plan.launches_per_forward + 3 + nms_launch_count(B)) * args.steps,
             "roofline": {"bound": "tensor", "kernel": "k_conv_v2 (75 launches per step)",
-                         "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16_sustained"], "frac_of_burst_peak": achieved / pk["bf16"],
-                         "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                         "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["bf16"], "frac_of_sustained_peak": achieved / pk["bf16_sustained"],
+                         "peak_source": pk["source"] + " bf16_tflops (burst; SURVEY 8d / BASELINE.md 4 prescribe it for the conv "
+                                                       "kernels; the sustained figure is " + f"{pk['bf16_sustained']:.1f})",
                          "ms_per_step_conv": ms_conv, "conv_share_of_step": ms_conv / (ms_dev / args.steps),
-                         "traffic": conv_traffic_per_launch(S, args.classes, B)},
+                         "traffic": conv_traffic_per_launch(S, args.classes, B),
+                         "traffic_source": "replayed: dram__bytes_read+write per conv launch from the committed ncu capture "
+                                           "of this workload (profiles/conv_traffic.json), not measured in this run"},
             "clocks": clocks,
             "stages": {
                 "nms": {"ms_per_step": ms_nms, "candidates_per_sec": B * n_cand / (ms_nms / 1e3), "unit": "boxes/s",
-                        "note": "K4 threshold compaction + K5 sorts + K6 greedy NMS on the step's own candidates"},
+                        "thresholded": n_pass, "kept": n_kept, "iou_pairs_upper_bound": n_pairs,
+                        "iou_pair_evals_per_sec": n_pairs / (ms_nms / 1e3),
+                        "hbm_bytes_algorithmic": 24 * n_pass + 4 * n_kept,
+                        "hbm_frac": (24 * n_pass + 4 * n_kept) / (ms_nms / 1e3) / 1e9 / pk["hbm"],
+                        "note": "K4 threshold compaction + K5 sorts + K6 greedy NMS on the step's own candidates; pairs = "
+                                "sum over (image, class) groups of n(n-1)/2 thresholded boxes (SURVEY 8d); the 28 B per box "
+                                "HBM figure makes this stage pair-test / latency bound, not bandwidth bound"},
                 "decode": {"ms_per_step": ms_decode, "achieved_gbs": B * n_cand * ((5 + args.classes) * 4 + 24) / ms_decode / 1e6,
                            "peak_gbs": pk["hbm"], "frac": B * n_cand * ((5 + args.classes) * 4 + 24) / ms_decode / 1e6 / pk["hbm"],
                            "bound": "hbm", "bytes_per_candidate": (5 + args.classes) * 4 + 24},
+                **extra,
             },
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -560,7 +780,7 @@ def main():
                 cpu_reference_step(sd, xc, args.classes, args.conf, args.iou, cfg.ANCHORS)
             dtc = time.perf_counter() - tc
             line["cpu_baseline"] = {"value": args.cpu_images * args.cpu_steps / dtc, "unit": "images/s",
-                                    "cores": torch.get_num_threads(), "kind": "port",
+                                    "cores": torch.get_num_threads(), "kind": cpu_reference_kind(),
                                     "sample": f"{args.cpu_images * args.cpu_steps} images of the same workload "
                                               f"({dtc:.1f} s; torch threads {torch.get_num_threads()}, os.cpu_count {os.cpu_count()})"}
         print(json.dumps(line), flush=True)
