@@ -109,6 +109,11 @@ typedef struct yolo_conv_desc {
    *                  of layer i; griddepcontrol.wait orders every global access after the previous launch);
    * tail_split_hint  cut the tiles of a last round that is at most half full into two half-width tiles.        */
   int32_t pdl_hint, tail_split_hint;
+  /* row_hint: 0 auto | 1 off | 2 on with the smem descriptor's base_offset field set to the tap (A/B of the two
+   * readings of the descriptor format).  Row-window mode: 3x3 layers whose weights fit shared memory (the early,
+   * L2-bandwidth-bound layers) load every filter row once per output-row segment and take the column taps as shifted
+   * views of that tile, and keep the weights resident: ~2.5x less L2 -> SM traffic than nine im2col loads per tile.   */
+  int32_t row_hint;
 } yolo_conv_desc;
 
 /* Size of the opaque, caller-owned plan blob (64-byte aligned storage).       */
@@ -138,7 +143,7 @@ int yolo_conv_fwd_stats(const void* plan_host, uint32_t* status, double* sums2c,
 /* Fused stem launch: x_nchw = (B,3,H,W) fp32; also ORs YB_STATUS_NAN_INPUT (model.py:175).               */
 int yolo_conv_fwd_stem(const void* plan_host, const float* x_nchw, uint32_t* status, yb_stream_t stream);
 /* tile configuration chosen by plan_init: info8 = block_n, block_k, stages, tiles_n, tiles_m,
- * impl (1|2), CTAs per cluster, launched CTAs */
+ * impl (1 | 2 | 3 = persistent kernel in row-window mode), CTAs per cluster, launched CTAs */
 int yolo_conv_plan_info(const void* plan_host, int32_t* info8);
 /* DEV TOOL: co-resident clusters of `cluster_size` CTAs of the 256-wide pair kernel (SM stranding per cluster size). */
 int yolo_conv_max_clusters(int cluster_size, int* max_clusters);

@@ -17,7 +17,7 @@ REL = 2.0 ** -7
 
 def _run_case(B, H, cin, cout, k, stride, act="leaky_relu", residual=False, upsample=False, fp32=False,
               a_mode=0, block_n=0, stages=0, in_pitch=None, out_pitch=None, seed=0, also_simt=True, impl=0, pair=0,
-              pdl=0, split=0, launches=1):
+              pdl=0, split=0, launches=1, row=0, W=None, expect_impl=None):
     from yolo_for_turbines_b200._lib import ACT_CODES, ConvDesc, lib, ptr, stream_ptr
     from yolo_for_turbines_b200.engine import make_conv_plan
 
@@ -26,12 +26,14 @@ def _run_case(B, H, cin, cout, k, stride, act="leaky_relu", residual=False, upsa
     cpad = (cout + 31) // 32 * 32
     in_pitch = in_pitch or cin
     out_pitch = out_pitch or cpad
-    x = torch.randn(B, H, H, in_pitch, generator=g).bfloat16()
+    W = W or H
+    x = torch.randn(B, H, W, in_pitch, generator=g).bfloat16()
     w = (torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k)) ** 0.5)
     scale = 0.5 + torch.rand(cout, generator=g)
     bias = 0.2 * torch.randn(cout, generator=g)
     Ho = (H + 2 * pad - k) // stride + 1
-    res = torch.randn(B, Ho, Ho, cpad, generator=g).bfloat16() if residual else None
+    Wo = (W + 2 * pad - k) // stride + 1
+    res = torch.randn(B, Ho, Wo, cpad, generator=g).bfloat16() if residual else None
 
     # oracle arithmetic: fp32 conv on the bf16-rounded operands
     xr = x[..., :cin].float().permute(0, 3, 1, 2)
@@ -54,28 +56,33 @@ def _run_case(B, H, cin, cout, k, stride, act="leaky_relu", residual=False, upsa
     sd, bd = sc.to(dev), bi.to(dev)
     rd = res.to(dev).contiguous() if residual else None
     Hy = Ho * (2 if upsample else 1)
+    Wy = Wo * (2 if upsample else 1)
     odt = torch.float32 if fp32 else torch.bfloat16
     status = torch.zeros(1, dtype=torch.int32, device=dev)
 
     d = ConvDesc()
-    d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch = B, H, H, cin, in_pitch
+    d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch = B, H, W, cin, in_pitch
     d.c_out, d.c_out_pad, d.out_pitch = cout, cpad, out_pitch
     d.ksize, d.stride, d.pad, d.act = k, stride, pad, ACT_CODES[act]
     d.has_residual, d.res_pitch = int(residual), cpad
     d.upsample2x, d.out_fp32, d.check_nan = int(upsample), int(fp32), 1
     d.a_mode, d.block_n_hint, d.stages_hint = a_mode, block_n, stages
     d.impl_hint, d.cta_pair_hint = impl, pair
-    d.pdl_hint, d.tail_split_hint = pdl, split
+    d.pdl_hint, d.tail_split_hint, d.row_hint = pdl, split, row
 
     outs = {}
-    yd = torch.full((B, Hy, Hy, out_pitch), 7.0, dtype=odt, device=dev)
+    yd = torch.full((B, Hy, Wy, out_pitch), 7.0, dtype=odt, device=dev)
     plan = make_conv_plan(d, ptr(xd), ptr(wd), ptr(sd), ptr(bd), ptr(rd), ptr(yd))
+    if expect_impl is not None:
+        info = (C.c_int32 * 8)()
+        lib.yolo_conv_plan_info(plan[1], info)
+        assert info[5] == expect_impl, f"plan chose impl {info[5]}, expected {expect_impl}" 
     for _ in range(launches):   # back-to-back launches of one plan: the programmatic-dependent-launch chain
         lib.yolo_conv_fwd(plan[1], ptr(status), stream_ptr())
     torch.cuda.synchronize()
     outs["tcgen05"] = yd.float().cpu()
     if also_simt:
-        ys = torch.full((B, Hy, Hy, out_pitch), 7.0, dtype=odt, device=dev)
+        ys = torch.full((B, Hy, Wy, out_pitch), 7.0, dtype=odt, device=dev)
         lib.yolo_conv_fwd_simt(C.byref(d), ptr(xd), ptr(wd), ptr(sd), ptr(bd), ptr(rd), ptr(ys), ptr(status), stream_ptr())
         torch.cuda.synchronize()
         outs["simt"] = ys.float().cpu()
@@ -88,7 +95,7 @@ def _run_case(B, H, cin, cout, k, stride, act="leaky_relu", residual=False, upsa
         cos = F.cosine_similarity(got.flatten(), ref.flatten(), dim=0)
         if bool(bad.any()) or cos < 0.9999:
             idx = torch.nonzero(bad)
-            rows = torch.unique(idx[:, 0] * Hy * Hy + idx[:, 1] * Hy + idx[:, 2]) if idx.numel() else idx
+            rows = torch.unique(idx[:, 0] * Hy * Wy + idx[:, 1] * Wy + idx[:, 2]) if idx.numel() else idx
             raise AssertionError(
                 f"{name}: max err {float(err.max()):.4g}, cos {float(cos):.6f}, bad {int(bad.sum())}/{bad.numel()}, "
                 f"first bad idx {idx[:5].tolist()}, bad pixel rows%128 {sorted(set((rows % 128).tolist()))[:16]}, "
@@ -163,6 +170,31 @@ def test_tail_split_and_pdl_switches():
     _run_case(B=40, H=13, cin=64, cout=512, k=3, stride=1, residual=True, also_simt=False, launches=2)
     _run_case(B=40, H=13, cin=64, cout=512, k=3, stride=1, residual=True, also_simt=False, split=1)
     _run_case(B=24, H=26, cin=64, cout=128, k=3, stride=1, act="mish", also_simt=False)   # bn 128 -> 64-wide halves
+
+
+ROW_CASES = [  # B, H, W, cin, cout, stride, residual  -- shapes the row-window mode takes (w_out >= 64, weights resident)
+    (2, 12, 104, 64, 128, 1, True),     # the 64->128 layers at 104^2: one 104-pixel segment per row
+    (1, 10, 208, 64, 128, 1, False),    # two segments of 104 per row
+    (3, 9, 152, 64, 64, 1, True),       # 608-geometry: two segments of 76; N = 64 (one epilogue box)
+    (2, 16, 80, 64, 128, 2, False),     # stride 2 along H only is not a real layer shape, but exercises h0 = 2 ho - 1 ... (W stride must be 1)
+    (1, 7, 128, 128, 64, 1, False),     # two 64-channel chunks per window, a full 128-pixel segment
+    (5, 3, 64, 64, 128, 1, True),       # odd number of segments: the last pair is ragged
+]
+
+
+@pytest.mark.parametrize("row", [0, 2], ids=["shifted_start", "shifted_start_plus_base_offset"])
+def test_row_window_mode(row):
+    """Row-window mode (resident weights, one TMA window per filter row, column taps as shifted shared-memory views)
+    against the fp32 oracle arithmetic, and against the im2col mode of the same kernel (row_hint = 1).  row = 0 / 2 are
+    the two readings of the shared-memory descriptor for a start address that is not 1024-byte aligned (plain shifted
+    start vs shifted start + base_offset field); the library default is the one that is correct on the hardware."""
+    for B, H, W, cin, cout, stride, res in ROW_CASES:
+        if stride == 2:
+            continue   # plain 3x3/s2 has stride 2 along W: not a row-window shape (covered by the folded case below)
+        a = _run_case(B=B, H=H, W=W, cin=cin, cout=cout, k=3, stride=1, residual=res, row=row, also_simt=False, expect_impl=3,
+                      launches=2)
+        b = _run_case(B=B, H=H, W=W, cin=cin, cout=cout, k=3, stride=1, residual=res, row=1, also_simt=False, expect_impl=2)
+        assert torch.equal(a["tcgen05"], b["tcgen05"]) or float((a["tcgen05"] - b["tcgen05"]).abs().max()) <= 2.0 ** -6
 
 
 def test_nan_layer_flag():
@@ -240,14 +272,16 @@ def test_variants_direct_store_paths(impl, pair):
     _run_case(B=1, H=13, cin=64, cout=64, k=1, stride=1, act="mish", residual=True, impl=impl, pair=pair, also_simt=False)
 
 
-def test_rectangular_geometry_pair_folded_stride2():
+@pytest.mark.parametrize("B,H,W", [(2, 16, 24), (1, 8, 256), (2, 6, 416)])
+def test_rectangular_geometry_pair_folded_stride2(B, H, W):
     """The engine runs the 32->64 3x3/s2 layer on input pixel PAIRS: a 3x2 filter, stride (2,1), left pad 1, right
-    pad 0, Cin' = 64.  Checked against the plain 3x3/s2/p1 convolution on the unfolded tensor."""
+    pad 0, Cin' = 64.  Checked against the plain 3x3/s2/p1 convolution on the unfolded tensor.  The wide cases take
+    the row-window mode of the persistent kernel (one segment of 128 pairs / two of 104), the narrow one im2col."""
     from yolo_for_turbines_b200._lib import ConvDesc, lib, ptr, stream_ptr
     from yolo_for_turbines_b200.engine import make_conv_plan
 
     g = torch.Generator().manual_seed(5)
-    B, H, W, I, O = 2, 16, 24, 32, 64
+    I, O = 32, 64
     x = torch.randn(B, H, W, I, generator=g).bfloat16()
     w = (torch.randn(O, I, 3, 3, generator=g) * (I * 9) ** -0.5).bfloat16().float()
     ref = F.leaky_relu(F.conv2d(x.float().permute(0, 3, 1, 2), w, None, 2, 1), 0.1).permute(0, 2, 3, 1)
@@ -259,14 +293,18 @@ def test_rectangular_geometry_pair_folded_stride2():
     xd = x.cuda()
     sc, bi = torch.ones(O, device="cuda"), torch.zeros(O, device="cuda")
     st = torch.zeros(1, dtype=torch.int32, device="cuda")
-    for impl in (1, 2):
+    wide = W // 2 >= 64
+    for impl, row in ((1, 0), (2, 1), (2, 0)):
         y = torch.zeros(B, H // 2, W // 2, O, dtype=torch.bfloat16, device="cuda")
         d = ConvDesc()
         d.batch, d.h_in, d.w_in, d.c_in, d.in_pitch, d.c_out, d.c_out_pad, d.out_pitch = B, H, W // 2, 2 * I, 2 * I, O, O, O
-        d.ksize, d.stride, d.pad, d.act, d.impl_hint = 3, 2, 1, 1, impl
+        d.ksize, d.stride, d.pad, d.act, d.impl_hint, d.row_hint = 3, 2, 1, 1, impl, row
         d.ksize_w, d.stride_w, d.pad_w_hi_plus1 = 2, 1, 1
         plan = make_conv_plan(d, ptr(xd), ptr(wd), ptr(sc), ptr(bi), None, ptr(y))
+        info = (C.c_int32 * 8)()
+        lib.yolo_conv_plan_info(plan[1], info)
+        assert info[5] == (3 if (impl == 2 and row == 0 and wide) else impl), (impl, row, info[5])
         lib.yolo_conv_fwd(plan[1], ptr(st), stream_ptr())
         torch.cuda.synchronize()
         err = (y.float().cpu() - ref).abs()
-        assert float(err.max()) <= REL * max(1.0, float(ref.abs().max())), (impl, float(err.max()))
+        assert float(err.max()) <= REL * max(1.0, float(ref.abs().max())), (impl, row, float(err.max()))

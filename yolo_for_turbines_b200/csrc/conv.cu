@@ -430,7 +430,7 @@ extern "C" int yolo_conv_plan_init(void* plan_host, size_t plan_bytes, const yol
   pl->stem_direct = 0;
   pl->ncta = 1;
   if (pl->impl == 2) {
-    rc = conv2_plan_setup(pl, d, h_out, w_out, im2col, encTiled, residual, y);
+    rc = conv2_plan_setup(pl, d, h_out, w_out, im2col, encTiled, x, residual, y);
     if (rc) return rc;
   }
   pl->magic = PLAN_MAGIC;
@@ -442,7 +442,7 @@ extern "C" int yolo_conv_plan_info(const void* plan_host, int32_t* info5) {
   YB_REQUIRE(pl && pl->magic == PLAN_MAGIC && info5, "conv plan info: bad plan");
   info5[0] = pl->block_n; info5[1] = pl->kc; info5[2] = pl->impl == 2 ? pl->kp2.stages : pl->kp.stages;
   info5[3] = pl->grid_x; info5[4] = pl->grid_y;
-  info5[5] = pl->impl; info5[6] = pl->ncta; info5[7] = pl->impl == 2 ? pl->grid2 : pl->grid_x * pl->grid_y;
+  info5[5] = (pl->impl == 2 && pl->kp2.row_mode) ? 3 : pl->impl; info5[6] = pl->ncta; info5[7] = pl->impl == 2 ? pl->grid2 : pl->grid_x * pl->grid_y;
   return YB_OK;
 }
 

@@ -46,6 +46,12 @@ struct Cfg {
   static constexpr uint32_t IDESC_HALF = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 4) << 17) |
                                          (uint32_t((BLOCK_M * NCTA) >> 4) << 24);   // tail-split tiles: N = BLOCK_N / 2
   __host__ __device__ static constexpr int NUM_BARS(int stages) { return 2 * stages + 4 + EPI_WARPS * WSLOTS; }
+  // row-window mode: one ring stage = a window of up to 136 input pixels x 64 channels (128-byte rows, 17 swizzle
+  // atoms); the layer's weights (num_kb k-blocks of B_BYTES) sit in front of the ring
+  static constexpr uint32_t ROW_STAGE_BYTES = 136 * 128;
+  static int smem_bytes_row(int stages, int num_kb) {
+    return num_kb * B_BYTES + stages * ROW_STAGE_BYTES + EPI_BYTES + (NUM_BARS(stages) + 1) * 8 + 16 + EPI_WARPS * SCRATCH_BYTES;
+  }
   // ring | epilogue slots | barriers | TMEM slot + last-CTA flag (16 B) | per-warp scale/bias scratch | channel sums.
   // The dynamic segment is 1024-byte aligned (no static shared memory in this kernel; checked at entry).
   static int smem_bytes(int stages, int extra) {
@@ -120,22 +126,29 @@ constexpr int STEM_GATHER_WARPS = 4;  // STEM mode: warps 10..13 build the A til
 // There is no A tensor map: four extra warps gather each output pixel PAIR's 2 x 27 taps straight from the
 // NCHW fp32 input, convert to bf16 and write the 128-byte K-major row (pair-folded layout, 128B swizzle) into
 // the ring; fence.proxy.async hands it to the tensor core.  The NaN-input flag (model.py:175) is raised here.
-template <int BLOCK_N, int KC, int NCTA, bool STEM = false>
+//
+// ROW = true: row-window mode (ConvKParams2::row_mode) for the early 3x3 layers, which are bound by L2 -> SM traffic:
+// resident weights, one TMA window per filter row, column taps as shifted shared-memory views.
+template <int BLOCK_N, int KC, int NCTA, bool STEM = false, bool ROW = false>
 __global__ void __launch_bounds__(CONV2_THREADS + (STEM ? STEM_GATHER_WARPS * 32 : 0), 1)
 k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   using C = Cfg<BLOCK_N, KC, NCTA>;
+  static_assert(!ROW || (KC == 64 && NCTA == 2 && !STEM), "row-window mode: 128-byte rows, CTA pairs");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0u) __trap();  // the 128B-swizzled stages need 1024-byte aligned bases
   const int stages = p.stages;
-  const uint32_t epi_base = smem_base + stages * C::STAGE_BYTES;
+  const uint32_t ring_base = ROW ? smem_base + uint32_t(p.num_kb) * C::B_BYTES : smem_base;   // ROW: weights first
+  const uint32_t stage_bytes = ROW ? C::ROW_STAGE_BYTES : C::STAGE_BYTES;
+  const uint32_t epi_base = ring_base + stages * stage_bytes;
   const uint32_t bar_base = epi_base + C::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (stages + s) * 8; };
   auto tfull_bar = [&](int a) { return bar_base + (2 * stages + a) * 8; };
   auto tempty_bar = [&](int a) { return bar_base + (2 * stages + 2 + a) * 8; };
   auto res_bar = [&](int w, int sl) { return bar_base + (2 * stages + 4 + w * WSLOTS + sl) * 8; };
-  const uint32_t tmem_slot = bar_base + C::NUM_BARS(stages) * 8;
+  const uint32_t wres_bar = bar_base + C::NUM_BARS(stages) * 8;                 // ROW: the resident weights have landed
+  const uint32_t tmem_slot = bar_base + (C::NUM_BARS(stages) + (ROW ? 1 : 0)) * 8;
   const uint32_t scratch_base = tmem_slot + 16;
   const uint32_t stats_base = scratch_base + EPI_WARPS * SCRATCH_BYTES;  // training forward: [2 * c_out_pad] fp32 channel sums of this CTA
 
@@ -165,6 +178,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     }
     for (int w = 0; w < EPI_WARPS; ++w)
       for (int sl = 0; sl < WSLOTS; ++sl) mbar_init(res_bar(w, sl), 1);
+    if constexpr (ROW) mbar_init(wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc_n<NCTA>(tmem_slot, C::TMEM_COLS);
@@ -175,6 +189,18 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   unsigned long long* const trace = p.trace ? p.trace + 32 * size_t(blockIdx.x) : nullptr;
   if (trace && threadIdx.x == 0) trace[1] = gtimer();
+  if constexpr (ROW) {
+    // The layer's weights (this CTA's half of every k-block) are parameters, not the previous launch's output: they
+    // are fetched before the dependency wait, i.e. while the previous layer is still draining.
+    if (warp == 0) {
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(wres_bar, uint32_t(p.num_kb) * C::B_BYTES * NCTA);
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_2d_2sm(&p.tmB, wres_bar, smem_base + uint32_t(kb) * C::B_BYTES, kb * KC, (int)rank * C::B_ROWS);
+      }
+      __syncwarp();
+    }
+  }
   if (p.pdl) {
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped
     // the tail of the previous launch in the stream.  The next launch may start its own prologue now; every access
@@ -184,12 +210,42 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
   }
   if (trace && threadIdx.x == 0) trace[2] = gtimer();
+  // ROW: virtual tile v -> this CTA's row segment: (valid, w block, output row = image * h_out + ho)
+  auto row_coords = [&](int v, bool& ok, int& wblk, int& orow) {
+    int seg = v * NCTA + (int)rank;
+    ok = seg < p.row_total;
+    if (!ok) seg = 0;            // peer CTA of a ragged last pair: loads valid data, stores nothing
+    wblk = seg % p.row_nblk;
+    orow = seg / p.row_nblk;
+  };
 
   if (warp == 0) {
     // ===== TMA producer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
     int s = 0, ntiles = 0;
     uint32_t ph = 0;
     unsigned long long wait_ns = 0;
+    if constexpr (ROW) {
+      const int nwin = p.ksize * p.cchunks;   // windows per tile: one per (filter row, 64-channel chunk)
+      for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++ntiles) {
+        bool ok;
+        int wblk, orow;
+        row_coords(v, ok, wblk, orow);
+        const int img = orow / p.row_h_out, ho = orow - img * p.row_h_out;
+        const int w0 = wblk * p.row_wb - p.pad, h0 = ho * p.stride - p.pad;
+        int r = 0, cc = 0;
+        for (int i = 0; i < nwin; ++i) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(full_bar(s), uint32_t(p.row_wb + p.ksize_w - 1) * 128u * NCTA);
+            tma_load_4d_2sm(&p.tmA, full_bar(s), ring_base + s * C::ROW_STAGE_BYTES, cc * KC, w0, h0 + r, img);
+            if (trace && ntiles == 0 && i == 0) trace[3] = gtimer();
+          }
+          __syncwarp();
+          if (++cc == p.cchunks) { cc = 0; ++r; }
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    } else
     for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++ntiles) {
       int mt, n0, nw;
       decode_tile<BLOCK_N>(p, v, mt, n0, nw);
@@ -247,8 +303,41 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       int s = 0;
       uint32_t ph = 0, tl = 0;
       unsigned long long wfull_ns = 0, wacc_ns = 0;
-      const uint64_t adesc0 = make_kmajor_desc<C::ROW_BYTES>(smem_base);
-      const uint64_t bdesc0 = make_kmajor_desc<C::ROW_BYTES>(smem_base + C::A_BYTES);
+      const uint64_t adesc0 = make_kmajor_desc<C::ROW_BYTES>(ROW ? ring_base : smem_base);
+      const uint64_t bdesc0 = make_kmajor_desc<C::ROW_BYTES>(ROW ? smem_base : smem_base + C::A_BYTES);
+      if constexpr (ROW) {
+        mbar_wait(wres_bar, 0);   // resident weights
+        tc_fence_after();
+        const int nwin = p.ksize * p.cchunks;
+        for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
+          const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+          mbar_wait(tempty_bar(acc), aph ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          int r = 0, cc = 0;
+          for (int i = 0; i < nwin; ++i) {
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            if (trace && tl == 0 && i == 0 && lane == 0) trace[4] = gtimer();
+            if (elect_one()) {
+              const uint64_t soff = uint64_t((uint32_t(s) * C::ROW_STAGE_BYTES) >> 4);
+              for (int st = 0; st < p.ksize_w; ++st) {
+                // column tap st = the same window, st pixels (128-byte rows) further: a shifted descriptor start
+                const uint64_t a_tap = adesc0 + soff + uint64_t(8 * st) + (p.row_bo ? (uint64_t(st) << 49) : 0ull);
+                const uint64_t b_tap = bdesc0 + uint64_t(((uint32_t)((r * p.ksize_w + st) * p.cchunks + cc) * C::B_BYTES) >> 4);
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k)
+                  umma_bf16_n<NCTA>(d_tmem, a_tap + uint64_t(2 * k), b_tap + uint64_t(2 * k), C::IDESC, (i | st | k) != 0 ? 1u : 0u);
+              }
+              umma_commit_n<NCTA>(empty_bar(s));
+              if (i == nwin - 1) umma_commit_n<NCTA>(tfull_bar(acc));
+            }
+            __syncwarp();
+            if (++cc == p.cchunks) { cc = 0; ++r; }
+            if (++s == stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      } else
       for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
         const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
         const uint32_t idesc = v < p.t_full ? C::IDESC : C::IDESC_HALF;
@@ -382,11 +471,21 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       return nb >= 2 ? (chalf + 1) * (nb / 2) : (uint32_t(chalf) == (t & 1u) ? nb : 0);
     };
     uint32_t ptl = 0;                  // tile number of the cursor's tile
+    // does this warp own valid output rows in virtual tile v?  (ROW: a row segment of row_wb pixels, else 128 GEMM rows)
+    auto warp_rows_valid = [&](int v, int cmt) {
+      if constexpr (ROW) {
+        bool ok; int wb_, or_;
+        row_coords(v, ok, wb_, or_);
+        return ok && quad * 32 < p.row_wb;
+      } else {
+        return (cmt * NCTA + (int)rank) * BLOCK_M + quad * 32 < p.M;
+      }
+    };
     auto res_cursor_settle = [&]() {   // skip tiles in which this warp has no rows or no boxes (they use no slots)
       while (pv < p.num_vtiles) {
         int cmt, cn0, cnw;
         decode_tile<BLOCK_N>(p, pv, cmt, cn0, cnw);
-        if ((cmt * NCTA + (int)rank) * BLOCK_M + quad * 32 < p.M && box_lo(cnw, ptl) < box_hi(cnw, ptl)) {
+        if (warp_rows_valid(pv, cmt) && box_lo(cnw, ptl) < box_hi(cnw, ptl)) {
           if (pb < 0) pb = box_lo(cnw, ptl);
           break;
         }
@@ -402,7 +501,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       const uint32_t cslot = pk % WSLOTS;
       if (lane == 0) {
         mbar_expect_tx(res_bar(ew, cslot), C::WBOX_BYTES);
-        tma_load_2d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, cn0 + pb * C::BOXC, cm0w);
+        if constexpr (ROW) {
+          bool ok; int wb_, or_;
+          row_coords(pv, ok, wb_, or_);
+          tma_load_4d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, cn0 + pb * C::BOXC, quad * 32, wb_, or_);
+        } else {
+          tma_load_2d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, cn0 + pb * C::BOXC, cm0w);
+        }
       }
       ++pk;
       if (++pb == box_hi(cnw, ptl)) { pb = -1; pv += num_clusters; ++ptl; res_cursor_settle(); }
@@ -415,8 +520,15 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       const int b_lo = box_lo(nw, tl), b_hi = box_hi(nw, tl);
       const int m0w = (mt * NCTA + (int)rank) * BLOCK_M + quad * 32;
       const int m = m0w + lane;
-      const bool valid = m < p.M;
-      const bool wvalid = m0w < p.M;
+      bool valid = m < p.M;
+      bool wvalid = m0w < p.M;
+      int row_wblk = 0, row_orow = 0;
+      if constexpr (ROW) {   // rows of this tile = pixels quad*32 + lane of one output-row segment
+        bool ok;
+        row_coords(v, ok, row_wblk, row_orow);
+        wvalid = ok && quad * 32 < p.row_wb;
+        valid = ok && quad * 32 + lane < p.row_wb;
+      }
       const bool tr0 = trace != nullptr && ew == 0 && tl == 0 && lane == 0;
       // this tile's per-column scale / bias, fetched while the accumulator is still being produced: lane l holds
       // columns n0 + 32 i + l; chunk 0 is handed to the scratch per 32-column step and the registers rotate
@@ -602,7 +714,8 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
               tma_store_2d(&p.tmY, wslot_base, nb, m0w);
               if constexpr (C::BOXC == 64) tma_store_2d(&p.tmY, wslot_base + 4096u, nb + 32, m0w);
             } else {
-              tma_store_2d(&p.tmY, slot_addr, nb, m0w);  // rows >= M are clipped by the tensor map
+              if constexpr (ROW) tma_store_4d(&p.tmY, slot_addr, nb, quad * 32, row_wblk, row_orow);  // pixels >= row_wb clipped
+              else tma_store_2d(&p.tmY, slot_addr, nb, m0w);  // rows >= M are clipped by the tensor map
             }
             bulk_commit_group();
           }
@@ -675,9 +788,9 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   }
 }
 
-template <int BN, int KC, int NCTA, bool STEM = false>
+template <int BN, int KC, int NCTA, bool STEM = false, bool ROW = false>
 int launch2(const ConvPlan* pl, const ConvKParams2& kp, cudaStream_t stream) {
-  auto kern = k_conv_v2<BN, KC, NCTA, STEM>;
+  auto kern = k_conv_v2<BN, KC, NCTA, STEM, ROW>;
   YB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)pl->grid2);
@@ -702,6 +815,10 @@ int smem_for(int ncta, int stages, int extra) {
   return ncta == 2 ? Cfg<BN, KC, 2>::smem_bytes(stages, extra) : Cfg<BN, KC, 1>::smem_bytes(stages, extra);
 }
 
+int smem_bytes_row_v2(int bn, int stages, int num_kb) {
+  return bn == 64 ? Cfg<64, 64, 2>::smem_bytes_row(stages, num_kb) : Cfg<128, 64, 2>::smem_bytes_row(stages, num_kb);
+}
+
 int smem_bytes_v2(int bn, int kc, int ncta, int stages, int extra) {
 #define YB_C2(BN, KC) if (bn == BN && kc == KC) return smem_for<BN, KC>(ncta, stages, extra);
   YB_C2(32, 32) YB_C2(64, 32) YB_C2(128, 32) YB_C2(256, 32) YB_C2(32, 64) YB_C2(64, 64) YB_C2(128, 64) YB_C2(256, 64)
@@ -712,7 +829,7 @@ int smem_bytes_v2(int bn, int kc, int ncta, int stages, int extra) {
 }  // namespace
 
 int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out, int im2col, PFN_encodeTiled encTiled,
-                     const void* residual, void* y) {
+                     const void* x, const void* residual, void* y) {
   const int kc = pl->kc;
   const bool stem = d->stem_c > 0;
   // default: a cta_group::2 pair (measured faster or equal on every YOLOv3 layer); 1 forces single CTAs
@@ -755,8 +872,41 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
     }
   }
 
+  // ---- row-window mode (ConvKParams2::row_mode): 3x3 layers whose whole weight tensor fits beside the ring ----------
+  int row_mode = 0, row_wb = 0, row_nblk = 1, row_stages = 0, row_smem = 0;
+  {
+    const int kw = yb_kw(d);
+    const bool shape_ok = !stem && ncta == 2 && kc == 64 && d->ksize == 3 && (kw == 3 || kw == 2) && yb_sw(d) == 1 &&
+                          d->pad == 1 && (d->stride == 1 || d->stride == 2) && tiles_n == 1 && (bn == 64 || bn == 128) &&
+                          !direct && !d->out_fp32 && !d->want_stats && d->a_mode == 0 && d->block_n_hint == 0 &&
+                          d->stages_hint == 0 && x != nullptr;
+    if (d->row_hint != 1 && shape_ok) {
+      int nblk = (w_out + 127) / 128;
+      while (nblk <= w_out && (w_out % nblk != 0 || w_out / nblk > 128)) ++nblk;
+      const int wb = nblk <= w_out ? w_out / nblk : 0;
+      int st = 6;
+      while (st > 2 && smem_bytes_row_v2(bn, st, num_kb) > 227 * 1024) --st;
+      // worth it when the window is reasonably full (the MMA always runs 128 rows) and at least 3 windows are in flight
+      if (wb >= 64 && st >= 3 && smem_bytes_row_v2(bn, st, num_kb) <= 227 * 1024) {
+        row_mode = 1; row_wb = wb; row_nblk = nblk; row_stages = st; row_smem = smem_bytes_row_v2(bn, st, num_kb);
+      }
+    }
+  }
+  if (row_mode) { t_full = num_vtiles = (int)(((long long)d->batch * h_out * row_nblk + 1) / 2); b_half = 0; }
+
   ConvKParams2& kp = pl->kp2;
   kp.tmA = pl->kp.tmA;  // same A geometry as v1 (128-row boxes of KC channels); unused by the stem
+  if (row_mode) {   // input windows: (channel, w, h, image) tiles of 64 x (row_wb + kw - 1) x 1 x 1, zero fill = padding
+    cuuint64_t dims[4] = {(cuuint64_t)d->c_in, (cuuint64_t)d->w_in, (cuuint64_t)d->h_in, (cuuint64_t)d->batch};
+    cuuint64_t strides[3] = {(cuuint64_t)d->in_pitch * 2, (cuuint64_t)d->w_in * d->in_pitch * 2,
+                             (cuuint64_t)d->h_in * d->w_in * d->in_pitch * 2};
+    cuuint32_t box[4] = {64u, (cuuint32_t)(row_wb + yb_kw(d) - 1), 1u, 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = encTiled(&kp.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: row-window tensor map A encode failed (%d)", (int)cr);
+  }
   // weight tile: BLOCK_N / NCTA rows per CTA (two half-height boxes when the tail is split)
   {
     const CUtensorMapSwizzle swz = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -780,6 +930,22 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: fp32 tensor map Y encode failed (%d)", (int)cr);
     kp.tmR = kp.tmY;
+  } else if (row_mode) {   // output / residual: (channel, w in segment, segment, image * h_out + ho), 32-pixel boxes per warp
+    cuuint64_t dims[4] = {(cuuint64_t)d->c_out_pad, (cuuint64_t)row_wb, (cuuint64_t)row_nblk, (cuuint64_t)d->batch * h_out};
+    cuuint32_t box[4] = {(cuuint32_t)boxc, 32u, 1u, 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint64_t ystr[3] = {(cuuint64_t)d->out_pitch * 2, (cuuint64_t)row_wb * d->out_pitch * 2, (cuuint64_t)w_out * d->out_pitch * 2};
+    CUresult cr = encTiled(&kp.tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, ystr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           bswz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: row-window tensor map Y encode failed (%d)", (int)cr);
+    if (d->has_residual) {
+      cuuint64_t rstr[3] = {(cuuint64_t)d->res_pitch * 2, (cuuint64_t)row_wb * d->res_pitch * 2, (cuuint64_t)w_out * d->res_pitch * 2};
+      cr = encTiled(&kp.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(residual), dims, rstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bswz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: row-window tensor map R encode failed (%d)", (int)cr);
+    } else {
+      kp.tmR = kp.tmY;
+    }
   } else if (!direct) {
     cuuint64_t dims[2] = {(cuuint64_t)d->c_out_pad, (cuuint64_t)M};
     cuuint32_t box[2] = {(cuuint32_t)boxc, 32u};  // one epilogue warp's 32 rows
@@ -814,6 +980,9 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   kp.stats = nullptr; kp.c_out_pad = d->c_out_pad; kp.fin_counter = nullptr;
   kp.s2_parity = d->s2_parity; kp.s2_cin = d->s2_cin;
   kp.t_full = t_full; kp.num_vtiles = num_vtiles; kp.b_half = b_half;
+  kp.row_mode = row_mode; kp.row_wb = row_wb; kp.row_nblk = row_nblk; kp.row_h_out = h_out;
+  kp.row_total = d->batch * h_out * row_nblk; kp.row_bo = d->row_hint == 2 ? 1 : 0;
+  if (row_mode) kp.stages = row_stages;
   kp.pdl = d->pdl_hint == 1 ? 0 : 1;
   kp.trace = nullptr; kp.trace_box = 0;
   pl->stem_direct = stem ? 1 : 0;
@@ -829,7 +998,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   pl->grid2 = clusters * ncta;
   pl->ncta = ncta;
   pl->block_n = bn;
-  pl->smem_bytes = smem;
+  pl->smem_bytes = row_mode ? row_smem : smem;
   pl->grid_x = tiles_n;
   pl->grid_y = tiles_m;
   return YB_OK;
@@ -876,6 +1045,12 @@ int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, doub
   kp.trace = trace;
   kp.trace_box = trace_box;
   if (stats && fin && fin_counter) { kp.fin = *fin; kp.fin_counter = fin_counter; }
+  if (kp.row_mode) {
+    if (pl->block_n == 64) return launch2<64, 64, 2, false, true>(pl, kp, stream);
+    if (pl->block_n == 128) return launch2<128, 64, 2, false, true>(pl, kp, stream);
+    yb_set_error("conv v2: no row-window kernel for block_n %d", pl->block_n);
+    return YB_ERR_UNSUPPORTED;
+  }
 #define YB_L2(BN, KC)                                                        \
   if (pl->block_n == BN && pl->kc == KC)                                     \
     return pl->ncta == 2 ? launch2<BN, KC, 2>(pl, kp, stream) : launch2<BN, KC, 1>(pl, kp, stream);

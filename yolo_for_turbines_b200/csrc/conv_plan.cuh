@@ -58,6 +58,12 @@ struct ConvKParams2 {
   // costs half a tile time when at most half of the CTA pairs would have had work (b_half: the weight tensor map
   // then holds half-height boxes and a whole tile issues two of them).
   int t_full, num_vtiles, b_half;
+  // Row-window mode (conv2.cu, template flag ROW): a CTA tile is ONE segment of an output row (row_wb <= 128 pixels,
+  // row_nblk segments per row), the weights of the whole layer stay resident in shared memory and every filter ROW is
+  // loaded once as a window of row_wb + ksize_w - 1 input pixels whose ksize_w column taps are shifted views of the same
+  // shared-memory tile (descriptor start + tap * 128 B).
+  int row_mode, row_wb, row_nblk, row_total;   // row_total = batch * h_out * row_nblk segments
+  int row_h_out, row_bo;                       // row_bo: 1 = also set the descriptor's base_offset field to the tap
   int pdl;              // launched with programmatic stream serialization: griddepcontrol.* brackets the prologue
   unsigned long long* trace;  // dev tool (yolo_conv_fwd_trace): 32 globaltimer stamps / counters per CTA, nullptr otherwise
   int trace_box;              // which epilogue box of the first tile gets the fine-grained stamps
@@ -84,7 +90,7 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
 
 // conv2.cu
 int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out, int im2col, PFN_encodeTiled encTiled,
-                     const void* residual, void* y);
+                     const void* x, const void* residual, void* y);
 int conv2_launch(const ConvPlan* pl, uint32_t* status, cudaStream_t stream, double* stats = nullptr,
                  const BnFinalize* fin = nullptr, unsigned int* fin_counter = nullptr,
                  unsigned long long* trace = nullptr, int trace_box = 0);

@@ -334,7 +334,7 @@ class ForwardPlan:
             d.upsample2x, d.out_fp32, d.check_nan = int(op.upsample), int(op.dst.fp32), int(op.check_nan)
             d.a_mode, d.block_n_hint, d.stages_hint = 0, engine.block_n_hint, engine.stages_hint
             d.impl_hint, d.cta_pair_hint = engine.impl_hint, engine.cta_pair_hint
-            d.pdl_hint, d.tail_split_hint = engine.pdl_hint, engine.tail_split_hint
+            d.pdl_hint, d.tail_split_hint, d.row_hint = engine.pdl_hint, engine.tail_split_hint, engine.row_hint
             x_ptr = sroot.buf.data_ptr() + soff * 2
             if self.stem_direct and op is self.ops[0]:
                 d.stem_c, x_ptr = 3, 0
@@ -419,6 +419,7 @@ class Engine:
         self.block_n_hint, self.stages_hint = 0, 0
         self.impl_hint, self.cta_pair_hint = 0, 0  # 0 = library defaults (include/yolo_b200.h)
         self.pdl_hint, self.tail_split_hint = 0, 0   # 1 switches the feature off (A/B runs, scripts/layer_times.py)
+        self.row_hint = 0                            # include/yolo_b200.h: 0 auto | 1 off | 2 on, base_offset variant
         # fused stem (no patch matrix): correct but not faster yet (gather-warp bound, 0.43 vs 0.22 + 0.24 ms), so opt-in
         self.stem_direct = os.environ.get("YOLO_B200_FUSED_STEM") == "1"
         self.allow_fold = hasattr(model, "layers") and hasattr(model, "num_classes") and os.environ.get("YOLO_B200_NO_FOLD") != "1"
