@@ -109,8 +109,8 @@ typedef struct yolo_conv_desc {
    *                  of layer i; griddepcontrol.wait orders every global access after the previous launch);
    * tail_split_hint  cut the tiles of a last round that is at most half full into two half-width tiles.        */
   int32_t pdl_hint, tail_split_hint;
-  /* row_hint: 0 auto | 1 off | 2 on with the smem descriptor's base_offset field set to the tap (A/B of the two
-   * readings of the descriptor format).  Row-window mode: 3x3 layers whose weights fit shared memory (the early,
+  /* row_hint: 0 auto | 1 off | 2 on with the smem descriptor's base_offset field set to the tap (measured WRONG on
+   * B200: tcgen05 swizzles on absolute shared-memory address bits, the field must stay 0; kept as an A/B switch).  Row-window mode: 3x3 layers whose weights fit shared memory (the early,
    * L2-bandwidth-bound layers) load every filter row once per output-row segment and take the column taps as shifted
    * views of that tile, and keep the weights resident: ~2.5x less L2 -> SM traffic than nine im2col loads per tile.   */
   int32_t row_hint;

@@ -1,4 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python scripts/box_index.py 2>&1 | tail -1
-timeout 600 python -m pytest tests/test_gpu_conv.py -q -m gpu --tb=short -k "row_window or rectangular" > gpurun_out/r2_c11_row.log 2>&1; echo "row tests exit $?"; tail -n 40 gpurun_out/r2_c11_row.log | cut -c1-400
+for id in "tests/test_gpu_conv.py::test_row_window_mode[shifted_start_plus_base_offset]" "tests/test_gpu_conv.py::test_row_window_mode[shifted_start]" "tests/test_gpu_conv.py::test_rectangular_geometry_pair_folded_stride2[2-16-24]" "tests/test_gpu_conv.py::test_rectangular_geometry_pair_folded_stride2[1-8-256]"; do
+  echo "=== $id"
+  timeout 300 python -m pytest "$id" -q -m gpu --tb=short -x 2>&1 | grep -E "passed|failed|Error|error|assert|bad " | head -8 | cut -c1-500
+done

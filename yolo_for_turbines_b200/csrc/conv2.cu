@@ -50,7 +50,7 @@ struct Cfg {
   // atoms); the layer's weights (num_kb k-blocks of B_BYTES) sit in front of the ring
   static constexpr uint32_t ROW_STAGE_BYTES = 136 * 128;
   static int smem_bytes_row(int stages, int num_kb) {
-    return num_kb * B_BYTES + stages * ROW_STAGE_BYTES + EPI_BYTES + (NUM_BARS(stages) + 1) * 8 + 16 + EPI_WARPS * SCRATCH_BYTES;
+    return num_kb * B_BYTES + stages * ROW_STAGE_BYTES + EPI_BYTES + (NUM_BARS(stages) + 2) * 8 + 16 + EPI_WARPS * SCRATCH_BYTES;   // +2: keeps the scratch 16-byte aligned
   }
   // ring | epilogue slots | barriers | TMEM slot + last-CTA flag (16 B) | per-warp scale/bias scratch | channel sums.
   // The dynamic segment is 1024-byte aligned (no static shared memory in this kernel; checked at entry).
@@ -148,7 +148,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   auto tempty_bar = [&](int a) { return bar_base + (2 * stages + 2 + a) * 8; };
   auto res_bar = [&](int w, int sl) { return bar_base + (2 * stages + 4 + w * WSLOTS + sl) * 8; };
   const uint32_t wres_bar = bar_base + C::NUM_BARS(stages) * 8;                 // ROW: the resident weights have landed
-  const uint32_t tmem_slot = bar_base + (C::NUM_BARS(stages) + (ROW ? 1 : 0)) * 8;
+  const uint32_t tmem_slot = bar_base + (C::NUM_BARS(stages) + (ROW ? 2 : 0)) * 8;   // 16-byte aligned (ld.shared.v4 scratch behind it)
   const uint32_t scratch_base = tmem_slot + 16;
   const uint32_t stats_base = scratch_base + EPI_WARPS * SCRATCH_BYTES;  // training forward: [2 * c_out_pad] fp32 channel sums of this CTA
 
