@@ -14,6 +14,7 @@
 // Warp roles (192 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer (leader CTA only issues),
 // 2..5 = epilogue (TMEM lane quadrant = warp % 4).
 #include <new>
+#include <type_traits>
 
 #include "conv_plan.cuh"
 #include "conv_ptx.cuh"
@@ -25,6 +26,7 @@ using namespace convptx;
 constexpr int CONV2_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 = two epilogue groups
 constexpr int WSLOTS = 2;           // per-warp ring of 32-row output/residual boxes in shared memory
 constexpr int EPI_WARPS = 8;
+enum { EPI_BF16 = 0, EPI_BF16_RES = 1, EPI_F32 = 2, EPI_DIRECT = 3 };   // epilogue store / residual modes
 constexpr int SCRATCH_BYTES = 256;  // per epilogue warp: scale[32] | bias[32] of the 32 columns being processed
 
 template <int BLOCK_N, int KC, int NCTA>
@@ -129,7 +131,8 @@ constexpr int STEM_GATHER_WARPS = 4;  // STEM mode: warps 10..13 build the A til
 //
 // ROW = true: row-window mode (ConvKParams2::row_mode) for the early 3x3 layers, which are bound by L2 -> SM traffic:
 // resident weights, one TMA window per filter row, column taps as shifted shared-memory views.
-template <int BLOCK_N, int KC, int NCTA, bool STEM = false, bool ROW = false>
+// TRACE = true: the yolo_conv_fwd_trace build (globaltimer stamps); the product instantiations carry none of it.
+template <int BLOCK_N, int KC, int NCTA, bool STEM = false, bool ROW = false, bool TRACE = false>
 __global__ void __launch_bounds__(CONV2_THREADS + (STEM ? STEM_GATHER_WARPS * 32 : 0), 1)
 k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   using C = Cfg<BLOCK_N, KC, NCTA>;
@@ -153,7 +156,9 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   const uint32_t stats_base = scratch_base + EPI_WARPS * SCRATCH_BYTES;  // training forward: [2 * c_out_pad] fp32 channel sums of this CTA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (p.trace && threadIdx.x == 0) p.trace[32 * size_t(blockIdx.x)] = gtimer();
+  if constexpr (TRACE) {
+    if (p.trace && threadIdx.x == 0) p.trace[32 * size_t(blockIdx.x)] = gtimer();
+  }
   if (p.stats != nullptr) {
     for (int i = threadIdx.x; i < 2 * p.c_out_pad; i += blockDim.x)
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(stats_base + 4u * i), "r"(0u) : "memory");
@@ -187,7 +192,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  unsigned long long* const trace = p.trace ? p.trace + 32 * size_t(blockIdx.x) : nullptr;
+  unsigned long long* const trace = (TRACE && p.trace) ? p.trace + 32 * size_t(blockIdx.x) : nullptr;
   if (trace && threadIdx.x == 0) trace[1] = gtimer();
   if constexpr (ROW) {
     // The layer's weights (this CTA's half of every k-block) are parameters, not the previous launch's output: they
@@ -439,6 +444,8 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       if (saw_nan) atomicOr(p.status, YB_STATUS_NAN_INPUT);
     }
   } else {
+    auto run_epilogue = [&](auto em_tag) {
+    constexpr int EM = decltype(em_tag)::value;
     // ===== epilogue: all eight warps work on EVERY tile.  Warp w reads TMEM lane quadrant w % 4 (its 32 rows) and
     // column half (w - 2) / 4 of the tile, so two warps per scheduler share the tile's epilogue and its latency is
     // half of what one group of four needs -- that latency is the tail of every launch and, on the short-K 1x1
@@ -447,9 +454,14 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     const int ew = warp - 2;
     const int chalf = ew >> 2;          // which half of the tile's boxes this warp owns
     const int quad = warp & 3;
-    // fp32 outputs (the scale heads) are staged too: 32-column fp32 boxes (128-byte rows) leave through TMA stores
-    const bool f32_staged = p.out_fp32 && !p.upsample2x && p.s2_parity == 0;
-    const bool direct = p.upsample2x || p.s2_parity != 0;
+    // The store / residual path is a COMPILE-TIME mode of this block (EM), picked once per launch below: the hot loop
+    // then carries no flag tests (ncu: the flag-test version spent ~55 % of its 1 070 instructions per box on them).
+    //   EPI_BF16      bf16 boxes staged in shared memory, TMA stores
+    //   EPI_BF16_RES  + residual boxes TMA-loaded into the same slots (prefetched one box ahead)
+    //   EPI_F32       fp32 boxes (the scale heads): 32-column fp32 boxes through TMA stores
+    //   EPI_DIRECT    per-thread global stores (2x2 upsample replication, stride-2 data-gradient scatter)
+    constexpr bool f32_staged = EM == EPI_F32;
+    constexpr bool direct = EM == EPI_DIRECT;
     const uint32_t wslot_base = epi_base + uint32_t(ew) * WSLOTS * C::WBOX_BYTES;
     const uint32_t scratch = scratch_base + uint32_t(ew) * SCRATCH_BYTES;
     const uint32_t swz = (C::BOX_ROW_BYTES == 128) ? (lane & 7) : ((lane >> 1) & 3);
@@ -460,7 +472,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     // slot.  The cursor runs up to one box ahead of the box being computed -- across tile boundaries, where the
     // loads of the next tile's first two boxes fly while this group waits for its accumulator -- instead of
     // starting every load right before its data is needed (one exposed L2 round trip per box).
-    const bool res_staged = p.has_residual && !direct;
+    constexpr bool res_staged = EM == EPI_BF16_RES;
     int pv = cluster_id, pb = -1;   // (virtual tile, box) the cursor points at; pb < 0: not yet placed in the tile
     uint32_t pk = 0;                                         // boxes whose residual load has been issued
     // boxes [box_lo, box_hi) of tile number t (of this CTA) with width w belong to this warp: half of the boxes each;
@@ -550,7 +562,8 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       size_t out_row[4];
       int n_out_rows = 1;
       out_row[0] = size_t(m);
-      if (p.upsample2x) {
+      if constexpr (!direct) {
+      } else if (p.upsample2x) {
         const int hw = p.h_out * p.w_out;
         const int img = m / hw;
         const int rem = m - img * hw;
@@ -586,7 +599,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         const int nb = n0 + b * C::BOXC;
         if (staged && !res_staged) {
           if (lane == 0) {
-            if (f32_staged) bulk_wait_group_read<0>();   // an fp32 box pair uses both slots: all earlier stores have read
+            if constexpr (f32_staged) bulk_wait_group_read<0>();   // an fp32 box pair uses both slots: all earlier stores have read
             else bulk_wait_group_read<WSLOTS - 1>();  // the TMA store that last used this slot has read it out
           }
           __syncwarp();
@@ -629,16 +642,18 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           if (tr0 && b == b_lo + p.trace_box && h == 0) trace[19] = gtimer();
           size_t drow = size_t(m);   // direct-path addressing: (row, column) of the residual / output element
           int dcol = n;
-          if (p.s2_parity) {
-            const int th = n >= p.s2_cin ? 1 : 0;
-            drow = out_row[0] + th;
-            dcol = n - th * p.s2_cin;
+          if constexpr (direct) {
+            if (p.s2_parity) {
+              const int th = n >= p.s2_cin ? 1 : 0;
+              drow = out_row[0] + th;
+              dcol = n - th * p.s2_cin;
+            }
           }
-          if (p.has_residual) {
+          if (res_staged || (direct && p.has_residual)) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 r;
-              if (!direct) {
+              if constexpr (!direct) {
                 const uint32_t a = row_addr + (((h * 4 + j) ^ swz) << 4);
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
@@ -658,7 +673,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) saw_nan |= (o[j] != o[j]);
           }
-          if (f32_staged) {
+          if constexpr (f32_staged) {
             // half h of the box -> its own 4 KB slot: 32 rows x 32 fp32 (128-byte rows, 128B swizzle)
             const uint32_t fa = wslot_base + uint32_t(h) * 4096u + uint32_t(lane) * 128u;
 #pragma unroll
@@ -666,7 +681,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(fa + ((uint32_t(j) ^ uint32_t(lane & 7)) << 4)),
                            "r"(__float_as_uint(o[4 * j])), "r"(__float_as_uint(o[4 * j + 1])),
                            "r"(__float_as_uint(o[4 * j + 2])), "r"(__float_as_uint(o[4 * j + 3])) : "memory");
-          } else if (!direct) {
+          } else if constexpr (!direct) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t a = row_addr + (((h * 4 + j) ^ swz) << 4);
@@ -710,7 +725,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           __syncwarp();
           if (tr0 && b == b_lo + p.trace_box) trace[12] = gtimer();
           if (lane == 0) {
-            if (f32_staged) {
+            if constexpr (f32_staged) {
               tma_store_2d(&p.tmY, wslot_base, nb, m0w);
               if constexpr (C::BOXC == 64) tma_store_2d(&p.tmY, wslot_base + 4096u, nb + 32, m0w);
             } else {
@@ -719,7 +734,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             }
             bulk_commit_group();
           }
-          if (p.stats != nullptr) {
+          if (EM == EPI_BF16 && p.stats != nullptr) {
             // Training forward (BatchNorm batch statistics, model.py:61 in train mode): column sums of the box just
             // staged, taken from the bf16 values that are actually stored.  Lane l owns the channel pair (2l, 2l+1):
             // one 4-byte word per row, 32 lanes read one 128-byte row -> conflict free.
@@ -753,6 +768,11 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     if (saw_nan) atomicOr(p.status, YB_STATUS_NAN_LAYER);
     if (lane == 0) bulk_wait_group_all();
     if (trace && lane == 0) atomicMax(trace + 7, gtimer());
+    };
+    if (p.upsample2x || p.s2_parity != 0) run_epilogue(std::integral_constant<int, EPI_DIRECT>{});
+    else if (p.out_fp32) run_epilogue(std::integral_constant<int, EPI_F32>{});
+    else if (p.has_residual) run_epilogue(std::integral_constant<int, EPI_BF16_RES>{});
+    else run_epilogue(std::integral_constant<int, EPI_BF16>{});
   }
 
   tc_fence_before();
@@ -790,7 +810,15 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
 
 template <int BN, int KC, int NCTA, bool STEM = false, bool ROW = false>
 int launch2(const ConvPlan* pl, const ConvKParams2& kp, cudaStream_t stream) {
-  auto kern = k_conv_v2<BN, KC, NCTA, STEM, ROW>;
+  auto kern = k_conv_v2<BN, KC, NCTA, STEM, ROW, false>;
+  if (kp.trace != nullptr) {   // dev tool: instantiated for the CTA-pair kernels with 128-byte rows only
+    if constexpr (KC == 64 && NCTA == 2 && !STEM && BN >= 64) {
+      kern = k_conv_v2<BN, KC, NCTA, STEM, ROW, true>;
+    } else {
+      yb_set_error("conv trace: no trace build of this tile configuration (block_n %d, kc %d, ctas %d)", BN, KC, NCTA);
+      return YB_ERR_UNSUPPORTED;
+    }
+  }
   YB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)pl->grid2);
