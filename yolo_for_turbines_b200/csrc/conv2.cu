@@ -117,8 +117,14 @@ __device__ __forceinline__ void decode_tile(const ConvKParams2& p, int v, int& m
     half = u & 1;
     nw = BLOCK_N >> 1;
   }
-  const int nt = t % p.tiles_n;
-  mt = t / p.tiles_n;
+  int nt;
+  if (p.tiles_n_sh >= 0) {   // power-of-two tile counts (all YOLOv3 layers): no integer division on the tile path
+    nt = t & ((1 << p.tiles_n_sh) - 1);
+    mt = t >> p.tiles_n_sh;
+  } else {
+    nt = t % p.tiles_n;
+    mt = t / p.tiles_n;
+  }
   n0 = nt * BLOCK_N + half * nw;
 }
 
@@ -220,8 +226,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     int seg = v * NCTA + (int)rank;
     ok = seg < p.row_total;
     if (!ok) seg = 0;            // peer CTA of a ragged last pair: loads valid data, stores nothing
-    wblk = seg % p.row_nblk;
-    orow = seg / p.row_nblk;
+    if (p.row_nblk_sh >= 0) {
+      wblk = seg & ((1 << p.row_nblk_sh) - 1);
+      orow = seg >> p.row_nblk_sh;
+    } else {
+      wblk = seg % p.row_nblk;
+      orow = seg / p.row_nblk;
+    }
   };
 
   if (warp == 0) {
@@ -465,6 +476,10 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     const uint32_t wslot_base = epi_base + uint32_t(ew) * WSLOTS * C::WBOX_BYTES;
     const uint32_t scratch = scratch_base + uint32_t(ew) * SCRATCH_BYTES;
     const uint32_t swz = (C::BOX_ROW_BYTES == 128) ? (lane & 7) : ((lane >> 1) & 3);
+    uint32_t soff[8];   // byte offset of 16-byte chunk c of this lane's row inside a swizzled box
+#pragma unroll
+    for (int c = 0; c < 8; ++c) soff[c] = (uint32_t(c) ^ swz) << 4;
+    const int act = p.act;
     uint32_t tl = 0, wbox = 0;
     bool saw_nan = false;
     // Residual prefetch cursor.  The residual box of output box k lands in slot k % WSLOTS and is overwritten in
@@ -483,21 +498,24 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       return nb >= 2 ? (chalf + 1) * (nb / 2) : (uint32_t(chalf) == (t & 1u) ? nb : 0);
     };
     uint32_t ptl = 0;                  // tile number of the cursor's tile
-    // does this warp own valid output rows in virtual tile v?  (ROW: a row segment of row_wb pixels, else 128 GEMM rows)
-    auto warp_rows_valid = [&](int v, int cmt) {
-      if constexpr (ROW) {
-        bool ok; int wb_, or_;
-        row_coords(v, ok, wb_, or_);
-        return ok && quad * 32 < p.row_wb;
-      } else {
-        return (cmt * NCTA + (int)rank) * BLOCK_M + quad * 32 < p.M;
-      }
-    };
-    auto res_cursor_settle = [&]() {   // skip tiles in which this warp has no rows or no boxes (they use no slots)
+    int c_n0 = 0, c_bhi = 0, c_a = 0, c_b = 0;   // cached for the cursor's tile: first column, end box, row coords
+    // Settles the cursor on the next tile in which this warp owns valid rows and boxes (others use no slots) and
+    // caches its coordinates: (first GEMM row) or, in row-window mode, (w block, output row).
+    auto res_cursor_settle = [&]() {
       while (pv < p.num_vtiles) {
-        int cmt, cn0, cnw;
-        decode_tile<BLOCK_N>(p, pv, cmt, cn0, cnw);
-        if (warp_rows_valid(pv, cmt) && box_lo(cnw, ptl) < box_hi(cnw, ptl)) {
+        int cmt, cnw;
+        decode_tile<BLOCK_N>(p, pv, cmt, c_n0, cnw);
+        bool rows_ok;
+        if constexpr (ROW) {
+          bool ok;
+          row_coords(pv, ok, c_a, c_b);
+          rows_ok = ok && quad * 32 < p.row_wb;
+        } else {
+          c_a = (cmt * NCTA + (int)rank) * BLOCK_M + quad * 32;
+          rows_ok = c_a < p.M;
+        }
+        c_bhi = box_hi(cnw, ptl);
+        if (rows_ok && box_lo(cnw, ptl) < c_bhi) {
           if (pb < 0) pb = box_lo(cnw, ptl);
           break;
         }
@@ -507,22 +525,16 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       }
     };
     auto res_issue_next = [&]() {      // warp-uniform; the caller guarantees the slot is free
-      int cmt, cn0, cnw;
-      decode_tile<BLOCK_N>(p, pv, cmt, cn0, cnw);
-      const int cm0w = (cmt * NCTA + (int)rank) * BLOCK_M + quad * 32;
       const uint32_t cslot = pk % WSLOTS;
       if (lane == 0) {
         mbar_expect_tx(res_bar(ew, cslot), C::WBOX_BYTES);
-        if constexpr (ROW) {
-          bool ok; int wb_, or_;
-          row_coords(pv, ok, wb_, or_);
-          tma_load_4d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, cn0 + pb * C::BOXC, quad * 32, wb_, or_);
-        } else {
-          tma_load_2d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, cn0 + pb * C::BOXC, cm0w);
-        }
+        if constexpr (ROW)
+          tma_load_4d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, c_n0 + pb * C::BOXC, quad * 32, c_a, c_b);
+        else
+          tma_load_2d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, c_n0 + pb * C::BOXC, c_a);
       }
       ++pk;
-      if (++pb == box_hi(cnw, ptl)) { pb = -1; pv += num_clusters; ++ptl; res_cursor_settle(); }
+      if (++pb == c_bhi) { pb = -1; pv += num_clusters; ++ptl; res_cursor_settle(); }
     };
     if (res_staged) res_cursor_settle();
     for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
@@ -638,7 +650,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
 #pragma unroll
           for (int i = 0; i + 1 < NCH; ++i) { r_sc[i] = r_sc[i + 1]; r_bi[i] = r_bi[i + 1]; }
           __syncwarp();
-          bn_act32(v, o, scratch, p.act);
+          bn_act32(v, o, scratch, act);
           if (tr0 && b == b_lo + p.trace_box && h == 0) trace[19] = gtimer();
           size_t drow = size_t(m);   // direct-path addressing: (row, column) of the residual / output element
           int dcol = n;
@@ -654,7 +666,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             for (int j = 0; j < 4; ++j) {
               uint4 r;
               if constexpr (!direct) {
-                const uint32_t a = row_addr + (((h * 4 + j) ^ swz) << 4);
+                const uint32_t a = row_addr + soff[h * 4 + j];
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
               } else {
@@ -684,7 +696,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           } else if constexpr (!direct) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t a = row_addr + (((h * 4 + j) ^ swz) << 4);
+              const uint32_t a = row_addr + soff[h * 4 + j];
               const uint32_t w0 = pack_bf16(o[8 * j + 0], o[8 * j + 1]), w1 = pack_bf16(o[8 * j + 2], o[8 * j + 3]);
               const uint32_t w2 = pack_bf16(o[8 * j + 4], o[8 * j + 5]), w3 = pack_bf16(o[8 * j + 6], o[8 * j + 7]);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
@@ -1008,6 +1020,8 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   kp.stats = nullptr; kp.c_out_pad = d->c_out_pad; kp.fin_counter = nullptr;
   kp.s2_parity = d->s2_parity; kp.s2_cin = d->s2_cin;
   kp.t_full = t_full; kp.num_vtiles = num_vtiles; kp.b_half = b_half;
+  auto log2_or_neg = [](int v) { int s = 0; while ((1 << s) < v) ++s; return (1 << s) == v ? s : -1; };
+  kp.tiles_n_sh = log2_or_neg(tiles_n); kp.row_nblk_sh = log2_or_neg(row_nblk);
   kp.row_mode = row_mode; kp.row_wb = row_wb; kp.row_nblk = row_nblk; kp.row_h_out = h_out;
   kp.row_total = d->batch * h_out * row_nblk; kp.row_bo = d->row_hint == 2 ? 1 : 0;
   if (row_mode) kp.stages = row_stages;
