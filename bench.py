@@ -583,21 +583,41 @@ def main():
     if plan.graph is not None:
         plan.graph.replay()
     torch.cuda.synchronize(dev)
+
+    def conv_pass():
+        if plan.stem_direct:
+            plan._launch_input(xs[0])  # the fused stem conv reads the image itself and lives outside the graph
+        if plan.graph is not None:
+            plan.graph.replay()      # the captured graph holds exactly the remaining conv launches
+        else:
+            plan._launch_convs()
+
+    # (a) sustained: back-to-back passes right after the long timed loops (power-capped clocks), median window;
+    #     compared with MEASURED_PEAKS' sustained cuBLAS figure (a seconds-long loop under the same cap)
     win_conv = []
     for _ in range(max(1, args.windows)):
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         for _ in range(conv_steps):
-            if plan.stem_direct:
-                plan._launch_input(xs[0])  # the fused stem conv reads the image itself and lives outside the graph
-            if plan.graph is not None:
-                plan.graph.replay()      # the captured graph holds exactly the remaining conv launches
-            else:
-                plan._launch_convs()
+            conv_pass()
         c1.record()
         torch.cuda.synchronize(dev)
         win_conv.append(c0.elapsed_time(c1) / conv_steps)
     ms_conv = statistics.median(win_conv)
+    # (b) burst: single passes after a short idle, best of 10 -- the statistic MEASURED_PEAKS uses for its burst
+    #     cuBLAS figure (best of 10 isolated matmuls), which SURVEY 8d / BASELINE.md 4 prescribe as the denominator
+    burst = []
+    for _ in range(10):
+        torch.cuda.synchronize(dev)
+        time.sleep(0.05)
+        conv_pass()                      # first pass after the idle brings the weights back into L2
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        conv_pass()
+        c1.record()
+        torch.cuda.synchronize(dev)
+        burst.append(c0.elapsed_time(c1))
+    ms_conv_burst = min(burst)
 
     # ---- stage timings that explain the step: decode (HBM roofline) and the NMS pipeline (boxes/s) -----
     from yolo_for_turbines_b200.utils import batched_nms, decode_boxes, _scaled_anchors
@@ -738,7 +758,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world),
             "timing": {"windows": len(win_dev), "statistic": "median window of `steps` steps, max over ranks per window",
-                       "ms_per_window": win_dev, "ms_per_window_e2e": win_e2e, "ms_per_conv_pass": win_conv},
+                       "ms_per_window": win_dev, "ms_per_window_e2e": win_e2e, "ms_per_conv_pass_sustained": win_conv,
+                       "ms_per_conv_pass_burst": burst},
             "workload_facts": {"candidates_per_image": n_cand, "kept_last_step": kept_total, "lanes": args.lanes,
                                "l2": f"{nbuf} rotating input batches of {B * 3 * S * S * 4 / 1e6:.0f} MB + "
                                      f"{plan.total_bytes / 1e9:.2f} GB of activations per step exceed the 126 MB L2"},
@@ -746,11 +767,17 @@ def main():
                     "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": (plan.launches_per_forward + 3 + nms_launch_count(B)) * args.steps,
             "roofline": {"bound": "tensor", "kernel": "k_conv_v2 (75 launches per step)",
-                         "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16"], "frac_of_sustained_peak": achieved / pk["bf16_sustained"],
-                         "peak_source": pk["source"] + " bf16_tflops (burst; SURVEY 8d / BASELINE.md 4 prescribe it for the conv "
-                                                       "kernels; the sustained figure is " + f"{pk['bf16_sustained']:.1f})",
-                         "ms_per_step_conv": ms_conv, "conv_share_of_step": ms_conv / (ms_dev / args.steps),
+                         "achieved": gflop * B / ms_conv_burst, "peak": pk["bf16"], "unit": "TFLOP/s",
+                         "frac": gflop * B / ms_conv_burst / pk["bf16"],
+                         "statistic": "burst vs burst: one pass of the 75 conv launches after a 50 ms idle, best of 10 -- the "
+                                      "statistic of MEASURED_PEAKS' bf16_tflops (best of 10 isolated cuBLAS GEMMs)",
+                         "ms_per_step_conv": ms_conv_burst,
+                         "sustained": {"achieved": achieved, "peak": pk["bf16_sustained"], "frac": achieved / pk["bf16_sustained"],
+                                       "frac_of_burst_peak": achieved / pk["bf16"], "ms_per_step_conv": ms_conv,
+                                       "statistic": "median window of back-to-back passes right after the timed loops "
+                                                    "(power-capped clocks) vs bf16_tflops_sustained"},
+                         "peak_source": pk["source"],
+                         "conv_share_of_step": ms_conv / (ms_dev / args.steps),
                          "traffic": conv_traffic_per_launch(S, args.classes, B),
                          "traffic_source": "replayed: dram__bytes_read+write per conv launch from the committed ncu capture "
                                            "of this workload (profiles/conv_traffic.json), not measured in this run"},
