@@ -132,56 +132,27 @@ def test_standalone_blocks_match_reference_shapes():
     assert sp(torch.rand(2, 512, 13, 13).cuda()).shape == (2, 3, 13, 13, 7)
 
 
-def test_fused_stem_path_matches_default_path():
-    """The opt-in fused stem (conv kernel gathers the 3x3x3 taps from the NCHW image) must agree with the default
-    patch-matrix path bit for bit: same bf16 operands, same fp32 accumulation order inside one K=64 block."""
-    m, sd = _model(2, "leaky_relu", 4)
-    x = torch.rand(2, 3, 96, 96, generator=torch.Generator().manual_seed(3)).cuda()
-    a = m(x)
-    eng = m._engine(x.device)
-    eng.stem_direct = True
-    eng.plans.clear()
-    b = m(x)
-    assert m._engine(x.device).plans[(2, 96, 96)].stem_direct
-    for u, v in zip(a, b):
-        assert torch.equal(u, v)
-    xn = x.clone()
-    xn[1, 2, 95, 95] = float("nan")
-    with pytest.raises(AssertionError):
-        m(xn)
-
-
-def test_detector_lanes_give_identical_results():
-    """Detector(lanes=2) alternates batches between two independent pipelines on their own streams; every result must
-    equal the single-lane result for the same input (kept rows bit for bit), also when results are read late."""
-    from oracle import yolo_oracle as orc
-    from yolo_for_turbines_b200.model import YOLOv3
-    from yolo_for_turbines_b200.utils import Detector
-
-    torch.manual_seed(3)
-    m = YOLOv3(num_classes=2).eval().cuda()
-    xs = [torch.rand(3, 3, 96, 96, device="cuda") for _ in range(6)]
-    single = Detector(m, orc.TURBINE_ANCHORS, 0.45, 0.4, "center")
-    ref = []
-    for x in xs:
-        res, plan = single(x)
-        ref.append([r.clone() for r in res.kept_rows()])
-        plan.check_status()
-    multi = Detector(m, orc.TURBINE_ANCHORS, 0.45, 0.4, "center", lanes=2)
-    for rounds in range(2):   # round 1: eager + capture, round 2: graph replays
-        pending = []
-        for i, x in enumerate(xs):
-            res, plan = multi(x)
-            pending.append((i, res, plan))
-            if len(pending) == 2:   # read each result one call late: its lane is reused only after this
-                j, r, p = pending.pop(0)
-                got = r.kept_rows()
-                p.check_status()
-                assert len(got) == len(ref[j]) and all(torch.equal(a, b) for a, b in zip(got, ref[j])), (rounds, j)
-        for j, r, p in pending:
-            got = r.kept_rows()
-            assert all(torch.equal(a, b) for a, b in zip(got, ref[j])), (rounds, j)
-    multi.join()
+def test_fused_stem_path_matches_patch_matrix_path():
+    """The fused stem (default: TMA image windows, taps built in shared memory) must agree with the patch-matrix path
+    (yolo_input_patchify + K=64 GEMM) bit for bit: same bf16 operands, same fp32 accumulation order inside one K=64
+    block.  Sizes cover one / two / four row segments per image row (96, 416, 608) and the NaN-input flag."""
+    for size, bsz in ((96, 2), (416, 1), (608, 1)):
+        m, sd = _model(2, "leaky_relu", 4)
+        x = torch.rand(bsz, 3, size, size, generator=torch.Generator().manual_seed(3)).cuda()
+        a = m(x)
+        eng = m._engine(x.device)
+        assert eng.plans[(bsz, size, size)].stem_direct
+        eng.stem_direct = False
+        eng.plans.clear()
+        b = m(x)
+        assert not m._engine(x.device).plans[(bsz, size, size)].stem_direct
+        for u, v in zip(a, b):
+            assert torch.equal(u, v), size
+    m, _ = _model(2, "leaky_relu", 4)
+    x = torch.rand(1, 3, 96, 96)
+    x[0, 2, 95, 95] = float("nan")
+    with pytest.raises(AssertionError):   # model.py:175 through the fused stem's own check
+        m(x.cuda())
 
 
 def test_forward_608_matches_oracle():

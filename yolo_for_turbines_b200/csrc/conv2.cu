@@ -129,11 +129,14 @@ __device__ __forceinline__ void decode_tile(const ConvKParams2& p, int v, int& m
 }
 
 constexpr int STEM_GATHER_WARPS = 4;  // STEM mode: warps 10..13 build the A tile from the fp32 NCHW image
+constexpr int STEM_IMG_STAGES = 6;    // STEM mode: ring of TMA-loaded image windows (3 channels x 3 rows x (2 wb + 2) pixels, fp32)
 
-// STEM = true: the network's first conv (Cin = 3, 3x3/s1/p1) without the patch-matrix round trip through HBM.
-// There is no A tensor map: four extra warps gather each output pixel PAIR's 2 x 27 taps straight from the
-// NCHW fp32 input, convert to bf16 and write the 128-byte K-major row (pair-folded layout, 128B swizzle) into
-// the ring; fence.proxy.async hands it to the tensor core.  The NaN-input flag (model.py:175) is raised here.
+// STEM = true: the network's first conv (Cin = 3, 3x3/s1/p1) straight from the NCHW fp32 image -- no patch matrix in HBM.
+// A tile is one segment of an output row (row_wb pixel PAIRS, as in row-window mode).  Warp 0 TMA-loads the segment's
+// 3 channels x 3 rows x (2 row_wb + 2) pixels window (zero fill = padding) into a ring; four gather warps turn each
+// pixel pair's 2 x 27 taps into the 128-byte K-major row of the pair-folded GEMM (bf16, 128B swizzle) in the A ring;
+// fence.proxy.async hands it to the tensor core; the 64 x 64 weight tile is resident.  NaN inputs raise the status
+// flag here (model.py:175).
 //
 // ROW = true: row-window mode (ConvKParams2::row_mode) for the early 3x3 layers, which are bound by L2 -> SM traffic:
 // resident weights, one TMA window per filter row, column taps as shifted shared-memory views.
@@ -143,21 +146,28 @@ __global__ void __launch_bounds__(CONV2_THREADS + (STEM ? STEM_GATHER_WARPS * 32
 k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   using C = Cfg<BLOCK_N, KC, NCTA>;
   static_assert(!ROW || (KC == 64 && NCTA == 2 && !STEM), "row-window mode: 128-byte rows, CTA pairs");
+  static_assert(!STEM || (KC == 64 && NCTA == 1 && BLOCK_N == 64), "stem mode: pair-folded 3->32 GEMM, single CTA");
+  constexpr bool ROWTILES = ROW || STEM;   // tiles are output-row segments (row_coords), stores use the 4-D map
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0u) __trap();  // the 128B-swizzled stages need 1024-byte aligned bases
   const int stages = p.stages;
-  const uint32_t ring_base = ROW ? smem_base + uint32_t(p.num_kb) * C::B_BYTES : smem_base;   // ROW: weights first
-  const uint32_t stage_bytes = ROW ? C::ROW_STAGE_BYTES : C::STAGE_BYTES;
-  const uint32_t epi_base = ring_base + stages * stage_bytes;
+  // ROW / STEM: the resident weights come first; STEM: the A ring is followed by the image-window ring
+  const uint32_t ring_base = (ROW || STEM) ? smem_base + uint32_t(p.num_kb) * C::B_BYTES : smem_base;
+  const uint32_t stage_bytes = ROW ? C::ROW_STAGE_BYTES : (STEM ? C::A_BYTES : C::STAGE_BYTES);
+  const uint32_t img_base = ring_base + stages * stage_bytes;
+  const uint32_t epi_base = img_base + (STEM ? STEM_IMG_STAGES * uint32_t(p.stem_img_bytes) : 0u);
   const uint32_t bar_base = epi_base + C::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (stages + s) * 8; };
   auto tfull_bar = [&](int a) { return bar_base + (2 * stages + a) * 8; };
   auto tempty_bar = [&](int a) { return bar_base + (2 * stages + 2 + a) * 8; };
   auto res_bar = [&](int w, int sl) { return bar_base + (2 * stages + 4 + w * WSLOTS + sl) * 8; };
-  const uint32_t wres_bar = bar_base + C::NUM_BARS(stages) * 8;                 // ROW: the resident weights have landed
-  const uint32_t tmem_slot = bar_base + (C::NUM_BARS(stages) + (ROW ? 2 : 0)) * 8;   // 16-byte aligned (ld.shared.v4 scratch behind it)
+  const uint32_t wres_bar = bar_base + C::NUM_BARS(stages) * 8;                 // ROW / STEM: the resident weights have landed
+  auto img_full_bar = [&](int i) { return wres_bar + 16 + i * 8; };              // STEM: image window i has landed
+  auto img_empty_bar = [&](int i) { return wres_bar + 16 + (STEM_IMG_STAGES + i) * 8; };
+  constexpr int EXTRA_BARS = ROW ? 2 : (STEM ? 2 + 2 * STEM_IMG_STAGES : 0);     // even: keeps the scratch 16-byte aligned
+  const uint32_t tmem_slot = bar_base + (C::NUM_BARS(stages) + EXTRA_BARS) * 8;
   const uint32_t scratch_base = tmem_slot + 16;
   const uint32_t stats_base = scratch_base + EPI_WARPS * SCRATCH_BYTES;  // training forward: [2 * c_out_pad] fp32 channel sums of this CTA
 
@@ -180,7 +190,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     tma_prefetch_desc(&p.tmY);
     if (p.has_residual) tma_prefetch_desc(&p.tmR);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar(s), STEM ? 1 + STEM_GATHER_WARPS : 1);  // + one arrive per gather warp
+      mbar_init(full_bar(s), STEM ? STEM_GATHER_WARPS : 1);  // STEM: one arrive per gather warp, no TMA bytes
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -189,7 +199,13 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     }
     for (int w = 0; w < EPI_WARPS; ++w)
       for (int sl = 0; sl < WSLOTS; ++sl) mbar_init(res_bar(w, sl), 1);
-    if constexpr (ROW) mbar_init(wres_bar, 1);
+    if constexpr (ROW || STEM) mbar_init(wres_bar, 1);
+    if constexpr (STEM) {
+      for (int i = 0; i < STEM_IMG_STAGES; ++i) {
+        mbar_init(img_full_bar(i), 1);
+        mbar_init(img_empty_bar(i), STEM_GATHER_WARPS);
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc_n<NCTA>(tmem_slot, C::TMEM_COLS);
@@ -200,6 +216,15 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   unsigned long long* const trace = (TRACE && p.trace) ? p.trace + 32 * size_t(blockIdx.x) : nullptr;
   if (trace && threadIdx.x == 0) trace[1] = gtimer();
+  if constexpr (STEM) {
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_expect_tx(wres_bar, C::B_BYTES);
+        tma_load_2d(&p.tmB, wres_bar, smem_base, 0, 0);
+      }
+      __syncwarp();
+    }
+  }
   if constexpr (ROW) {
     // The layer's weights (this CTA's half of every k-block) are parameters, not the previous launch's output: they
     // are fetched before the dependency wait, i.e. while the previous layer is still draining.
@@ -240,7 +265,23 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     int s = 0, ntiles = 0;
     uint32_t ph = 0;
     unsigned long long wait_ns = 0;
-    if constexpr (ROW) {
+    if constexpr (STEM) {
+      int si = 0;
+      uint32_t iph = 0;
+      for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++ntiles) {
+        bool ok;
+        int wblk, orow;
+        row_coords(v, ok, wblk, orow);
+        const int img = orow / p.row_h_out, ho = orow - img * p.row_h_out;
+        mbar_wait(img_empty_bar(si), iph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(img_full_bar(si), uint32_t(p.stem_boxw) * 9u * 4u);
+          tma_load_4d(&p.tmA, img_full_bar(si), img_base + si * uint32_t(p.stem_img_bytes), 2 * wblk * p.row_wb - 1, ho - 1, 0, img);
+        }
+        __syncwarp();
+        if (++si == STEM_IMG_STAGES) { si = 0; iph ^= 1u; }
+      }
+    } else if constexpr (ROW) {
       const int nwin = p.ksize * p.cchunks;   // windows per tile: one per (filter row, 64-channel chunk)
       for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++ntiles) {
         bool ok;
@@ -319,9 +360,30 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       int s = 0;
       uint32_t ph = 0, tl = 0;
       unsigned long long wfull_ns = 0, wacc_ns = 0;
-      const uint64_t adesc0 = make_kmajor_desc<C::ROW_BYTES>(ROW ? ring_base : smem_base);
-      const uint64_t bdesc0 = make_kmajor_desc<C::ROW_BYTES>(ROW ? smem_base : smem_base + C::A_BYTES);
-      if constexpr (ROW) {
+      const uint64_t adesc0 = make_kmajor_desc<C::ROW_BYTES>((ROW || STEM) ? ring_base : smem_base);
+      const uint64_t bdesc0 = make_kmajor_desc<C::ROW_BYTES>((ROW || STEM) ? smem_base : smem_base + C::A_BYTES);
+      if constexpr (STEM) {
+        mbar_wait(wres_bar, 0);   // resident weights
+        tc_fence_after();
+        for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
+          const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+          mbar_wait(tempty_bar(acc), aph ^ 1u);
+          tc_fence_after();
+          mbar_wait(full_bar(s), ph);   // the gather warps have written (and proxy-fenced) this A tile
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t soff = uint64_t((uint32_t(s) * C::A_BYTES) >> 4);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k)
+              umma_bf16_n<NCTA>(tmem_base + acc * BLOCK_N, adesc0 + soff + uint64_t(2 * k), bdesc0 + uint64_t(2 * k), C::IDESC,
+                                k != 0 ? 1u : 0u);
+            umma_commit_n<NCTA>(empty_bar(s));
+            umma_commit_n<NCTA>(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+      } else if constexpr (ROW) {
         mbar_wait(wres_bar, 0);   // resident weights
         tc_fence_after();
         const int nwin = p.ksize * p.cchunks;
@@ -394,39 +456,36 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
   } else if (STEM && warp >= 2 + EPI_WARPS) {
     // ===== STEM gather warps: one thread per A row = one output pixel pair =====
     if constexpr (STEM) {
-      const int gr = (warp - 2 - EPI_WARPS) * 32 + lane;
-      const int W = p.stem_w, H = p.stem_h, W2 = W >> 1;
-      const size_t plane = size_t(H) * W;
-      int s = 0;
-      uint32_t ph = 0;
+      const int gr = (warp - 2 - EPI_WARPS) * 32 + lane;   // A row = pixel pair gr of the tile's row segment
+      int s = 0, si = 0;
+      uint32_t ph = 0, iph = 0;
       bool saw_nan = false;
-      for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
-        const int m = (t / p.tiles_n) * BLOCK_M + gr;  // pixel-pair index (tiles_n == 1 for the stem)
+      const bool in_seg = gr < p.row_wb;
+      for (int v = cluster_id; v < p.num_vtiles; v += num_clusters) {
+        mbar_wait(img_full_bar(si), iph);
         mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t row_addr = smem_base + s * C::STAGE_BYTES + gr * 128;
-        const bool valid = m < p.M;
-        const int b = valid ? m / (H * W2) : 0;
-        const int rem = valid ? m - b * (H * W2) : 0;
-        const int i = rem / W2, j0 = (rem - i * W2) * 2;
-        const float* xb = p.stem_x + size_t(b) * 3 * plane;
-        // the pair's two 3x3 windows span columns j0-1 .. j0+2: 9 (row, channel) lines of [left | mid.x mid.y | right],
-        // all loads issued before any use (one memory round trip per tile)
+        const uint32_t row_addr = ring_base + s * C::A_BYTES + gr * 128;
+        // window layout: [channel][filter row][stem_boxw floats], column 0 = pixel 2 * segment start - 1; the pair's two
+        // 3x3 windows span columns 2 gr .. 2 gr + 3 (two 8-byte loads per line, conflict free across the warp)
+        const uint32_t wbase = img_base + si * uint32_t(p.stem_img_bytes) + uint32_t(2 * gr) * 4u;
         float xv[3][3][4];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
-            const int ii = i + kh - 1;
-            const bool rin = valid && ii >= 0 && ii < H;
-            const float* line = xb + size_t(c) * plane + size_t(rin ? ii : 0) * W + j0;
-            const float2 mid = rin ? __ldg(reinterpret_cast<const float2*>(line)) : make_float2(0.f, 0.f);
-            xv[c][kh][0] = (rin && j0 > 0) ? __ldg(line - 1) : 0.f;
-            xv[c][kh][1] = mid.x;
-            xv[c][kh][2] = mid.y;
-            xv[c][kh][3] = (rin && j0 + 2 < W) ? __ldg(line + 2) : 0.f;
+            const uint32_t a = wbase + uint32_t((c * 3 + kh) * p.stem_boxw) * 4u;
+            if (in_seg) {
+              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(xv[c][kh][0]), "=f"(xv[c][kh][1]) : "r"(a));
+              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(xv[c][kh][2]), "=f"(xv[c][kh][3]) : "r"(a + 8u));
+            } else {
+              xv[c][kh][0] = xv[c][kh][1] = xv[c][kh][2] = xv[c][kh][3] = 0.f;
+            }
           }
           saw_nan |= (xv[c][1][1] != xv[c][1][1]) | (xv[c][1][2] != xv[c][1][2]);  // each image element checked once
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(img_empty_bar(si));   // this warp has read the window
+        if (++si == STEM_IMG_STAGES) { si = 0; iph ^= 1u; }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float v[32];
@@ -473,6 +532,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     //   EPI_DIRECT    per-thread global stores (2x2 upsample replication, stride-2 data-gradient scatter)
     constexpr bool f32_staged = EM == EPI_F32;
     constexpr bool direct = EM == EPI_DIRECT;
+    const bool up_coalesced = direct && C::BOXC == 64 && p.upsample2x && !p.out_fp32;   // bf16 2x2 upsample store
     const uint32_t wslot_base = epi_base + uint32_t(ew) * WSLOTS * C::WBOX_BYTES;
     const uint32_t scratch = scratch_base + uint32_t(ew) * SCRATCH_BYTES;
     const uint32_t swz = (C::BOX_ROW_BYTES == 128) ? (lane & 7) : ((lane >> 1) & 3);
@@ -506,7 +566,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         int cmt, cnw;
         decode_tile<BLOCK_N>(p, pv, cmt, c_n0, cnw);
         bool rows_ok;
-        if constexpr (ROW) {
+        if constexpr (ROWTILES) {
           bool ok;
           row_coords(pv, ok, c_a, c_b);
           rows_ok = ok && quad * 32 < p.row_wb;
@@ -528,7 +588,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       const uint32_t cslot = pk % WSLOTS;
       if (lane == 0) {
         mbar_expect_tx(res_bar(ew, cslot), C::WBOX_BYTES);
-        if constexpr (ROW)
+        if constexpr (ROWTILES)
           tma_load_4d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, c_n0 + pb * C::BOXC, quad * 32, c_a, c_b);
         else
           tma_load_2d(&p.tmR, res_bar(ew, cslot), wslot_base + cslot * C::WBOX_BYTES, c_n0 + pb * C::BOXC, c_a);
@@ -547,7 +607,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       bool valid = m < p.M;
       bool wvalid = m0w < p.M;
       int row_wblk = 0, row_orow = 0;
-      if constexpr (ROW) {   // rows of this tile = pixels quad*32 + lane of one output-row segment
+      if constexpr (ROWTILES) {   // rows of this tile = pixels quad*32 + lane of one output-row segment
         bool ok;
         row_coords(v, ok, row_wblk, row_orow);
         wvalid = ok && quad * 32 < p.row_wb;
@@ -702,6 +762,17 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
                            : "memory");
             }
+          } else if (up_coalesced) {
+            // 2x2 upsample store, step 1: stage the bf16 half box (swizzled like a TMA box); the warp writes it out
+            // below with whole 128-byte lines per 8 lanes instead of one 16-byte fragment per lane and row
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t a = wslot_base + lane * C::BOX_ROW_BYTES + soff[h * 4 + j];
+              const uint32_t w0 = pack_bf16(o[8 * j + 0], o[8 * j + 1]), w1 = pack_bf16(o[8 * j + 2], o[8 * j + 3]);
+              const uint32_t w2 = pack_bf16(o[8 * j + 4], o[8 * j + 5]), w3 = pack_bf16(o[8 * j + 6], o[8 * j + 7]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                           : "memory");
+            }
           } else if (valid) {
             if (p.out_fp32) {
               for (int rr = 0; rr < n_out_rows; ++rr) {
@@ -732,6 +803,32 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         if (tr0 && b == b_lo + p.trace_box) trace[21] = gtimer();
         if constexpr (C::BOXC == 64) process_half(v1, 1);
         if (tr0 && b == b_lo + p.trace_box) trace[22] = gtimer();
+        if constexpr (direct) {
+          if (up_coalesced) {
+            // step 2: lanes 8 i .. 8 i + 7 own row 4 it + i of the box (16 bytes each = one 128-byte line) and store it
+            // to the row's 2x2 block of output pixels (nn.Upsample(scale_factor=2), model.py:222): four full lines
+            // per row instead of 4 x 8 scattered 16-byte stores -- the LSU-bound pattern that cost 15-18 us per launch
+            __syncwarp();
+            const unsigned long long my_r00 = valid ? (unsigned long long)out_row[0] : ~0ull;
+            const size_t W2 = size_t(2 * p.w_out);
+            __nv_bfloat16* const ybase = static_cast<__nv_bfloat16*>(p.y) + nb + (lane & 7) * 8;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + (lane >> 3);
+              uint4 val;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                           : "r"(wslot_base + uint32_t(r) * C::BOX_ROW_BYTES + ((uint32_t(lane & 7) ^ uint32_t(r & 7)) << 4)));
+              const unsigned long long r00 = __shfl_sync(0xffffffffu, my_r00, r);
+              if (r00 != ~0ull) {
+                *reinterpret_cast<uint4*>(ybase + size_t(r00) * p.out_pitch) = val;
+                *reinterpret_cast<uint4*>(ybase + size_t(r00 + 1) * p.out_pitch) = val;
+                *reinterpret_cast<uint4*>(ybase + size_t(r00 + W2) * p.out_pitch) = val;
+                *reinterpret_cast<uint4*>(ybase + size_t(r00 + W2 + 1) * p.out_pitch) = val;
+              }
+            }
+            __syncwarp();   // the slot is rewritten by the next box
+          }
+        }
         if (staged) {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
@@ -741,7 +838,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
               tma_store_2d(&p.tmY, wslot_base, nb, m0w);
               if constexpr (C::BOXC == 64) tma_store_2d(&p.tmY, wslot_base + 4096u, nb + 32, m0w);
             } else {
-              if constexpr (ROW) tma_store_4d(&p.tmY, slot_addr, nb, quad * 32, row_wblk, row_orow);  // pixels >= row_wb clipped
+              if constexpr (ROWTILES) tma_store_4d(&p.tmY, slot_addr, nb, quad * 32, row_wblk, row_orow);  // pixels >= row_wb clipped
               else tma_store_2d(&p.tmY, slot_addr, nb, m0w);  // rows >= M are clipped by the tensor map
             }
             bulk_commit_group();
@@ -933,6 +1030,22 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
     }
   }
   if (row_mode) { t_full = num_vtiles = (int)(((long long)d->batch * h_out * row_nblk + 1) / 2); b_half = 0; }
+  // ---- fused stem: tiles are row segments of pixel pairs too; the image window box holds 2 wb + 2 pixels (<= 256) -----
+  int stem_boxw = 0, stem_img_bytes = 0, stem_smem = 0;
+  if (stem) {
+    int nblk = (w_out + 125) / 126;
+    while (nblk <= w_out && (w_out % nblk != 0 || w_out / nblk > 126)) ++nblk;
+    YB_REQUIRE(nblk <= w_out && w_out / nblk >= 32, "conv stem: image width %d (pairs) has no usable row segmentation", w_out);
+    row_wb = w_out / nblk; row_nblk = nblk;
+    stem_boxw = (2 * row_wb + 2 + 3) / 4 * 4;
+    stem_img_bytes = (stem_boxw * 9 * 4 + 1023) / 1024 * 1024;
+    stages = 4;
+    stem_smem = Cfg<64, 64, 1>::B_BYTES + stages * Cfg<64, 64, 1>::A_BYTES + STEM_IMG_STAGES * stem_img_bytes + Cfg<64, 64, 1>::EPI_BYTES +
+                (Cfg<64, 64, 1>::NUM_BARS(stages) + 2 + 2 * STEM_IMG_STAGES) * 8 + 16 + EPI_WARPS * SCRATCH_BYTES;
+    YB_REQUIRE(stem_smem <= 227 * 1024, "conv stem: shared memory");
+    t_full = num_vtiles = d->batch * h_out * row_nblk;
+    b_half = 0;
+  }
 
   ConvKParams2& kp = pl->kp2;
   kp.tmA = pl->kp.tmA;  // same A geometry as v1 (128-row boxes of KC channels); unused by the stem
@@ -970,7 +1083,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     YB_REQUIRE(cr == CUDA_SUCCESS, "conv v2: fp32 tensor map Y encode failed (%d)", (int)cr);
     kp.tmR = kp.tmY;
-  } else if (row_mode) {   // output / residual: (channel, w in segment, segment, image * h_out + ho), 32-pixel boxes per warp
+  } else if (row_mode || stem) {   // output / residual: (channel, w in segment, segment, image * h_out + ho), 32-pixel boxes per warp
     cuuint64_t dims[4] = {(cuuint64_t)d->c_out_pad, (cuuint64_t)row_wb, (cuuint64_t)row_nblk, (cuuint64_t)d->batch * h_out};
     cuuint32_t box[4] = {(cuuint32_t)boxc, 32u, 1u, 1u};
     cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -1031,8 +1144,9 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   if (stem) {
     YB_REQUIRE(bn == 64 && kc == 64 && d->stem_c == 3 && d->ksize == 1 && tiles_n == 1 && !d->has_residual && !direct,
                "conv stem: needs the pair-folded 3->32 stem geometry (c_in 64, c_out 64)");
-    stages = stages > 6 ? 6 : stages;
     kp.stages = stages;
+    kp.stem_boxw = stem_boxw; kp.stem_img_bytes = stem_img_bytes;
+    pl->enc_tiled = (void*)encTiled;
   }
 
   int clusters = max_clusters;
@@ -1040,7 +1154,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   pl->grid2 = clusters * ncta;
   pl->ncta = ncta;
   pl->block_n = bn;
-  pl->smem_bytes = row_mode ? row_smem : smem;
+  pl->smem_bytes = stem ? stem_smem : (row_mode ? row_smem : smem);
   pl->grid_x = tiles_n;
   pl->grid_y = tiles_m;
   return YB_OK;
@@ -1070,9 +1184,21 @@ int conv2_query_max_clusters(int cluster, int* out) {
 int conv2_launch_stem(const ConvPlan* pl, const float* x_nchw, uint32_t* status, cudaStream_t stream) {
   YB_REQUIRE(pl->stem_direct && pl->block_n == 64 && pl->kc == 64 && pl->ncta == 1, "conv stem: plan is not a stem plan");
   YB_REQUIRE(x_nchw && status, "conv stem: null pointer");
+  YB_REQUIRE((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0, "conv stem: the image must be 16-byte aligned");
   ConvKParams2 kp = pl->kp2;
   kp.status = status;
   kp.stem_x = x_nchw;
+  {   // the caller's image moves from call to call: its (W, H, 3, B) fp32 tensor map is encoded per launch (host, ~1 us)
+    const int W = kp.stem_w, H = kp.stem_h;
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3ull, (cuuint64_t)pl->d.batch};
+    cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)3 * H * W * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kp.stem_boxw, 3u, 3u, 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = ((PFN_encodeTiled)pl->enc_tiled)(&kp.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x_nchw), dims, strides,
+                                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    YB_REQUIRE(cr == CUDA_SUCCESS, "conv stem: image tensor map encode failed (%d)", (int)cr);
+  }
   return launch2<64, 64, 1, true>(pl, kp, stream);
 }
 

@@ -48,6 +48,7 @@ struct ConvKParams2 {
   int act, has_residual, upsample2x, out_fp32, check_nan, a_im2col;
   const float* stem_x;  // STEM mode: fp32 NCHW image (set per launch)
   int stem_h, stem_w;
+  int stem_boxw, stem_img_bytes;   // STEM: floats per line of an image window in shared memory, bytes per window stage
   int c_out_pad;
   int s2_parity, s2_cin;  // stride-2 data-gradient sub-convolution (yolo_conv_desc.s2_parity)
   BnFinalize fin;       // training forward: finalize by the CTA that finishes last (fin_counter != nullptr)
@@ -74,6 +75,7 @@ struct ConvPlan {
   ConvKParams kp;
   ConvKParams2 kp2;
   int impl, ncta, grid2, stem_direct;
+  void* enc_tiled;   // cuTensorMapEncodeTiled (the stem's image map is encoded per launch)
   const void* w;
   yolo_conv_desc d;
   int block_n, kc, grid_x, grid_y, smem_bytes;

@@ -420,8 +420,9 @@ class Engine:
         self.impl_hint, self.cta_pair_hint = 0, 0  # 0 = library defaults (include/yolo_b200.h)
         self.pdl_hint, self.tail_split_hint = 0, 0   # 1 switches the feature off (A/B runs, scripts/layer_times.py)
         self.row_hint = 0                            # include/yolo_b200.h: 0 auto | 1 off | 2 on, base_offset variant
-        # fused stem (no patch matrix): correct but not faster yet (gather-warp bound, 0.43 vs 0.22 + 0.24 ms), so opt-in
-        self.stem_direct = os.environ.get("YOLO_B200_FUSED_STEM") == "1"
+        # fused stem (default): the first conv reads the NCHW fp32 image itself (TMA windows -> bf16 taps in shared memory),
+        # no patch matrix in HBM.  YOLO_B200_FUSED_STEM=0 restores yolo_input_patchify + a K=64 GEMM (the A/B baseline).
+        self.stem_direct = os.environ.get("YOLO_B200_FUSED_STEM") != "0"
         self.allow_fold = hasattr(model, "layers") and hasattr(model, "num_classes") and os.environ.get("YOLO_B200_NO_FOLD") != "1"
         self.packed: Dict[int, PackedConv] = {}
         blocks = [m for m in model.modules() if isinstance(m, CNNBlock)]
