@@ -275,8 +275,10 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         const int img = orow / p.row_h_out, ho = orow - img * p.row_h_out;
         mbar_wait(img_empty_bar(si), iph ^ 1u);
         if (elect_one()) {
+          // window start: pixel 2 * segment start - 4.  TMA needs a 16-byte aligned start in the innermost (fp32 pixel)
+          // dimension -- an x0 of -1 raises an illegal-instruction fault -- so the left halo pixel sits in column 3
           mbar_expect_tx(img_full_bar(si), uint32_t(p.stem_boxw) * 9u * 4u);
-          tma_load_4d(&p.tmA, img_full_bar(si), img_base + si * uint32_t(p.stem_img_bytes), 2 * wblk * p.row_wb - 1, ho - 1, 0, img);
+          tma_load_4d(&p.tmA, img_full_bar(si), img_base + si * uint32_t(p.stem_img_bytes), 2 * wblk * p.row_wb - 4, ho - 1, 0, img);
         }
         __syncwarp();
         if (++si == STEM_IMG_STAGES) { si = 0; iph ^= 1u; }
@@ -465,9 +467,9 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         mbar_wait(img_full_bar(si), iph);
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t row_addr = ring_base + s * C::A_BYTES + gr * 128;
-        // window layout: [channel][filter row][stem_boxw floats], column 0 = pixel 2 * segment start - 1; the pair's two
-        // 3x3 windows span columns 2 gr .. 2 gr + 3 (two 8-byte loads per line, conflict free across the warp)
-        const uint32_t wbase = img_base + si * uint32_t(p.stem_img_bytes) + uint32_t(2 * gr) * 4u;
+        // window layout: [channel][filter row][stem_boxw floats], column 0 = pixel 2 * segment start - 4; the pair's two
+        // 3x3 windows span columns 2 gr + 3 .. 2 gr + 6
+        const uint32_t wbase = img_base + si * uint32_t(p.stem_img_bytes) + uint32_t(2 * gr + 3) * 4u;
         float xv[3][3][4];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -475,8 +477,9 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           for (int kh = 0; kh < 3; ++kh) {
             const uint32_t a = wbase + uint32_t((c * 3 + kh) * p.stem_boxw) * 4u;
             if (in_seg) {
-              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(xv[c][kh][0]), "=f"(xv[c][kh][1]) : "r"(a));
-              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(xv[c][kh][2]), "=f"(xv[c][kh][3]) : "r"(a + 8u));
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[c][kh][0]) : "r"(a));
+              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(xv[c][kh][1]), "=f"(xv[c][kh][2]) : "r"(a + 4u));
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[c][kh][3]) : "r"(a + 12u));
             } else {
               xv[c][kh][0] = xv[c][kh][1] = xv[c][kh][2] = xv[c][kh][3] = 0.f;
             }
@@ -1033,11 +1036,11 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   // ---- fused stem: tiles are row segments of pixel pairs too; the image window box holds 2 wb + 2 pixels (<= 256) -----
   int stem_boxw = 0, stem_img_bytes = 0, stem_smem = 0;
   if (stem) {
-    int nblk = (w_out + 125) / 126;
-    while (nblk <= w_out && (w_out % nblk != 0 || w_out / nblk > 126)) ++nblk;
+    int nblk = (w_out + 123) / 124;
+    while (nblk <= w_out && (w_out % nblk != 0 || w_out / nblk > 124 || (w_out / nblk) % 2 != 0)) ++nblk;
     YB_REQUIRE(nblk <= w_out && w_out / nblk >= 32, "conv stem: image width %d (pairs) has no usable row segmentation", w_out);
     row_wb = w_out / nblk; row_nblk = nblk;
-    stem_boxw = (2 * row_wb + 2 + 3) / 4 * 4;
+    stem_boxw = (2 * row_wb + 5 + 3) / 4 * 4;   // pixels -4 .. 2 wb + 1 of the segment, padded to 16 bytes
     stem_img_bytes = (stem_boxw * 9 * 4 + 1023) / 1024 * 1024;
     stages = 4;
     stem_smem = Cfg<64, 64, 1>::B_BYTES + stages * Cfg<64, 64, 1>::A_BYTES + STEM_IMG_STAGES * stem_img_bytes + Cfg<64, 64, 1>::EPI_BYTES +
