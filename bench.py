@@ -424,9 +424,6 @@ def stage_map_gather(args, dev, dist, rank, world, model, cfg):
     n_img, S = 8 * max(world, 1), 416
     gen = torch.Generator().manual_seed(2024)
     imgs = torch.rand(n_img, 3, S, S, generator=gen)
-    gg = torch.Generator().manual_seed(7)
-    gts = torch.cat([torch.cat([torch.full((20, 1), float(i)), torch.rand(20, 2, generator=gg), 0.05 + 0.35 * torch.rand(20, 2, generator=gg),
-                                torch.ones(20, 1), torch.randint(0, args.classes, (20, 1), generator=gg).float()], dim=1) for i in range(n_img)])
     det = Detector(model, cfg.ANCHORS, args.iou, 0.01, "center")
 
     def rows_of(lo, hi):
@@ -439,6 +436,20 @@ def stage_map_gather(args, dev, dist, rank, world, model, cfg):
             plan.check_status()
         return torch.cat(out) if out else torch.zeros(0, 7, device=dev)
 
+    # Synthetic ground truth that the random-init network can actually hit (otherwise mAP is 0 by construction): per
+    # image, 10 random boxes (SURVEY 8d config 3 statistics, seed 7) plus jittered copies of the image's 10 best-scored
+    # detections.  Every rank computes the full set (deterministic kernels, seeded images), so all ranks agree on it.
+    full = rows_of(0, n_img)
+    gg = torch.Generator().manual_seed(7)
+    gts = []
+    for i in range(n_img):
+        rnd = torch.cat([torch.full((10, 1), float(i)), torch.rand(10, 2, generator=gg), 0.05 + 0.35 * torch.rand(10, 2, generator=gg),
+                         torch.ones(10, 1), torch.randint(0, args.classes, (10, 1), generator=gg).float()], dim=1)
+        top = full[full[:, 0] == i][:10].cpu().clone()
+        top[:, 1:5] *= 1.0 + 0.05 * (torch.rand(top.shape[0], 4, generator=gg) - 0.5)
+        top[:, 5] = 1.0
+        gts += [rnd, top]
+    gts = torch.cat(gts)
     lo, hi = shard_range(n_img, rank, world)
     local = rows_of(lo, hi)
     gl = gts[(gts[:, 0] >= lo) & (gts[:, 0] < hi)].to(dev)
@@ -449,7 +460,6 @@ def stage_map_gather(args, dev, dist, rank, world, model, cfg):
     m_dist = float(distributed_mAP(local, gl, 0.5, "center", args.classes))
     torch.cuda.synchronize(dev)
     ms = 1e3 * (time.perf_counter() - t0)
-    full = rows_of(0, n_img)
     m_one = float(calc_mAP(full, gts.to(dev), 0.5, "center", args.classes))
     n_rows = torch.tensor([local.shape[0]], device=dev)
     if dist is not None:
