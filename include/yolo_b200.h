@@ -114,6 +114,15 @@ typedef struct yolo_conv_desc {
    * L2-bandwidth-bound layers) load every filter row once per output-row segment and take the column taps as shifted
    * views of that tile, and keep the weights resident: ~2.5x less L2 -> SM traffic than nine im2col loads per tile.   */
   int32_t row_hint;
+  /* Head conv with the anchor decode in its epilogue (ScalePredictionBlock's last conv, model.py:135-138, followed by
+   * cells_to_boxes, utils.py:86-148): decode_mode = 1 makes y a CANDIDATE tensor -- fp32 rows [cx,cy,w,h,obj,cls] --
+   * instead of the fp32 head: GEMM row (image, i, j) and anchor a go to row
+   *   image * dec_rows_per_image + dec_row_offset + a * S * S + i * S + j        (S = h_out = w_out),
+   * exactly what yolo_decode writes from the stored head (same arithmetic, bit-identical), so the (5+nc)*4 B per cell
+   * head tensor never reaches HBM.  Needs 3 * (5 + dec_nc) <= c_out_pad = one tile (nc <= 80), out_fp32 = 1,
+   * act = none.  dec_anchor_bits: the three (w, h) anchors already multiplied by S, as IEEE-754 bit patterns.       */
+  int32_t decode_mode, dec_nc, dec_rows_per_image, dec_row_offset;
+  int32_t dec_anchor_bits[6];
 } yolo_conv_desc;
 
 /* Size of the opaque, caller-owned plan blob (64-byte aligned storage).       */

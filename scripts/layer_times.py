@@ -41,6 +41,7 @@ x = torch.rand(args.batch, 3, args.size, args.size, device=dev)
 det = Detector(m, cfg.ANCHORS, 0.45, args.conf, "center")
 res, plan = det(x)
 plan.check_status()
+plan.run(x)   # model.forward's path: conv-only graph with fp32 heads (the Detector fuses the decode into the head convs)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 st, sp = stream_ptr(dev), ptr(plan.status)
 

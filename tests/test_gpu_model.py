@@ -229,3 +229,28 @@ def test_standalone_blocks_in_train_mode_use_batch_statistics():
     sp = ScalePredictionBlock(512, num_classes=2).cuda()
     out = sp(torch.randn(5, 512, 13, 13).cuda())
     assert out.shape == (5, 3, 13, 13, 7) and bool(torch.isfinite(out).all())
+
+
+@pytest.mark.parametrize("nc,size,bsz", [(80, 416, 2), (2, 96, 3), (80, 608, 1)])
+def test_detector_fused_decode_equals_decode_of_stored_heads(nc, size, bsz):
+    """Head convs with the anchor decode in their epilogue (the Detector's default) against yolo_decode on the stored
+    fp32 heads: same arithmetic on the same accumulators, so candidates and survivors must be bit-identical."""
+    from yolo_for_turbines_b200.utils import Detector
+
+    m, sd = _model(nc, "leaky_relu", 8)
+    anchors = orc.ANCHORS if nc == 80 else orc.TURBINE_ANCHORS
+    x = torch.rand(bsz, 3, size, size, generator=torch.Generator().manual_seed(21)).cuda()
+    fused = Detector(m, anchors, 0.45, 0.3, "center")
+    plain = Detector(m, anchors, 0.45, 0.3, "center")
+    plain.fuse_decode = False
+    for _ in range(3):   # eager call, graph capture, graph replay
+        ra, plan = fused(x)
+        plan.check_status()
+        assert plan.cand is not None and fused._state[next(iter(fused._state))]["fused"] is True
+        ca, ka, oa = ra.boxes.clone(), ra.keep_idx.clone(), ra.keep_off.clone()
+        rb, plan = plain(x)
+        plan.check_status()
+        assert torch.equal(ca.view(-1, 6), rb.boxes.view(-1, 6))
+        assert torch.equal(oa, rb.keep_off)
+        n = int(oa[-1])
+        assert n > 0 and torch.equal(ka[:n], rb.keep_idx[:n])

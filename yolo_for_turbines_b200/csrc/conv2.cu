@@ -14,6 +14,7 @@
 // Warp roles (192 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer (leader CTA only issues),
 // 2..5 = epilogue (TMEM lane quadrant = warp % 4).
 #include <new>
+#include <string.h>
 #include <type_traits>
 
 #include "conv_plan.cuh"
@@ -881,7 +882,100 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     if (lane == 0) bulk_wait_group_all();
     if (trace && lane == 0) atomicMax(trace + 7, gtimer());
     };
-    if (p.upsample2x || p.s2_parity != 0) run_epilogue(std::integral_constant<int, EPI_DIRECT>{});
+    // ===== head conv + anchor decode (yolo_conv_desc::decode_mode) =====
+    // The accumulator row of a pixel holds the 3 x (5 + nc) head logits of its three anchor cells.  One thread scans
+    // its row in column order -- sigmoid / exp on the first five of each anchor, first-maximum argmax over the class
+    // logits (NaN counts as maximal), the arithmetic of csrc/decode.cu op for op (utils.py:102-143) -- and writes the
+    // three 24-byte candidate rows: the fp32 head ((5 + nc) * 4 B per cell, written and read back) never exists.
+    // A whole tile belongs to ONE group of four warps (tile parity), the other group takes the next tile.
+    auto run_decode_epilogue = [&]() {
+      const int ew = warp - 2, chalf = ew >> 2, quad = warp & 3;
+      const uint32_t scratch = scratch_base + uint32_t(ew) * SCRATCH_BYTES;
+      constexpr int NHALF = BLOCK_N / 32;
+      const int ch = 5 + p.dec_nc, S = p.dec_S, SS = S * S;
+      float* const out = static_cast<float*>(p.y);
+      uint32_t tl = 0;
+      for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
+        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+        const bool mine = uint32_t(chalf) == (tl & 1u);
+        const int m = (v * NCTA + (int)rank) * BLOCK_M + quad * 32 + lane;   // tiles_n == 1: tile v = M tile v
+        const bool valid = m < p.M;
+        float r_sc[NHALF], r_bi[NHALF];
+#pragma unroll
+        for (int i = 0; i < NHALF; ++i) {
+          r_sc[i] = mine ? __ldg(p.scale + 32 * i + lane) : 0.f;
+          r_bi[i] = mine ? __ldg(p.bias + 32 * i + lane) : 0.f;
+        }
+        mbar_wait(tfull_bar(acc), aph);
+        tc_fence_after();
+        if (!mine) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (NCTA == 1) mbar_arrive_local(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc));
+          }
+          continue;
+        }
+        const int img = valid ? m / SS : 0;
+        const int rem = valid ? m - img * SS : 0;
+        const int ci = rem / S, cj = rem - ci * S;
+        float* const orow = out + (size_t(img) * p.dec_rpi + p.dec_off + size_t(ci) * S + cj) * 6;
+        int a = 0, k = 0, bi = -1;
+        bool bnan = false;
+        float best = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
+#pragma unroll 1
+        for (int hb = 0; hb < NHALF; ++hb) {
+          uint32_t vv[32];
+          tmem_ld32_nowait(tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + hb * 32, vv);
+          tmem_wait_ld();
+          if (hb == NHALF - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (NCTA == 1) mbar_arrive_local(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc));
+            }
+          }
+          __syncwarp();
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + 4u * lane), "f"(r_sc[0]) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + 128u + 4u * lane), "f"(r_bi[0]) : "memory");
+#pragma unroll
+          for (int i = 0; i + 1 < NHALF; ++i) { r_sc[i] = r_sc[i + 1]; r_bi[i] = r_bi[i + 1]; }
+          __syncwarp();
+          float o[32];
+          bn_act32(vv, o, scratch, p.act);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const float val = o[jj];
+            if (a < 3) {
+              if (k < 5) {
+                t0 = k == 0 ? val : t0; t1 = k == 1 ? val : t1; t2 = k == 2 ? val : t2; t3 = k == 3 ? val : t3;
+                t4 = k == 4 ? val : t4;
+              } else {
+                const bool vn = val != val;   // argmax over raw logits: first maximal index, NaN counts as maximal
+                if (bi < 0 || (!bnan && (vn || val > best))) { best = val; bi = k - 5; bnan = vn; }
+              }
+              if (++k == ch) {
+                if (valid) {
+                  const float x = 1.0f / (1.0f + expf(-t0)), y = 1.0f / (1.0f + expf(-t1));           // utils.py:106
+                  const float w = __fmul_rn(expf(t2), p.dec_anchors[2 * a]);                           // utils.py:110
+                  const float h = __fmul_rn(expf(t3), p.dec_anchors[2 * a + 1]);
+                  const float obj = 1.0f / (1.0f + expf(-t4));                                         // utils.py:111
+                  float2* dst = reinterpret_cast<float2*>(orow + size_t(a) * SS * 6);
+                  dst[0] = make_float2(__fmul_rn(p.dec_inv_s, __fadd_rn(x, float(cj))),                // utils.py:125
+                                       __fmul_rn(p.dec_inv_s, __fadd_rn(y, float(ci))));               // utils.py:142
+                  dst[1] = make_float2(__fmul_rn(p.dec_inv_s, w), __fmul_rn(p.dec_inv_s, h));          // utils.py:143
+                  dst[2] = make_float2(obj, bi < 0 ? 0.f : float(bi));
+                }
+                k = 0; ++a; bi = -1; bnan = false;
+              }
+            }
+          }
+        }
+      }
+    };
+    if (p.dec_mode) {
+      if constexpr ((BLOCK_N == 256 || BLOCK_N == 32) && !STEM && !ROW) run_decode_epilogue();
+    } else if (p.upsample2x || p.s2_parity != 0) run_epilogue(std::integral_constant<int, EPI_DIRECT>{});
     else if (p.out_fp32) run_epilogue(std::integral_constant<int, EPI_F32>{});
     else if (p.has_residual) run_epilogue(std::integral_constant<int, EPI_BF16_RES>{});
     else run_epilogue(std::integral_constant<int, EPI_BF16>{});
@@ -1077,7 +1171,13 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   }
   const int boxc = bn < 64 ? bn : 64;
   const CUtensorMapSwizzle bswz = boxc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  if (d->out_fp32 && !direct) {   // scale heads: fp32 boxes of 32 columns x 32 rows
+  if (d->decode_mode) {
+    YB_REQUIRE(d->out_fp32 && !direct && !d->has_residual && d->act == YB_ACT_NONE && tiles_n == 1 && (bn == 256 || bn == 32) &&
+                   3 * (5 + d->dec_nc) <= d->c_out_pad && d->dec_nc >= 1 && h_out == w_out && !stem && !row_mode,
+               "conv decode mode: needs a bias-only head conv whose 3 x (5 + nc) channels form one tile of 32 or 256");
+    kp.tmY = kp.tmA;   // no TMA store in this mode: the epilogue writes 24-byte candidate rows
+    kp.tmR = kp.tmA;
+  } else if (d->out_fp32 && !direct) {   // scale heads: fp32 boxes of 32 columns x 32 rows
     cuuint64_t dims[2] = {(cuuint64_t)d->c_out_pad, (cuuint64_t)M};
     cuuint32_t box[2] = {32u, 32u};
     cuuint32_t estr[2] = {1, 1};
@@ -1143,6 +1243,10 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   if (row_mode) kp.stages = row_stages;
   kp.pdl = d->pdl_hint == 1 ? 0 : 1;
   kp.trace = nullptr; kp.trace_box = 0;
+  kp.dec_mode = d->decode_mode ? 1 : 0; kp.dec_nc = d->dec_nc; kp.dec_S = h_out; kp.dec_rpi = d->dec_rows_per_image;
+  kp.dec_off = d->dec_row_offset;
+  kp.dec_inv_s = (float)(1.0 / (double)(h_out > 0 ? h_out : 1));   // utils.py:125: a Python double 1/S cast to fp32
+  for (int i = 0; i < 6; ++i) memcpy(&kp.dec_anchors[i], &d->dec_anchor_bits[i], 4);
   pl->stem_direct = stem ? 1 : 0;
   if (stem) {
     YB_REQUIRE(bn == 64 && kc == 64 && d->stem_c == 3 && d->ksize == 1 && tiles_n == 1 && !d->has_residual && !direct,

@@ -66,6 +66,9 @@ struct ConvKParams2 {
   int row_mode, row_wb, row_nblk, row_total;   // row_total = batch * h_out * row_nblk segments
   int row_h_out, row_bo;
   int tiles_n_sh, row_nblk_sh;                 // log2 when tiles_n / row_nblk is a power of two (the usual case), else -1                       // row_bo: 1 = also set the descriptor's base_offset field to the tap
+  // head conv + anchor decode (yolo_conv_desc::decode_mode): y = candidate rows
+  int dec_mode, dec_nc, dec_S, dec_rpi, dec_off;
+  float dec_inv_s, dec_anchors[6];
   int pdl;              // launched with programmatic stream serialization: griddepcontrol.* brackets the prologue
   unsigned long long* trace;  // dev tool (yolo_conv_fwd_trace): 32 globaltimer stamps / counters per CTA, nullptr otherwise
   int trace_box;              // which epilogue box of the first tile gets the fine-grained stamps

@@ -588,11 +588,7 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   // segment is total / (batch * classes) boxes long at most -- short segments want many small CTAs
   // Measured on random-init YOLOv3 heads (class-skewed segments, profiles/r1_nms_cta_size.txt): 128 / 256 / 512 threads
   // give 0.99 / 0.71 / 0.61 ms at 416 (conf 0.5) and 4.6 / 3.1 / 1.9 ms at 608 (conf 0.01), 1024 threads 0.94 / 2.8 ms.
-  int nt = 512;
-  if (const char* e = getenv("YOLO_B200_NMS_THREADS")) {
-    const int v = atoi(e);
-    if (v == 128 || v == 256 || v == 512 || v == 1024) nt = v;
-  }
+  const int nt = 512;
   const size_t nms_smem = size_t(NMS_QPT) * nt * sizeof(uint32_t);
   int grid = sms * (nt == 1024 ? 1 : (nt == 512 ? 3 : (nt == 256 ? 6 : 12)));
   if (grid > total) grid = total;

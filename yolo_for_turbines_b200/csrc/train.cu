@@ -527,11 +527,7 @@ int check_rows(long long P, int C, int pitch, const char* what) {
 int reduce_grid(long long P, int groups) {
   const int lanes = TR_THREADS / groups;
   long long blocks = (P + (long long)lanes * 8 - 1) / ((long long)lanes * 8);  // >= 8 rows per thread
-  static int cap = 0;  // every block ends with one double atomic per channel statistic: the tail grows with the grid
-  if (cap == 0) {
-    const char* e = getenv("YOLO_B200_REDUCE_BLOCKS");
-    cap = e && atoi(e) > 0 ? atoi(e) : 148 * 3;
-  }
+  const int cap = 148 * 3;  // every block ends with one double atomic per channel statistic: the tail grows with the grid
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;

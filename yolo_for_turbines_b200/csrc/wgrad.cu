@@ -471,17 +471,11 @@ extern "C" int yolo_wgrad_plan_init(void* plan_host, size_t plan_bytes, const yo
   kp.n_per_tap = d->c_in / nt;
   // CTA pairs (k_wgrad_pair) for Cout multiples of 256 with 64-channel boxes on both operands
   // Measured (profiles/r1_wgrad_micro.txt): on the 3x3 layers two co-resident single CTAs per SM (831 TFLOP/s) beat
-  // one pair per two SMs (674), on the 1x1 layers the pair wins (21 vs 27 us), so pairs are the default for 1x1 only;
-  // YOLO_B200_WGRAD_PAIR=1 forces them wherever eligible, =0 disables them.
+  // one pair per two SMs (674), on the 1x1 layers the pair wins (21 vs 27 us), so pairs are used for 1x1 only.
   const bool eligible = d->c_out_pad % 256 == 0 && nt >= 128 && xc == 64 && dc == 64;
   bool pair = eligible && d->ksize == 1;
-  if (const char* e = getenv("YOLO_B200_WGRAD_PAIR")) pair = eligible && atoi(e) != 0;
   pl->pair = pair ? 1 : 0;
   int tp = 512 / nt;                       // accumulators that fit TMEM
-  if (const char* e = getenv("YOLO_B200_WGRAD_TP")) {      // tuning aid
-    const int v = atoi(e);
-    if (v >= 1 && v < tp) tp = v;
-  }
   if (tp > kp.taps) tp = kp.taps;
   if (kp.taps == 9 && tp >= 3 && tp < 9) tp = 3;   // 3 balanced groups instead of e.g. 4 + 4 + 1
   if (nt == 256) tp = 1;                   // 48 KB per tap and stage: keep the ring deep instead
@@ -508,10 +502,6 @@ extern "C" int yolo_wgrad_plan_init(void* plan_host, size_t plan_bytes, const yo
   int stages = (int)(((pair_up ? 108u : 220u) * 1024u) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
-  if (const char* e = getenv("YOLO_B200_WGRAD_STAGES")) {  // tuning aid
-    const int v = atoi(e);
-    if (v >= 1 && v < stages) stages = v;
-  }
   kp.stages = stages;
   pl->nt = nt;
   pl->smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;

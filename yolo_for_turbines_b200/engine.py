@@ -182,12 +182,13 @@ class _Act:
 
 
 class _ConvOp:
-    __slots__ = ("pc", "src", "dst", "res", "upsample", "check_nan", "plan", "plan_ptr", "name")
+    __slots__ = ("pc", "src", "dst", "res", "upsample", "check_nan", "plan", "plan_ptr", "name", "desc", "ptrs", "plan_dec",
+                 "plan_dec_ptr")
 
     def __init__(self, pc, src, dst, res=None, check_nan=True, name=""):
         self.pc, self.src, self.dst, self.res = pc, src, dst, res
         self.upsample, self.check_nan, self.name = False, check_nan, name
-        self.plan = self.plan_ptr = None
+        self.plan = self.plan_ptr = self.desc = self.ptrs = self.plan_dec = self.plan_dec_ptr = None
 
 
 def _aligned_blob(nbytes: int, align: int = 64):
@@ -344,10 +345,13 @@ class ForwardPlan:
                 rroot, roff = op.res.resolve()
                 d.has_residual, d.res_pitch = 1, rroot.C * f
                 r_ptr = C.c_void_p(rroot.buf.data_ptr() + roff * 2)
+            op.desc, op.ptrs = d, (C.c_void_p(x_ptr), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), r_ptr)
             op.plan, op.plan_ptr = make_conv_plan(d, C.c_void_p(x_ptr), ptr(pc.w), ptr(pc.scale), ptr(pc.bias), r_ptr,
                                                   C.c_void_p(y_ptr))
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = use_graph
+        self.cand: Optional[torch.Tensor] = None      # decode_plans(): (B, sum 3 S^2, 6) candidate rows written by the head convs
+        self._dec_key = None
         self.launches_per_forward = len(self.ops) + (0 if self.stem_direct else 1)
 
     # ------------------------------------------------------------------------------------------
@@ -363,11 +367,47 @@ class ForwardPlan:
                                          (h.H * h.W * root.C, ch, h.W * root.C, root.C, 1)))
         return outs
 
-    def _launch_convs(self):
+    def decode_plans(self, anchors) -> bool:
+        """Head convs with the anchor decode in their epilogue (yolo_conv_desc.decode_mode): builds, once per anchor
+        set, a candidate tensor `self.cand` (B, 3*(S1^2+S2^2+S3^2), 6) in the reference's order (utils.py:300-309) and a
+        second plan per head conv that writes it.  Returns False when the heads do not fit the fused form (more than
+        80 classes: 3*(5+nc) must fit one 256-column tile), in which case the caller decodes the stored heads."""
+        import struct
+
+        key = tuple(float(v) for s_ in anchors for a in s_ for v in a)
+        if self._dec_key == key:
+            return self.cand is not None
+        self._dec_key, self.cand = key, None
+        head_ops = [op for op in self.ops if op.dst.fp32]
+        if len(head_ops) != len(self.head_meta) or len(anchors) < len(head_ops):
+            return False
+        for op, (na, nc) in zip(head_ops, self.head_meta):
+            if na != 3 or op.pc.c_out_pad not in (32, 256) or 3 * (5 + nc) > op.pc.c_out_pad or op.dst.H != op.dst.W:
+                return False
+        n = sum(3 * op.dst.H * op.dst.W for op in head_ops)
+        with torch.cuda.device(self.engine.device):
+            cand = torch.zeros(self.B, n, 6, dtype=torch.float32, device=self.engine.device)
+            off = 0
+            for i, (op, (na, nc)) in enumerate(zip(head_ops, self.head_meta)):
+                S = op.dst.H
+                d = ConvDesc.from_buffer_copy(op.desc)
+                d.decode_mode, d.dec_nc, d.dec_rows_per_image, d.dec_row_offset = 1, nc, n, off
+                a = anchors[i] if torch.is_tensor(anchors) else torch.tensor([*anchors[i]])
+                scaled = (a.detach().to(device="cpu", dtype=torch.float32) * S).reshape(-1).tolist()   # utils.py:303, fp32
+                for k in range(6):
+                    d.dec_anchor_bits[k] = struct.unpack("<i", struct.pack("<f", scaled[k]))[0]
+                x_ptr, w, sc, bi, _ = op.ptrs
+                op.plan_dec, op.plan_dec_ptr = make_conv_plan(d, x_ptr, w, sc, bi, None, ptr(cand))
+                off += 3 * S * S
+        self.cand = cand
+        return True
+
+    def _launch_convs(self, decode: bool = False):
+        """decode=True: the head convs write candidate rows into self.cand (decode_plans) instead of fp32 heads."""
         st = stream_ptr(self.engine.device)
         sp = ptr(self.status)
         for op in (self.ops[1:] if self.stem_direct else self.ops):
-            lib.yolo_conv_fwd(op.plan_ptr, sp, st)
+            lib.yolo_conv_fwd(op.plan_dec_ptr if (decode and op.plan_dec_ptr is not None) else op.plan_ptr, sp, st)
 
     def _launch_input(self, x):
         """Everything that reads the caller's tensor (its address changes per call, so it stays out of the CUDA

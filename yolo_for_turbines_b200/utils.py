@@ -293,6 +293,7 @@ class Detector:
         self.anchors = config.ANCHORS if anchors is None else anchors
         self.iou_threshold, self.obj_threshold, self.box_format = iou_threshold, obj_threshold, box_format
         self.use_graph = True
+        self.fuse_decode = True    # head convs decode in their epilogue when the plan supports it (engine.decode_plans)
         self._state = {}
 
     def _get_state(self, B, grids, device, lane=0):
@@ -306,17 +307,21 @@ class Detector:
             self._state[key] = st
         return st
 
-    def _post(self, plan, st):
-        """decode x3 + batched NMS on the plan's head buffers (all launches on the current stream)."""
-        heads = plan.head_views()
-        off = 0
-        for i, h in enumerate(heads):
-            s = h.shape[2]
-            decode_boxes(h, _scaled_anchors(self.anchors, i, s), s, True, out=st["cand"], out_offset=off)
-            off += 3 * s * s
+    def _post(self, plan, st, fused: bool = False):
+        """decode x3 (unless the head convs already wrote plan.cand) + batched NMS, all launches on the current stream."""
+        if fused:
+            cand = plan.cand
+            nc = max(m[1] for m in plan.head_meta)
+        else:
+            heads = plan.head_views()
+            cand, off = st["cand"], 0
+            for i, h in enumerate(heads):
+                s = h.shape[2]
+                decode_boxes(h, _scaled_anchors(self.anchors, i, s), s, True, out=cand, out_offset=off)
+                off += 3 * s * s
+            nc = max(h.shape[-1] - 5 for h in heads)
         # classes come from the decode's argmax: integers < num_classes, so the grouping sort needs one pass
-        nc = max(h.shape[-1] - 5 for h in heads)
-        return batched_nms(st["cand"].view(-1, 6), st["off"], self.iou_threshold, self.obj_threshold, self.box_format,
+        return batched_nms(cand.view(-1, 6), st["off"], self.iou_threshold, self.obj_threshold, self.box_format,
                            workspace=st["ws"], class_bits=8 if nc <= 256 else (16 if nc <= 65536 else 0))
 
     def __call__(self, x: torch.Tensor):
@@ -356,19 +361,23 @@ class Detector:
             st = self._get_state(plan.B, [h.H for h in plan.heads], x.device, lane)
             if st.get("plan") is not plan:  # the model re-planned (new engine): drop the stale graph
                 st.update(plan=plan, graph=None, calls=0, res=None)
+            fused = bool(self.fuse_decode and plan.decode_plans(self.anchors))
+            if st.get("fused") is not fused:
+                st.update(graph=None, calls=0, res=None, fused=fused)
             if st["graph"] is not None:
                 plan._launch_input(x)
                 st["graph"].replay()
             elif st["calls"] == 0 or not self.use_graph:
-                plan.run(x)
-                st["res"] = self._post(plan, st)
+                plan._launch_input(x)
+                plan._launch_convs(decode=fused)   # eager: also sets the dynamic-smem attributes outside capture
+                st["res"] = self._post(plan, st, fused)
             else:
                 plan._launch_input(x)
                 torch.cuda.current_stream(x.device).synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    plan._launch_convs()
-                    st["res"] = self._post(plan, st)
+                    plan._launch_convs(decode=fused)
+                    st["res"] = self._post(plan, st, fused)
                 st["graph"] = g
                 g.replay()
             st["calls"] += 1
