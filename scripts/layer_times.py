@@ -96,6 +96,11 @@ for op in plan.ops:
 print(f"{'layer':34s} {'cin':>5s} {'cout':>5s} k s {'H':>4s} {'BN':>4s} {'KC':>3s} st {'ctas':>6s} {'ms':>8s} {'TFLOP/s':>8s}")
 for r in rows:
     print(f"{r[0]:34s} {r[1]:5d} {r[2]:5d} {r[3]} {r[4]} {r[5]:4d} {r[6]:4d} {r[7]:3d} {r[8]:2d} {r[9]:6d} {r[10]:8.4f} {r[11]:8.1f}")
+if plan.decode_plans(cfg.ANCHORS):
+    for op in plan.ops:
+        if op.plan_dec_ptr is not None:
+            ms = timed(lambda: lib.yolo_conv_fwd(op.plan_dec_ptr, sp, st))
+            print(f"{op.name + ' +decode':34s} head conv with the anchor decode in its epilogue: {ms:8.4f} ms")
 print(f"conv total (isolated, L2 flushed): {tot_ms:.3f} ms  {tot_gf:.1f} GFLOP  {tot_gf / tot_ms:.1f} TFLOP/s")
 ms_in = timed(lambda: plan._launch_input(x))
 print(f"input patchify: {ms_in:.4f} ms  ({x.numel() * 4 / 1e6:.0f} MB in, {args.batch * args.size ** 2 * 64 / 1e6:.0f} MB out)")

@@ -923,6 +923,10 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
         int a = 0, k = 0, bi = -1;
         bool bnan = false;
         float best = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
+        // finished anchors are parked (raw t0..t4 + class) in a small per-thread array and decoded in ONE loop after the
+        // scan: with the sigmoid / exp / store code inlined into each of the 32 unrolled column steps the loop body was
+        // ~150 KB of code and ran from instruction-cache misses (0.20 ms instead of ~0.02 ms on the 52x52 head)
+        float fin[3][6];
 #pragma unroll 1
         for (int hb = 0; hb < NHALF; ++hb) {
           uint32_t vv[32];
@@ -951,10 +955,114 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
                 t0 = k == 0 ? val : t0; t1 = k == 1 ? val : t1; t2 = k == 2 ? val : t2; t3 = k == 3 ? val : t3;
                 t4 = k == 4 ? val : t4;
               } else {
-                const bool vn = val != val;   // argmax over raw logits: first maximal index, NaN counts as maximal
-                if (bi < 0 || (!bnan && (vn || val > best))) { best = val; bi = k - 5; bnan = vn; }
+                // argmax over raw logits: first maximal index, NaN counts as maximal.  Branch-free (selects): the test
+                // differs per lane, and a divergent branch per column costs far more than three selects
+                const bool vn = val != val;
+                const bool take = (bi < 0) | (!bnan & (vn | (val > best)));
+                best = take ? val : best;
+                bi = take ? k - 5 : bi;
+                bnan = take ? vn : bnan;
               }
               if (++k == ch) {
+                fin[a][0] = t0; fin[a][1] = t1; fin[a][2] = t2; fin[a][3] = t3; fin[a][4] = t4;
+                fin[a][5] = bi < 0 ? 0.f : float(bi);
+                k = 0; ++a; bi = -1; bnan = false;
+              }
+            }
+          }
+        }
+        if (valid) {
+#pragma unroll 1
+          for (int a2 = 0; a2 < 3; ++a2) {
+            const float x = 1.0f / (1.0f + expf(-fin[a2][0])), y = 1.0f / (1.0f + expf(-fin[a2][1]));   // utils.py:106
+            const float w = __fmul_rn(expf(fin[a2][2]), p.dec_anchors[2 * a2]);                           // utils.py:110
+            const float h = __fmul_rn(expf(fin[a2][3]), p.dec_anchors[2 * a2 + 1]);
+            const float obj = 1.0f / (1.0f + expf(-fin[a2][4]));                                          // utils.py:111
+            float2* dst = reinterpret_cast<float2*>(orow + size_t(a2) * SS * 6);
+            dst[0] = make_float2(__fmul_rn(p.dec_inv_s, __fadd_rn(x, float(cj))),                         // utils.py:125
+                                 __fmul_rn(p.dec_inv_s, __fadd_rn(y, float(ci))));                        // utils.py:142
+            dst[1] = make_float2(__fmul_rn(p.dec_inv_s, w), __fmul_rn(p.dec_inv_s, h));                   // utils.py:143
+            dst[2] = make_float2(obj, fin[a2][5]);
+          }
+        }
+      }
+    };
+    // The same scan with the class count known at compile time (COCO's 80 on the 256-column tile, the turbine model's 2
+    // on the 32-column tile): after full unrolling every column's role (which anchor, which of its 5 + nc values) is a
+    // constant, so a class column costs one compare-or-unordered, one NaN guard and two selects, and the decode of a
+    // finished anchor sits at exactly three places in straight-line code.
+    auto run_decode_epilogue_static = [&](auto nc_tag) {
+      constexpr int NC = decltype(nc_tag)::value, CH = 5 + NC;
+      const int ew = warp - 2, chalf = ew >> 2, quad = warp & 3;
+      const uint32_t scratch = scratch_base + uint32_t(ew) * SCRATCH_BYTES;
+      constexpr int NHALF = BLOCK_N / 32;
+      const int S = p.dec_S, SS = S * S;
+      float* const out = static_cast<float*>(p.y);
+      uint32_t tl = 0;
+      for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
+        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+        const bool mine = uint32_t(chalf) == (tl & 1u);
+        const int m = (v * NCTA + (int)rank) * BLOCK_M + quad * 32 + lane;
+        const bool valid = m < p.M;
+        float r_sc[NHALF], r_bi[NHALF];
+#pragma unroll
+        for (int i = 0; i < NHALF; ++i) {
+          r_sc[i] = mine ? __ldg(p.scale + 32 * i + lane) : 0.f;
+          r_bi[i] = mine ? __ldg(p.bias + 32 * i + lane) : 0.f;
+        }
+        mbar_wait(tfull_bar(acc), aph);
+        tc_fence_after();
+        if (!mine) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (NCTA == 1) mbar_arrive_local(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc));
+          }
+          continue;
+        }
+        const int img = valid ? m / SS : 0;
+        const int rem = valid ? m - img * SS : 0;
+        const int ci = rem / S, cj = rem - ci * S;
+        float* const orow = out + (size_t(img) * p.dec_rpi + p.dec_off + size_t(ci) * S + cj) * 6;
+        float best = -INFINITY, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
+        int bi = -1;
+#pragma unroll
+        for (int hb = 0; hb < NHALF; ++hb) {
+          if (hb * 32 < 3 * CH) {   // (compile time) chunks past the last anchor are not read at all
+            uint32_t vv[32];
+            tmem_ld32_nowait(tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + hb * 32, vv);
+            tmem_wait_ld();
+          if ((hb + 1) * 32 >= 3 * CH) {   // last chunk that is read: hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (NCTA == 1) mbar_arrive_local(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc));
+            }
+          }
+          __syncwarp();
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + 4u * lane), "f"(r_sc[hb]) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(scratch + 128u + 4u * lane), "f"(r_bi[hb]) : "memory");
+          __syncwarp();
+          float o[32];
+          bn_act32(vv, o, scratch, YB_ACT_NONE);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int c = hb * 32 + jj;
+            if (c < 3 * CH) {
+              const int k = c % CH, a = c / CH;
+              const float val = o[jj];
+              if (k == 0) t0 = val;
+              else if (k == 1) t1 = val;
+              else if (k == 2) t2 = val;
+              else if (k == 3) t3 = val;
+              else if (k == 4) t4 = val;
+              else {
+                // first maximal index, NaN counts as maximal: take when val > best or val is NaN, unless best already is
+                const bool take = !(val <= best) & (best == best);
+                best = take ? val : best;
+                bi = take ? k - 5 : bi;
+              }
+              if (k == CH - 1) {
                 if (valid) {
                   const float x = 1.0f / (1.0f + expf(-t0)), y = 1.0f / (1.0f + expf(-t1));           // utils.py:106
                   const float w = __fmul_rn(expf(t2), p.dec_anchors[2 * a]);                           // utils.py:110
@@ -966,15 +1074,23 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
                   dst[1] = make_float2(__fmul_rn(p.dec_inv_s, w), __fmul_rn(p.dec_inv_s, h));          // utils.py:143
                   dst[2] = make_float2(obj, bi < 0 ? 0.f : float(bi));
                 }
-                k = 0; ++a; bi = -1; bnan = false;
+                best = -INFINITY;
+                bi = -1;
               }
             }
+          }
           }
         }
       }
     };
     if (p.dec_mode) {
-      if constexpr ((BLOCK_N == 256 || BLOCK_N == 32) && !STEM && !ROW) run_decode_epilogue();
+      if constexpr (BLOCK_N == 256 && !STEM && !ROW) {
+        if (p.dec_nc == 80) run_decode_epilogue_static(std::integral_constant<int, 80>{});
+        else run_decode_epilogue();
+      } else if constexpr (BLOCK_N == 32 && !STEM && !ROW) {
+        if (p.dec_nc == 2) run_decode_epilogue_static(std::integral_constant<int, 2>{});
+        else run_decode_epilogue();
+      }
     } else if (p.upsample2x || p.s2_parity != 0) run_epilogue(std::integral_constant<int, EPI_DIRECT>{});
     else if (p.out_fp32) run_epilogue(std::integral_constant<int, EPI_F32>{});
     else if (p.has_residual) run_epilogue(std::integral_constant<int, EPI_BF16_RES>{});
