@@ -601,6 +601,9 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       if (++pb == c_bhi) { pb = -1; pv += num_clusters; ++ptl; res_cursor_settle(); }
     };
     if (res_staged) res_cursor_settle();
+    constexpr int NCH = (BLOCK_N / 64 > C::BOXC / 32) ? BLOCK_N / 64 : C::BOXC / 32;   // 32-column chunks one warp can own: half a tile, or a whole one-box tile
+    float m_sc[NCH], m_bi[NCH];   // this warp's per-column scale / bias (lane l: columns sb_lo + 32 i + l)
+    int sb_lo = -1, sb_hi = -1;
     for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++tl) {
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       int mt, n0, nw;
@@ -620,15 +623,22 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       const bool tr0 = trace != nullptr && ew == 0 && tl == 0 && lane == 0;
       // this tile's per-column scale / bias, fetched while the accumulator is still being produced: lane l holds
       // columns n0 + 32 i + l; chunk 0 is handed to the scratch per 32-column step and the registers rotate
-      constexpr int NCH = (BLOCK_N / 64 > C::BOXC / 32) ? BLOCK_N / 64 : C::BOXC / 32;   // 32-column chunks one warp can own: half a tile, or a whole one-box tile
       float r_sc[NCH], r_bi[NCH];
       const int c_lo = n0 + b_lo * C::BOXC, c_hi = n0 + b_hi * C::BOXC;
+      // (re)fetched only when the column range changes: with one N tile per layer (all 1x1 layers up to 256 channels, the
+      // 52x52 3x3 layers) that is once per launch -- on short-K tiles the accumulator of the NEXT tile is usually ready
+      // when a tile's epilogue ends, so a per-tile fetch exposed its L2 round trip (1-4 us under load) on every tile
+      if (c_lo != sb_lo || c_hi != sb_hi) {
+        sb_lo = c_lo; sb_hi = c_hi;
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const bool in = c_lo + 32 * i < c_hi;
-        r_sc[i] = in ? __ldg(p.scale + c_lo + 32 * i + lane) : 0.f;
-        r_bi[i] = in ? __ldg(p.bias + c_lo + 32 * i + lane) : 0.f;
+        for (int i = 0; i < NCH; ++i) {
+          const bool in = c_lo + 32 * i < c_hi;
+          m_sc[i] = in ? __ldg(p.scale + c_lo + 32 * i + lane) : 0.f;
+          m_bi[i] = in ? __ldg(p.bias + c_lo + 32 * i + lane) : 0.f;
+        }
       }
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) { r_sc[i] = m_sc[i]; r_bi[i] = m_bi[i]; }
       if (res_staged && wvalid && b_lo < b_hi) {
         // tile boundary: every earlier store of this warp was committed long ago -- take both slots
         if (lane == 0) bulk_wait_group_read<0>();
