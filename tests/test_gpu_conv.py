@@ -17,7 +17,7 @@ REL = 2.0 ** -7
 
 def _run_case(B, H, cin, cout, k, stride, act="leaky_relu", residual=False, upsample=False, fp32=False,
               a_mode=0, block_n=0, stages=0, in_pitch=None, out_pitch=None, seed=0, also_simt=True, impl=0, pair=0,
-              pdl=0, split=0, launches=1, row=0, W=None, expect_impl=None):
+              pdl=0, split=0, launches=1, row=0, W=None, expect_impl=None, mc=0):
     from yolo_for_turbines_b200._lib import ACT_CODES, ConvDesc, lib, ptr, stream_ptr
     from yolo_for_turbines_b200.engine import make_conv_plan
 
@@ -68,7 +68,7 @@ def _run_case(B, H, cin, cout, k, stride, act="leaky_relu", residual=False, upsa
     d.upsample2x, d.out_fp32, d.check_nan = int(upsample), int(fp32), 1
     d.a_mode, d.block_n_hint, d.stages_hint = a_mode, block_n, stages
     d.impl_hint, d.cta_pair_hint = impl, pair
-    d.pdl_hint, d.tail_split_hint, d.row_hint = pdl, split, row
+    d.pdl_hint, d.tail_split_hint, d.row_hint, d.mc_hint = pdl, split, row, mc
 
     outs = {}
     yd = torch.full((B, Hy, Wy, out_pitch), 7.0, dtype=odt, device=dev)
@@ -195,6 +195,20 @@ def test_row_window_mode(row=0):
                       launches=2)
         b = _run_case(B=B, H=H, W=W, cin=cin, cout=cout, k=3, stride=1, residual=res, row=1, also_simt=False, expect_impl=2)
         assert torch.equal(a["tcgen05"], b["tcgen05"]) or float((a["tcgen05"] - b["tcgen05"]).abs().max()) <= 2.0 ** -6
+
+
+def test_weight_tile_multicast_across_two_cta_pairs():
+    """Clusters of two CTA pairs sharing the weight tile by TMA multicast (mc_hint 0 = auto on for 256-wide tiles with
+    >= 8 M tiles) against the oracle arithmetic and against the plain pair kernel (mc_hint = 1): odd and even numbers
+    of M tiles (the second pair of the last cluster idles), 1x1 / 3x3 / stride 2, residual, tail-split tiles."""
+    cases = [dict(B=64, H=13, cin=128, cout=512, k=1, stride=1),                       # 43 M tiles x 2 N tiles, split tail
+             dict(B=40, H=13, cin=64, cout=256, k=3, stride=1, residual=True),         # 27 M tiles x 1
+             dict(B=16, H=26, cin=64, cout=512, k=3, stride=2),                        # 11 M tiles x 2, im2col stride 2
+             dict(B=24, H=26, cin=128, cout=256, k=3, stride=1, residual=True, act="mish")]   # 64 M tiles (even)
+    for c in cases:
+        a = _run_case(**c, also_simt=False, mc=0, launches=2)
+        b = _run_case(**c, also_simt=False, mc=1)
+        assert torch.equal(a["tcgen05"], b["tcgen05"]), c
 
 
 def test_nan_layer_flag():

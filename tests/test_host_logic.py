@@ -104,7 +104,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(dll, s), f"{s} declared in include/yolo_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == syms  # the ctypes table binds exactly the header's surface
     assert _lib.lib.yolo_version() == 100
-    assert ctypes.sizeof(_lib.ConvDesc) == 43 * 4
+    assert ctypes.sizeof(_lib.ConvDesc) == 44 * 4
     assert _lib.lib.yolo_nms_workspace_bytes(10647 * 64, 64) > 10647 * 64 * 40
 
 

@@ -33,7 +33,7 @@ class ConvDesc(C.Structure):
         "act", "has_residual", "res_pitch", "upsample2x", "out_fp32", "check_nan", "a_mode", "block_n_hint",
         "stages_hint", "impl_hint", "cta_pair_hint", "ksize_w", "stride_w", "pad_w_hi_plus1", "stem_c", "want_stats", "pad_h_hi_plus1", "s2_parity", "s2_cin",
         "pdl_hint", "tail_split_hint", "row_hint", "decode_mode", "dec_nc", "dec_rows_per_image", "dec_row_offset")] + [
-        ("dec_anchor_bits", C.c_int32 * 6)]
+        ("dec_anchor_bits", C.c_int32 * 6), ("mc_hint", C.c_int32)]
 
 
 class BnFinalizeDesc(C.Structure):

@@ -180,10 +180,16 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     for (int i = threadIdx.x; i < 2 * p.c_out_pad; i += blockDim.x)
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(stats_base + 4u * i), "r"(0u) : "memory");
   }
-  const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
+  // A cluster is one CTA pair, or (p.mc == 2) two pairs on neighbouring M tiles sharing the weight tile by multicast.
+  const uint32_t crank = (NCTA == 2) ? cluster_ctarank() : 0u;
+  const uint32_t rank = crank & 1u;                 // rank inside the MMA pair
+  const int pq = int(crank >> 1);                   // which pair of the cluster (0 unless p.mc == 2)
+  const int mc = (NCTA == 2) ? p.mc : 1;
   const bool leader = rank == 0;
-  const int cluster_id = blockIdx.x / NCTA;
-  const int num_clusters = gridDim.x / NCTA;
+  const int cluster_id = blockIdx.x / (NCTA * mc);
+  const int num_clusters = gridDim.x / (NCTA * mc);
+  const uint16_t pair_mask = uint16_t(0x3u << (2 * pq));          // tcgen05.commit multicast: this pair's two CTAs
+  const uint16_t ring_mask = mc == 2 ? uint16_t(0xF) : pair_mask;  // ... and, for ring stages, every CTA that writes into them
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -192,7 +198,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     if (p.has_residual) tma_prefetch_desc(&p.tmR);
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), STEM ? STEM_GATHER_WARPS : 1);  // STEM: one arrive per gather warp, no TMA bytes
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), (NCTA == 2) ? p.mc : 1);   // one tcgen05.commit per pair whose loads land in this stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -309,7 +315,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
     for (int v = cluster_id; v < p.num_vtiles; v += num_clusters, ++ntiles) {
       int mt, n0, nw;
       decode_tile<BLOCK_N>(p, v, mt, n0, nw);
-      int m0 = (mt * NCTA + (int)rank) * BLOCK_M;
+      int m0 = ((mt * mc + pq) * NCTA + (int)rank) * BLOCK_M;
       if (m0 >= p.M) m0 = 0;  // peer CTA of a ragged last pair: load valid rows, results are discarded
       const bool whole = nw == BLOCK_N;
       const int nb0 = n0 + (int)rank * (whole ? C::B_ROWS : C::B_ROWS / 2);   // this CTA's rows of the weight tile
@@ -346,8 +352,14 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           } else {
             if (p.a_im2col) tma_load_im2col_4d_2sm(&p.tmA, full_bar(s), sa, cc * KC, cw, ch, img, (uint16_t)tq, (uint16_t)tr);
             else tma_load_2d_2sm(&p.tmA, full_bar(s), sa, cc * KC, m0);
-            tma_load_2d_2sm(&p.tmB, full_bar(s), sb, kb * KC, nb0);
-            if (b_second) tma_load_2d_2sm(&p.tmB, full_bar(s), sb + C::B_BYTES / 2, kb * KC, nb0 + C::B_ROWS / 2);
+            if (mc == 2 && whole) {
+              // this CTA fetches rows [pq * 64, +64) of its pair-half of the weight tile for BOTH pairs
+              tma_load_2d_2sm_mc(&p.tmB, full_bar(s), sb + uint32_t(pq) * (C::B_BYTES / 2), kb * KC, nb0 + pq * (C::B_ROWS / 2),
+                                 uint16_t((1u << rank) | (1u << (2 + rank))));
+            } else {
+              tma_load_2d_2sm(&p.tmB, full_bar(s), sb, kb * KC, nb0);
+              if (b_second) tma_load_2d_2sm(&p.tmB, full_bar(s), sb + C::B_BYTES / 2, kb * KC, nb0 + C::B_ROWS / 2);
+            }
           }
           if (trace && ntiles == 0 && kb == 0) trace[3] = gtimer();
         }
@@ -447,8 +459,8 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
             for (int k = 0; k < KC / 16; ++k)
               umma_bf16_n<NCTA>(d_tmem, adesc0 + soff + uint64_t(2 * k), bdesc0 + soff + uint64_t(2 * k), idesc,
                                 (kb | k) != 0 ? 1u : 0u);
-            umma_commit_n<NCTA>(empty_bar(s));
-            if (kb == p.num_kb - 1) umma_commit_n<NCTA>(tfull_bar(acc));
+            umma_commit_n<NCTA>(empty_bar(s), ring_mask);
+            if (kb == p.num_kb - 1) umma_commit_n<NCTA>(tfull_bar(acc), pair_mask);
           }
           __syncwarp();
           if (++s == stages) { s = 0; ph ^= 1u; }
@@ -575,7 +587,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
           row_coords(pv, ok, c_a, c_b);
           rows_ok = ok && quad * 32 < p.row_wb;
         } else {
-          c_a = (cmt * NCTA + (int)rank) * BLOCK_M + quad * 32;
+          c_a = ((cmt * mc + pq) * NCTA + (int)rank) * BLOCK_M + quad * 32;
           rows_ok = c_a < p.M;
         }
         c_bhi = box_hi(cnw, ptl);
@@ -609,7 +621,7 @@ k_conv_v2(const __grid_constant__ ConvKParams2 p) {
       int mt, n0, nw;
       decode_tile<BLOCK_N>(p, v, mt, n0, nw);
       const int b_lo = box_lo(nw, tl), b_hi = box_hi(nw, tl);
-      const int m0w = (mt * NCTA + (int)rank) * BLOCK_M + quad * 32;
+      const int m0w = ((mt * mc + pq) * NCTA + (int)rank) * BLOCK_M + quad * 32;
       const int m = m0w + lane;
       bool valid = m < p.M;
       bool wvalid = m0w < p.M;
@@ -1159,7 +1171,7 @@ int launch2(const ConvPlan* pl, const ConvKParams2& kp, cudaStream_t stream) {
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.x = pl->csize > 0 ? pl->csize : NCTA;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1187,6 +1199,16 @@ int smem_bytes_v2(int bn, int kc, int ncta, int stages, int extra) {
 }
 
 }  // namespace
+
+// co-resident clusters of 4 CTAs of the 256-wide pair kernel (B200: 33 = 132 of 148 SMs), queried once
+static int clusters_of_4() {
+  static int n4 = -1;
+  if (n4 < 0) {
+    int v = 0;
+    n4 = (conv2_query_max_clusters(4, &v) == YB_OK) ? v : 0;
+  }
+  return n4;
+}
 
 int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out, int im2col, PFN_encodeTiled encTiled,
                      const void* x, const void* residual, void* y) {
@@ -1217,12 +1239,19 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   int dev = 0, sms = 148;
   YB_CHECK_CUDA(cudaGetDevice(&dev));
   YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int max_clusters = sms / ncta;
   const int direct = d->upsample2x || d->s2_parity;
+  // ---- weight-tile multicast across two CTA pairs (ConvKParams2::mc) ------------------------------------------
+  int mc = 1;
+  if (d->mc_hint != 1 && ncta == 2 && bn == 256 && kc == 64 && !stem && !d->out_fp32 && !direct && !d->want_stats &&
+      tiles_m >= 8 && d->block_n_hint == 0 && d->stages_hint == 0) {
+    if (clusters_of_4() >= 16) mc = 2;
+  }
+  const int max_clusters = mc == 2 ? clusters_of_4() : sms / ncta;
+  const int tiles_m_sched = (tiles_m + mc - 1) / mc;   // M tiles per cluster step
   // Tail splitting (ConvKParams2::t_full): the last round of a persistent launch holds num_tiles % clusters tiles.
   // When at most half of the CTA pairs would get one, every such tile is cut into two half-width tiles: the round
   // then costs about half a tile time (13x13 3x3 layers: 2.5 instead of 3 rounds).
-  int t_full = tiles_m * tiles_n, num_vtiles = t_full, b_half = 0;
+  int t_full = tiles_m_sched * tiles_n, num_vtiles = t_full, b_half = mc == 2 ? 1 : 0;   // mc: 64-row weight boxes
   if (d->tail_split_hint != 1 && bn >= 128 && !d->out_fp32 && !direct && !d->want_stats && !stem) {
     const int rem = t_full % max_clusters;
     if (rem > 0 && 2 * rem <= max_clusters) {
@@ -1368,6 +1397,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   kp.row_total = d->batch * h_out * row_nblk; kp.row_bo = d->row_hint == 2 ? 1 : 0;
   if (row_mode) kp.stages = row_stages;
   kp.pdl = d->pdl_hint == 1 ? 0 : 1;
+  kp.mc = mc;
   kp.trace = nullptr; kp.trace_box = 0;
   kp.dec_mode = d->decode_mode ? 1 : 0; kp.dec_nc = d->dec_nc; kp.dec_S = h_out; kp.dec_rpi = d->dec_rows_per_image;
   kp.dec_off = d->dec_row_offset;
@@ -1384,7 +1414,8 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
 
   int clusters = max_clusters;
   if (clusters > kp.num_vtiles) clusters = kp.num_vtiles;
-  pl->grid2 = clusters * ncta;
+  pl->grid2 = clusters * ncta * mc;
+  pl->csize = ncta * mc;
   pl->ncta = ncta;
   pl->block_n = bn;
   pl->smem_bytes = stem ? stem_smem : (row_mode ? row_smem : smem);

@@ -69,6 +69,9 @@ struct ConvKParams2 {
   // head conv + anchor decode (yolo_conv_desc::decode_mode): y = candidate rows
   int dec_mode, dec_nc, dec_S, dec_rpi, dec_off;
   float dec_inv_s, dec_anchors[6];
+  // mc = 2: clusters of two CTA pairs that work on neighbouring M tiles of the same N tile and share the weight tile
+  // through TMA multicast (each CTA loads a quarter of it for both pairs): 25 % less L2 -> SM traffic on the big layers
+  int mc;
   int pdl;              // launched with programmatic stream serialization: griddepcontrol.* brackets the prologue
   unsigned long long* trace;  // dev tool (yolo_conv_fwd_trace): 32 globaltimer stamps / counters per CTA, nullptr otherwise
   int trace_box;              // which epilogue box of the first tile gets the fine-grained stamps
@@ -77,7 +80,7 @@ struct ConvKParams2 {
 struct ConvPlan {
   ConvKParams kp;
   ConvKParams2 kp2;
-  int impl, ncta, grid2, stem_direct;
+  int impl, ncta, grid2, stem_direct, csize;
   void* enc_tiled;   // cuTensorMapEncodeTiled (the stem's image map is encoded per launch)
   const void* w;
   yolo_conv_desc d;

@@ -193,6 +193,15 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* tm, uint32_t 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(kL2Default)
       : "memory");
 }
+// weight-tile multicast across the two CTA pairs of a 4-CTA cluster: the box lands at the same shared-memory offset in
+// every CTA of `mask`, and each destination pair's leader barrier (peer bit cleared) receives the bytes
+__device__ __forceinline__ void tma_load_2d_2sm_mc(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%4, %5}], [%2], %3, %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerBitMask), "h"(mask), "r"(c0), "r"(c1), "l"(kL2Default)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col_4d_2sm(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c,
                                                        int w, int h, int n, uint16_t off_w, uint16_t off_h) {
   asm volatile(
@@ -274,11 +283,10 @@ __device__ __forceinline__ void umma_bf16_n(uint32_t d_tmem, uint64_t adesc, uin
 // tcgen05.commit: arrive on `bar` when all MMAs issued so far by this thread have completed.  With a CTA
 // pair the arrive is multicast to the barrier at the same offset in both CTAs.
 template <int NCTA>
-__device__ __forceinline__ void umma_commit_n(uint32_t bar) {
+__device__ __forceinline__ void umma_commit_n(uint32_t bar, uint16_t mask = 0x3) {
   if constexpr (NCTA == 1) {
     umma_commit(bar);
   } else {
-    const uint16_t mask = 0x3;
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(mask)
                  : "memory");

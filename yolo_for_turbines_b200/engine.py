@@ -336,6 +336,7 @@ class ForwardPlan:
             d.a_mode, d.block_n_hint, d.stages_hint = 0, engine.block_n_hint, engine.stages_hint
             d.impl_hint, d.cta_pair_hint = engine.impl_hint, engine.cta_pair_hint
             d.pdl_hint, d.tail_split_hint, d.row_hint = engine.pdl_hint, engine.tail_split_hint, engine.row_hint
+            d.mc_hint = engine.mc_hint
             x_ptr = sroot.buf.data_ptr() + soff * 2
             if self.stem_direct and op is self.ops[0]:
                 d.stem_c, x_ptr = 3, 0
@@ -460,6 +461,7 @@ class Engine:
         self.impl_hint, self.cta_pair_hint = 0, 0  # 0 = library defaults (include/yolo_b200.h)
         self.pdl_hint, self.tail_split_hint = 0, 0   # 1 switches the feature off (A/B runs, scripts/layer_times.py)
         self.row_hint = 0                            # include/yolo_b200.h: 0 auto | 1 off | 2 on, base_offset variant
+        self.mc_hint = 0                             # weight-tile multicast across two CTA pairs: 0 auto | 1 off
         # fused stem (default): the first conv reads the NCHW fp32 image itself (TMA windows -> bf16 taps in shared memory),
         # no patch matrix in HBM.  YOLO_B200_FUSED_STEM=0 restores yolo_input_patchify + a K=64 GEMM (the A/B baseline).
         self.stem_direct = os.environ.get("YOLO_B200_FUSED_STEM") != "0"
