@@ -123,10 +123,11 @@ typedef struct yolo_conv_desc {
    * act = none.  dec_anchor_bits: the three (w, h) anchors already multiplied by S, as IEEE-754 bit patterns.       */
   int32_t decode_mode, dec_nc, dec_rows_per_image, dec_row_offset;
   int32_t dec_anchor_bits[6];
-  /* mc_hint: 0 auto | 1 off.  Weight-tile multicast: clusters of two CTA pairs on neighbouring M tiles of one N tile;
-   * every CTA TMA-loads a quarter of the 256-row weight tile and multicasts it to the matching CTA of the other pair
-   * (25 % less L2 -> SM traffic on the big 3x3 layers, which are bound by it).  B200 fits 33 clusters of 4 (132 of
-   * 148 SMs), so it is used only where the saved traffic outweighs the 16 idle SMs.                                   */
+  /* mc_hint: 0 | 1 off (default), 2 on.  Weight-tile multicast: clusters of two CTA pairs on neighbouring M tiles of
+   * one N tile; every CTA TMA-loads a quarter of the 256-row weight tile and multicasts it to the matching CTA of the
+   * other pair (25 % less L2 -> SM traffic).  Correct (bit-identical) but MEASURED SLOWER on B200: only 33 clusters of
+   * 4 CTAs are co-resident (132 of 148 SMs) and every big 3x3 layer loses 3-8 % (profiles/r2_multicast_ab.txt), so it
+   * stays an opt-in A/B switch.                                                                                         */
   int32_t mc_hint;
 } yolo_conv_desc;
 

@@ -27,7 +27,7 @@ ap.add_argument("--conf", type=float, default=0.5)
 ap.add_argument("--no-pdl", action="store_true")
 ap.add_argument("--no-split", action="store_true")
 ap.add_argument("--no-row", action="store_true")
-ap.add_argument("--no-mc", action="store_true")
+ap.add_argument("--mc", action="store_true", help="weight-tile multicast across two CTA pairs (opt-in)")
 ap.add_argument("--warm", action="store_true", help="no L2 flush: run the producing layer right before the timed one (in-graph cache state)")
 args = ap.parse_args()
 
@@ -38,7 +38,7 @@ eng = m._engine(dev)
 eng.block_n_hint, eng.stages_hint = args.block_n, args.stages
 eng.impl_hint, eng.cta_pair_hint = args.impl, args.pair
 eng.pdl_hint, eng.tail_split_hint, eng.row_hint = int(args.no_pdl), int(args.no_split), int(args.no_row)
-eng.mc_hint = int(args.no_mc)
+eng.mc_hint = 2 if args.mc else 0
 x = torch.rand(args.batch, 3, args.size, args.size, device=dev)
 det = Detector(m, cfg.ANCHORS, 0.45, args.conf, "center")
 res, plan = det(x)

@@ -198,16 +198,16 @@ def test_row_window_mode(row=0):
 
 
 def test_weight_tile_multicast_across_two_cta_pairs():
-    """Clusters of two CTA pairs sharing the weight tile by TMA multicast (mc_hint 0 = auto on for 256-wide tiles with
-    >= 8 M tiles) against the oracle arithmetic and against the plain pair kernel (mc_hint = 1): odd and even numbers
+    """Clusters of two CTA pairs sharing the weight tile by TMA multicast (mc_hint = 2; opt-in, measured slower on B200
+    because only 132 of 148 SMs fit clusters of 4) against the oracle arithmetic and against the plain pair kernel: odd and even numbers
     of M tiles (the second pair of the last cluster idles), 1x1 / 3x3 / stride 2, residual, tail-split tiles."""
     cases = [dict(B=64, H=13, cin=128, cout=512, k=1, stride=1),                       # 43 M tiles x 2 N tiles, split tail
              dict(B=40, H=13, cin=64, cout=256, k=3, stride=1, residual=True),         # 27 M tiles x 1
              dict(B=16, H=26, cin=64, cout=512, k=3, stride=2),                        # 11 M tiles x 2, im2col stride 2
              dict(B=24, H=26, cin=128, cout=256, k=3, stride=1, residual=True, act="mish")]   # 64 M tiles (even)
     for c in cases:
-        a = _run_case(**c, also_simt=False, mc=0, launches=2)
-        b = _run_case(**c, also_simt=False, mc=1)
+        a = _run_case(**c, also_simt=False, mc=2, launches=2)
+        b = _run_case(**c, also_simt=False, mc=0)
         assert torch.equal(a["tcgen05"], b["tcgen05"]), c
 
 

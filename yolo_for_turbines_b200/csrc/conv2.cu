@@ -1242,7 +1242,7 @@ int conv2_plan_setup(ConvPlan* pl, const yolo_conv_desc* d, int h_out, int w_out
   const int direct = d->upsample2x || d->s2_parity;
   // ---- weight-tile multicast across two CTA pairs (ConvKParams2::mc) ------------------------------------------
   int mc = 1;
-  if (d->mc_hint != 1 && ncta == 2 && bn == 256 && kc == 64 && !stem && !d->out_fp32 && !direct && !d->want_stats &&
+  if (d->mc_hint == 2 && ncta == 2 && bn == 256 && kc == 64 && !stem && !d->out_fp32 && !direct && !d->want_stats &&
       tiles_m >= 8 && d->block_n_hint == 0 && d->stages_hint == 0) {
     if (clusters_of_4() >= 16) mc = 2;
   }
