@@ -696,10 +696,15 @@ def main():
     rows_host = [torch.empty(B * n_cand, 6, dtype=torch.float32).pin_memory() for _ in range(D)]
     results = [None] * D
 
+    u8 = {"on": False}   # second e2e record: uint8 HWC frames up, letterbox kernel on the copy stream (demo.py:37-39's input side)
+
     def upload(i):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[i % D])      # the forward that read this buffer has finished
-            dx[i % D].copy_(hx[i % 2], non_blocking=True)
+            if u8["on"]:
+                lplans[i % D].run(hx_u8[i % 2])          # 1/4 of the fp32 bytes; writes dx[i % D] (the plan's output)
+            else:
+                dx[i % D].copy_(hx[i % 2], non_blocking=True)
             up_done[i % D].record(copy_stream)
 
     def launch(i):
@@ -750,6 +755,35 @@ def main():
         win_e2e.append(max_over_ranks(t0.elapsed_time(t1)))
     ms_e2e = statistics.median(win_e2e)
     clocks = sampler.finish()
+    # ---- the same loop from uint8 HWC frames: H2D of B x S x S x 3 bytes, yolo_letterbox_u8 (/255, HWC -> CHW; identity
+    # geometry for S x S frames) on the copy stream, then the identical detect + D2H ----
+    e2e_u8 = None
+    try:
+        from yolo_for_turbines_b200.preprocess import LetterboxPlan
+        lplans = [LetterboxPlan(B, S, S, S, 3, dev) for _ in range(D)]
+        for k in range(D):
+            lplans[k].out = dx[k]                          # the letterbox kernel writes the detector's input buffer
+        gu = torch.Generator().manual_seed(4321 + rank)
+        hx_u8 = [torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, generator=gu).pin_memory() for _ in range(2)]
+        u8["on"] = True
+        e2e_run(2 * D + 1)
+        win_u8 = []
+        for _ in range(max(1, args.windows)):
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            d2h_u8 = e2e_run(args.steps)
+            t1.record()
+            barrier()
+            win_u8.append(max_over_ranks(t0.elapsed_time(t1)))
+        u8["on"] = False
+        e2e_u8 = {"value": B * world * args.steps / (statistics.median(win_u8) / 1e3), "unit": "images/s",
+                  "h2d_bytes_per_step": B * S * S * 3, "d2h_bytes_per_step": d2h_u8 // args.steps, "ms_per_window": win_u8,
+                  "input": f"{B} uint8 HWC frames of {S}x{S}x3 from pinned host memory -> yolo_letterbox_u8 -> the same "
+                           "Detector call and read-back as `e2e`"}
+    except Exception as e:   # a stage record must never take the headline line down
+        u8["on"] = False
+        e2e_u8 = {"error": f"{type(e).__name__}: {e}"}
     extra = {}
     if not args.no_extra_stages:
         for name, fn in (("map_gather", lambda: stage_map_gather(args, dev, dist, rank, world, model, cfg)),
@@ -811,6 +845,7 @@ def main():
                            "note": "standalone yolo_decode x3 on stored fp32 heads; the Detector's step fuses the decode into the "
                                    "head convs' epilogue (no head tensor in HBM), so this stage is NOT part of `value` when "
                                    "in_timed_step is false"},
+                "e2e_uint8": e2e_u8,
                 **extra,
             },
         }

@@ -61,3 +61,22 @@ def test_letterbox_feeds_the_detector():
     res, plan = det(x)
     plan.check_status()
     assert len(res.to_lists()) == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w,size", [(120, 160, 96), (96, 96, 96), (50, 33, 64)])
+def test_letterbox_plan_equals_letterbox_batch_and_oracle(h, w, size):
+    """The static serving-loop variant (one uint8 H2D copy + one launch per batch) is the same arithmetic."""
+    from oracle import preprocess_oracle as po
+    from yolo_for_turbines_b200.preprocess import LetterboxPlan, letterbox_batch
+
+    rng = np.random.default_rng(11)
+    frames = rng.integers(0, 256, (3, h, w, 3), dtype=np.uint8)
+    lp = LetterboxPlan(3, h, w, size)
+    got = lp.run(torch.from_numpy(frames).pin_memory()).cpu().numpy()
+    ref = letterbox_batch([f for f in frames], size).cpu().numpy()
+    assert np.array_equal(got, ref)
+    for i in range(3):
+        assert np.array_equal(got[i], po.letterbox(frames[i], size))
+    with pytest.raises(Exception):
+        lp.run(torch.zeros(3, h, w, 3))   # fp32 frames are refused, not converted

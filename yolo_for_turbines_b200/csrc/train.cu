@@ -199,23 +199,78 @@ __global__ void __launch_bounds__(TR_THREADS) k_bn_stats_fused(const __nv_bfloat
   }
 }
 
-// a = act(z * scale + bias) (+ residual); up2x: every pixel is stored to its 2x2 block of a (2h, 2w) tensor
+// Streaming row kernels (k_bn_act_fwd, k_bn_act_bwd_apply): every thread owns EW_ITEMS (row, 8-channel group) items
+// and issues ALL of their 16-byte loads before the first use.  With one item per thread both kernels ran at ~2.8 TB/s
+// whether the tensors came from L2 or from DRAM (time proportional to the grid size: profiles/
+// r2_train_launches_warm_before.csv).  Measured effect over the 72 layers of a step (same list, _after): the pure
+// multiply-add pass 2 of the backward 1.54 -> 1.15 ms; the forward pass with Mish 1.69 -> 1.65 ms, i.e. that one is
+// bound by instruction issue (exp + reciprocal + ~16 ALU ops per element), not by loads in flight.
+// Item j of thread t is t + j * nq with nq a multiple of `groups`, so the items of a thread share their channel group
+// (scale / bias are fetched once) and a warp's accesses stay contiguous.
+constexpr int EW_ITEMS = 4;
+__host__ __device__ inline unsigned ew_quarter(unsigned n_items, unsigned groups) {
+  const unsigned q = (n_items + EW_ITEMS - 1) / EW_ITEMS;
+  return (q + groups - 1) / groups * groups;
+}
+__device__ __forceinline__ void st8_stream(__nv_bfloat16* p, const uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// a = act(z * scale + bias) (+ residual)
 __global__ void __launch_bounds__(TR_THREADS) k_bn_act_fwd(const __nv_bfloat16* __restrict__ z, int z_pitch, RowGeom g,
                                                            const float* __restrict__ scale, const float* __restrict__ bias,
                                                            int act, const __nv_bfloat16* __restrict__ res, int res_pitch,
-                                                           __nv_bfloat16* __restrict__ y, int y_pitch, int up2x) {
+                                                           __nv_bfloat16* __restrict__ y, int y_pitch, unsigned nq) {
   // 32-bit index split (the host wrapper guarantees P * groups < 2^31): a 64-bit division per thread costs more
-  // instructions than the whole activation, and these kernels are issue-bound
+  // instructions than the whole activation
+  const unsigned t = blockIdx.x * unsigned(TR_THREADS) + threadIdx.x;
+  if (t >= nq) return;
+  const unsigned groups = unsigned(g.groups), rq = nq / groups;
+  const unsigned r0 = t / groups;
+  const int c = int(t - r0 * groups) * 8;
+  uint4 zu[EW_ITEMS], ru[EW_ITEMS];
+  bool ok[EW_ITEMS];
+#pragma unroll
+  for (int j = 0; j < EW_ITEMS; ++j) {
+    const unsigned r = r0 + unsigned(j) * rq;
+    ok[j] = r < unsigned(g.P);
+    if (ok[j]) zu[j] = ld8(z, size_t(r), z_pitch, c);
+  }
+  if (res) {
+#pragma unroll
+    for (int j = 0; j < EW_ITEMS; ++j)
+      if (ok[j]) ru[j] = ld8(res, size_t(r0 + unsigned(j) * rq), res_pitch, c);
+  }
+  float sc[8], bi[8];
+  ld8f(scale + c, sc); ld8f(bias + c, bi);
+#pragma unroll
+  for (int j = 0; j < EW_ITEMS; ++j) {
+    if (!ok[j]) continue;
+    float f[8];
+    unpack8(zu[j], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = act_fwd(fmaf(f[k], sc[k], bi[k]), act);
+    if (res) {
+      float rr[8];
+      unpack8(ru[j], rr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += rr[k];
+    }
+    st8_stream(y + size_t(r0 + unsigned(j) * rq) * y_pitch + c, pack8(f));
+  }
+}
+
+// the same with every pixel stored to its 2x2 block of a (2h, 2w) tensor (= nn.Upsample(2) of the activation); two layers
+__global__ void __launch_bounds__(TR_THREADS) k_bn_act_fwd_up2x(const __nv_bfloat16* __restrict__ z, int z_pitch, RowGeom g,
+                                                                const float* __restrict__ scale, const float* __restrict__ bias,
+                                                                int act, const __nv_bfloat16* __restrict__ res, int res_pitch,
+                                                                __nv_bfloat16* __restrict__ y, int y_pitch) {
   const unsigned idx = blockIdx.x * unsigned(TR_THREADS) + threadIdx.x;
   if (idx >= unsigned(g.P) * unsigned(g.groups)) return;
   const unsigned r = idx / unsigned(g.groups);
   const int c = int(idx - r * unsigned(g.groups)) * 8;
   float f[8];
   unpack8(ld8(z, size_t(r), z_pitch, c), f);
-  const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
-  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-  const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float sc[8], bi[8];
+  ld8f(scale + c, sc); ld8f(bias + c, bi);
 #pragma unroll
   for (int k = 0; k < 8; ++k) f[k] = act_fwd(fmaf(f[k], sc[k], bi[k]), act);
   if (res) {
@@ -225,20 +280,16 @@ __global__ void __launch_bounds__(TR_THREADS) k_bn_act_fwd(const __nv_bfloat16* 
     for (int k = 0; k < 8; ++k) f[k] += rr[k];
   }
   const uint4 o = pack8(f);
-  if (!up2x) {
-    *reinterpret_cast<uint4*>(y + size_t(r) * y_pitch + c) = o;
-  } else {
-    const long long hw = (long long)g.h * g.w;
-    const long long img = r / hw;
-    const int rem = int(r - img * hw);
-    const int i = rem / g.w, j = rem - i * g.w;
-    const size_t W2 = size_t(2 * g.w);
-    const size_t r00 = (size_t(img) * (2 * g.h) + 2 * i) * W2 + 2 * j;
-    *reinterpret_cast<uint4*>(y + r00 * y_pitch + c) = o;
-    *reinterpret_cast<uint4*>(y + (r00 + 1) * y_pitch + c) = o;
-    *reinterpret_cast<uint4*>(y + (r00 + W2) * y_pitch + c) = o;
-    *reinterpret_cast<uint4*>(y + (r00 + W2 + 1) * y_pitch + c) = o;
-  }
+  const long long hw = (long long)g.h * g.w;
+  const long long img = r / hw;
+  const int rem = int(r - img * hw);
+  const int i = rem / g.w, j = rem - i * g.w;
+  const size_t W2 = size_t(2 * g.w);
+  const size_t r00 = (size_t(img) * (2 * g.h) + 2 * i) * W2 + 2 * j;
+  *reinterpret_cast<uint4*>(y + r00 * y_pitch + c) = o;
+  *reinterpret_cast<uint4*>(y + (r00 + 1) * y_pitch + c) = o;
+  *reinterpret_cast<uint4*>(y + (r00 + W2) * y_pitch + c) = o;
+  *reinterpret_cast<uint4*>(y + (r00 + W2 + 1) * y_pitch + c) = o;
 }
 
 // gradient arriving at this layer's output, 8 channels of row r; up2x = backward of nn.Upsample(2): the sum of
@@ -324,7 +375,9 @@ __global__ void __launch_bounds__(TR_THREADS, 3) k_bn_act_bwd_reduce(const BnBwd
     };
     long long r = r0 + lane;
     if (!p.up2x) {
-      for (; r + lanes < r1; r += 2ll * lanes) {  // two rows (four 16-byte loads) in flight per thread
+      for (; r + lanes < r1; r += 2ll * lanes) {  // two rows (four 16-byte loads) in flight per thread; four rows measured
+        // slower (2.82 vs 2.64 ms over the 72 layers: the Mish derivative makes this pass issue-bound, and the deeper
+        // unroll costs a resident block per SM)
         const uint4 z0 = ld8(p.z, size_t(r), p.z_pitch, c), z1 = ld8(p.z, size_t(r + lanes), p.z_pitch, c);
         const uint4 d0 = ld8(p.dA, size_t(r), p.dA_pitch, c), d1 = ld8(p.dA, size_t(r + lanes), p.dA_pitch, c);
         float zf[8], d[8];
@@ -352,12 +405,46 @@ __global__ void k_bias_finalize(const double* __restrict__ sums, int C, float* _
   if (c < C) dbias[c] = float(sums[2 * c]);
 }
 
-// Pass 2: dz = scale*dy + c1*z + c0, in place over the dy that pass 1 left in the dz buffer; optional zero-stuffed
-// copy at 2x resolution (value at (2i, 2j))
-__global__ void __launch_bounds__(TR_THREADS, 4) k_bn_act_bwd_apply(const BnBwdParams p, const float* __restrict__ c1,
-                                                                    const float* __restrict__ c0, __nv_bfloat16* __restrict__ dz,
-                                                                    int dz_pitch, __nv_bfloat16* __restrict__ stuffed,
-                                                                    int stuffed_pitch) {
+// Pass 2: dz = scale*dy + c1*z + c0, in place over the dy that pass 1 left in the dz buffer (EW_ITEMS items per thread,
+// all loads first: see k_bn_act_fwd)
+__global__ void __launch_bounds__(TR_THREADS) k_bn_act_bwd_apply(const BnBwdParams p, const float* __restrict__ c1,
+                                                                 const float* __restrict__ c0, __nv_bfloat16* __restrict__ dz,
+                                                                 int dz_pitch, unsigned nq) {
+  const RowGeom& g = p.g;
+  const unsigned t = blockIdx.x * unsigned(TR_THREADS) + threadIdx.x;
+  if (t >= nq) return;
+  const unsigned groups = unsigned(g.groups), rq = nq / groups;
+  const unsigned r0 = t / groups;
+  const int c = int(t - r0 * groups) * 8;
+  uint4 zu[EW_ITEMS], du[EW_ITEMS];
+  bool ok[EW_ITEMS];
+#pragma unroll
+  for (int j = 0; j < EW_ITEMS; ++j) {
+    const unsigned r = r0 + unsigned(j) * rq;
+    ok[j] = r < unsigned(g.P);
+    if (ok[j]) {
+      zu[j] = ld8(p.z, size_t(r), p.z_pitch, c);
+      du[j] = *reinterpret_cast<const uint4*>(dz + size_t(r) * dz_pitch + c);   // dy, left here by pass 1
+    }
+  }
+  float sc[8], a1[8], a0[8];
+  ld8f(p.scale + c, sc); ld8f(c1 + c, a1); ld8f(c0 + c, a0);
+#pragma unroll
+  for (int j = 0; j < EW_ITEMS; ++j) {
+    if (!ok[j]) continue;
+    float zf[8], d[8], o[8];
+    unpack8(zu[j], zf); unpack8(du[j], d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(sc[k], d[k], fmaf(a1[k], zf[k], a0[k]));
+    *reinterpret_cast<uint4*>(dz + size_t(r0 + unsigned(j) * rq) * dz_pitch + c) = pack8(o);
+  }
+}
+
+// the same plus a zero-stuffed copy at 2x resolution (value at (2i, 2j)): the stride-2 layers' data-gradient operand
+__global__ void __launch_bounds__(TR_THREADS, 4) k_bn_act_bwd_apply_stuffed(const BnBwdParams p, const float* __restrict__ c1,
+                                                                            const float* __restrict__ c0, __nv_bfloat16* __restrict__ dz,
+                                                                            int dz_pitch, __nv_bfloat16* __restrict__ stuffed,
+                                                                            int stuffed_pitch) {
   const RowGeom& g = p.g;
   const unsigned idx = blockIdx.x * unsigned(TR_THREADS) + threadIdx.x;   // 32-bit split, see k_bn_act_fwd
   if (idx >= unsigned(g.P) * unsigned(g.groups)) return;
@@ -374,19 +461,17 @@ __global__ void __launch_bounds__(TR_THREADS, 4) k_bn_act_bwd_apply(const BnBwdP
   }
   const uint4 u = pack8(o);
   *reinterpret_cast<uint4*>(dz + size_t(r) * dz_pitch + c) = u;
-  if (stuffed) {
-    const long long hw = (long long)g.h * g.w;
-    const long long img = r / hw;
-    const int rem = int(r - img * hw);
-    const int i = rem / g.w, j = rem - i * g.w;
-    const size_t W2 = size_t(2 * g.w);
-    const size_t r00 = (size_t(img) * (2 * g.h) + 2 * i) * W2 + 2 * j;
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(stuffed + r00 * stuffed_pitch + c) = u;
-    *reinterpret_cast<uint4*>(stuffed + (r00 + 1) * stuffed_pitch + c) = zero;
-    *reinterpret_cast<uint4*>(stuffed + (r00 + W2) * stuffed_pitch + c) = zero;
-    *reinterpret_cast<uint4*>(stuffed + (r00 + W2 + 1) * stuffed_pitch + c) = zero;
-  }
+  const long long hw = (long long)g.h * g.w;
+  const long long img = r / hw;
+  const int rem = int(r - img * hw);
+  const int i = rem / g.w, j = rem - i * g.w;
+  const size_t W2 = size_t(2 * g.w);
+  const size_t r00 = (size_t(img) * (2 * g.h) + 2 * i) * W2 + 2 * j;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  *reinterpret_cast<uint4*>(stuffed + r00 * stuffed_pitch + c) = u;
+  *reinterpret_cast<uint4*>(stuffed + (r00 + 1) * stuffed_pitch + c) = zero;
+  *reinterpret_cast<uint4*>(stuffed + (r00 + W2) * stuffed_pitch + c) = zero;
+  *reinterpret_cast<uint4*>(stuffed + (r00 + W2 + 1) * stuffed_pitch + c) = zero;
 }
 
 // forward + data-gradient operand packs of one layer in one pass over the fp32 weights:
@@ -524,10 +609,10 @@ int check_rows(long long P, int C, int pitch, const char* what) {
   YB_REQUIRE(P * (C / 8) < (1ll << 31), "%s: more than 2^31 (row, channel group) pairs", what);
   return YB_OK;
 }
-int reduce_grid(long long P, int groups) {
+int reduce_grid(long long P, int groups, int per_sm = 3) {
   const int lanes = TR_THREADS / groups;
   long long blocks = (P + (long long)lanes * 8 - 1) / ((long long)lanes * 8);  // >= 8 rows per thread
-  const int cap = 148 * 3;  // every block ends with one double atomic per channel statistic: the tail grows with the grid
+  const int cap = 148 * per_sm;  // every block ends with one double atomic per channel statistic: the tail grows with the grid
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -578,9 +663,16 @@ extern "C" int yolo_bn_act_fwd(const void* z, long long P, int C, int z_pitch, c
   YB_REQUIRE(!up2x || (h >= 1 && w >= 1 && P % ((long long)h * w) == 0), "yolo_bn_act_fwd: bad 2x geometry");
   RowGeom g{P, C, C / 8, h, w};
   const long long n = P * g.groups;
-  k_bn_act_fwd<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, (cudaStream_t)stream>>>(
-      static_cast<const __nv_bfloat16*>(z), z_pitch, g, scale, bias, act, static_cast<const __nv_bfloat16*>(residual), res_pitch,
-      static_cast<__nv_bfloat16*>(y), y_pitch, up2x);
+  if (up2x) {
+    k_bn_act_fwd_up2x<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, (cudaStream_t)stream>>>(
+        static_cast<const __nv_bfloat16*>(z), z_pitch, g, scale, bias, act, static_cast<const __nv_bfloat16*>(residual), res_pitch,
+        static_cast<__nv_bfloat16*>(y), y_pitch);
+  } else {
+    const unsigned nq = ew_quarter((unsigned)n, (unsigned)g.groups);
+    k_bn_act_fwd<<<(nq + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, (cudaStream_t)stream>>>(
+        static_cast<const __nv_bfloat16*>(z), z_pitch, g, scale, bias, act, static_cast<const __nv_bfloat16*>(residual), res_pitch,
+        static_cast<__nv_bfloat16*>(y), y_pitch, nq);
+  }
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
@@ -607,8 +699,14 @@ extern "C" int yolo_bn_act_bwd(const void* dA, int dA_pitch, int up2x, const voi
                                                                              static_cast<__nv_bfloat16*>(dz), dz_pitch);
   YB_CHECK_LAUNCH();
   const long long n = P * p.g.groups;
-  k_bn_act_bwd_apply<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, stream>>>(
-      p, c1c0, c1c0 + C, static_cast<__nv_bfloat16*>(dz), dz_pitch, static_cast<__nv_bfloat16*>(stuffed), stuffed_pitch);
+  if (stuffed) {
+    k_bn_act_bwd_apply_stuffed<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, stream>>>(
+        p, c1c0, c1c0 + C, static_cast<__nv_bfloat16*>(dz), dz_pitch, static_cast<__nv_bfloat16*>(stuffed), stuffed_pitch);
+  } else {
+    const unsigned nq = ew_quarter((unsigned)n, (unsigned)p.g.groups);
+    k_bn_act_bwd_apply<<<(nq + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, stream>>>(p, c1c0, c1c0 + C,
+                                                                                      static_cast<__nv_bfloat16*>(dz), dz_pitch, nq);
+  }
   YB_CHECK_LAUNCH();
   return YB_OK;
 }

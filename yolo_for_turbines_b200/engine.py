@@ -461,7 +461,8 @@ class Engine:
         self.impl_hint, self.cta_pair_hint = 0, 0  # 0 = library defaults (include/yolo_b200.h)
         self.pdl_hint, self.tail_split_hint = 0, 0   # 1 switches the feature off (A/B runs, scripts/layer_times.py)
         self.row_hint = 0                            # include/yolo_b200.h: 0 auto | 1 off | 2 on, base_offset variant
-        self.mc_hint = 0                             # weight-tile multicast across two CTA pairs: 2 = on (measured slower)
+        # weight-tile multicast across two CTA pairs: 2 = on (measured slower in isolation; YOLO_B200_MC=2 for A/B runs)
+        self.mc_hint = int(os.environ.get("YOLO_B200_MC", "0"))
         # fused stem (default): the first conv reads the NCHW fp32 image itself (TMA windows -> bf16 taps in shared memory),
         # no patch matrix in HBM.  YOLO_B200_FUSED_STEM=0 restores yolo_input_patchify + a K=64 GEMM (the A/B baseline).
         self.stem_direct = os.environ.get("YOLO_B200_FUSED_STEM") != "0"

@@ -3,6 +3,7 @@ called by code/demo.py:37-39) and of `plot_original`'s inverse box mapping (code
 
     x = letterbox_batch([img0, img1, ...], 416)        # uint8 HWC images of any size -> (B, 3, 416, 416) fp32 CUDA
     boxes = unletterbox_boxes(kept_rows, h, w, 416)     # rows normalised to the square -> to the original image
+    x = LetterboxPlan(64, 480, 640, 416).run(frames)    # serving loop: fixed frame size, one copy + one launch per batch
 
 `letterbox_batch(...)[i]` equals `set_only_image_transforms(S)(image=img_i)["image"]`: albumentations' LongestMaxSize
 (round-half-even output size, cv2.INTER_LINEAR uint8 fixed point) + centred zero PadIfNeeded + /255 + ToTensorV2, in
@@ -68,6 +69,42 @@ def letterbox_batch(images: Sequence, size: int, device=None, out: torch.Tensor 
         lib.yolo_letterbox_u8(ptr(table), B, size, channels, ptr(out), stream_ptr(device))
     out._yb_keepalive = (keep, table)   # sources and table must outlive the asynchronous launch
     return out
+
+
+class LetterboxPlan:
+    """Static serving-loop variant of `letterbox_batch` for frames of ONE size: a device uint8 staging buffer
+    [B, h, w, c], the descriptor table and the fp32 [B, c, size, size] output are allocated once, so a step is one
+    H2D copy of the uint8 frames (a quarter of the fp32 tensor's bytes even before any down-scaling) and one launch:
+
+        lp = LetterboxPlan(64, 480, 640, 416)
+        x = lp.run(frames_u8_pinned)          # [64, 480, 640, 3] uint8, host (pinned) or device -> [64, 3, 416, 416] fp32
+
+    Same arithmetic as `letterbox_batch` (it is the same kernel, yolo_letterbox_u8)."""
+
+    def __init__(self, batch: int, h: int, w: int, size: int, channels: int = 3, device=None):
+        device = torch.device("cuda" if device is None else device)
+        if device.type != "cuda":
+            raise YoloB200Error("LetterboxPlan runs on a CUDA device only (no CPU fallback)")
+        if C.sizeof(_Desc) != lib.yolo_letterbox_desc_bytes():
+            raise YoloB200Error("letterbox descriptor layout mismatch between preprocess.py and libyolo_b200.so")
+        self.batch, self.h, self.w, self.size, self.channels, self.device = batch, h, w, size, channels, device
+        self.staging = torch.empty(batch, h, w, channels, dtype=torch.uint8, device=device)
+        self.out = torch.empty(batch, channels, size, size, dtype=torch.float32, device=device)
+        nh, nw, top, left = letterbox_geometry(h, w, size)
+        descs = (_Desc * batch)()
+        per = h * w * channels
+        for i in range(batch):
+            descs[i] = _Desc(self.staging.data_ptr() + i * per, h, w, nh, nw, top, left)
+        self.table = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(device)
+
+    def run(self, frames: torch.Tensor) -> torch.Tensor:
+        """Asynchronous on the current stream; `frames` is uint8 [B, h, w, c] (pinned host memory for a non-blocking copy)."""
+        if frames.dtype != torch.uint8 or tuple(frames.shape) != tuple(self.staging.shape):
+            raise YoloB200Error(f"expected uint8 frames of shape {tuple(self.staging.shape)}, got {frames.dtype} {tuple(frames.shape)}")
+        self.staging.copy_(frames, non_blocking=True)
+        with torch.cuda.device(self.device):
+            lib.yolo_letterbox_u8(ptr(self.table), self.batch, self.size, self.channels, ptr(self.out), stream_ptr(self.device))
+        return self.out
 
 
 def unletterbox_boxes(boxes, orig_h: int, orig_w: int, size: int):
