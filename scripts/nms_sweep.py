@@ -15,11 +15,35 @@ from oracle import yolo_oracle as orc  # noqa: E402  (CPU baseline leg only)
 from yolo_for_turbines_b200.utils import NmsWorkspace, batched_nms, map_match  # noqa: E402
 
 B = 64
-dev = torch.device("cuda", 0)
+WORLD, RANK, LOCAL = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+torch.cuda.set_device(LOCAL)
+dev = torch.device("cuda", LOCAL)
+dist = None
+if WORLD > 1:   # torchrun: every rank sweeps its own seeded boxes (weak scaling, no collective on the data path);
+    import torch.distributed as dist   # NCCL only carries the barrier and the max-over-ranks of the device times
+    _fd = os.dup(1)
+    os.dup2(2, 1)   # NCCL's banner goes to stderr
+    dist.init_process_group("nccl", device_id=dev)
+    dist.barrier()
+    sys.stdout.flush()
+    os.dup2(_fd, 1)
+
+
+def max_over_ranks(ms):
+    if dist is None:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def say(*a, **k):
+    if RANK == 0:
+        print(*a, **k)
 
 
 def make(total, nc, seed=42):
-    g = torch.Generator(device=dev).manual_seed(seed)
+    g = torch.Generator(device=dev).manual_seed(seed + RANK)
     b = torch.rand(total, 6, generator=g, device=dev)
     b[:, 2:4] = 0.02 + 0.28 * b[:, 2:4]
     b[:, 5] = torch.floor(b[:, 5] * nc)
@@ -33,16 +57,19 @@ def gpu_time(fn, reps=5):
     torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
+        if dist is not None:
+            dist.barrier()
         a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
         c.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(c))
+        ts.append(max_over_ranks(a.elapsed_time(c)))
     return sorted(ts)[len(ts) // 2]
 
 
-print(f"{'N/batch':>9s} {'nc':>3s} {'conf':>5s} {'kept':>8s} {'GPU ms':>8s} {'GPU Mbox/s':>11s} {'CPU ref s (extrap.)':>20s} {'CPU kbox/s':>10s} {'speedup':>9s}")
+say(f"{WORLD} GPU(s); N/batch is PER GPU, Mbox/s is the aggregate over all ranks (max-over-ranks device time)")
+say(f"{'N/batch':>9s} {'nc':>3s} {'conf':>5s} {'kept':>8s} {'GPU ms':>8s} {'GPU Mbox/s':>11s} {'CPU ref s (extrap.)':>20s} {'CPU kbox/s':>10s} {'speedup':>9s}")
 for total in (10_000, 30_000, 100_000, 300_000, 1_000_000):
     per = total // B
     total = per * B
@@ -56,7 +83,7 @@ for total in (10_000, 30_000, 100_000, 300_000, 1_000_000):
             # CPU: the reference's algorithm on image 0 (and 1 more when cheap), scaled to 64 images
             n_img = 2 if per <= 2000 else 1
             cpu = 0.0
-            if per <= 5000:
+            if per <= 5000 and WORLD == 1:
                 for i in range(n_img):
                     rows = boxes[i * per:(i + 1) * per].cpu().tolist()
                     t0 = time.perf_counter()
@@ -68,11 +95,11 @@ for total in (10_000, 30_000, 100_000, 300_000, 1_000_000):
                 sp = f"{cpu * 1e3 / ms:9.0f}"
             else:
                 cpu_s, rate, sp = f"{'(skipped: > minutes)':>20s}", f"{'-':>10s}", f"{'-':>9s}"
-            print(f"{total:9d} {nc:3d} {conf:5.2f} {kept:8d} {ms:8.3f} {total / ms / 1e3:11.1f} {cpu_s} {rate} {sp}", flush=True)
+            say(f"{total:9d} {nc:3d} {conf:5.2f} {kept:8d} {ms:8.3f} {WORLD * total / ms / 1e3:11.1f} {cpu_s} {rate} {sp}", flush=True)
 
 # mAP matching at evaluation scale: D detections vs G ground truths
-print()
-print(f"{'D dets':>9s} {'G gts':>7s} {'images':>7s} {'GPU ms (map_match)':>20s}")
+say()
+say(f"{'D dets':>9s} {'G gts':>7s} {'images':>7s} {'GPU ms (map_match)':>20s}")
 for D, G, n_img in ((10_000, 1_000, 64), (100_000, 10_000, 640), (1_000_000, 35_000, 5000)):
     g = torch.Generator(device=dev).manual_seed(7)
     gts = torch.rand(G, 7, generator=g, device=dev)
@@ -83,4 +110,7 @@ for D, G, n_img in ((10_000, 1_000, 64), (100_000, 10_000, 640), (1_000_000, 35_
     dets[:, 1:5] += 0.03 * torch.randn(D, 4, generator=g, device=dev)
     dets[:, 5] = torch.rand(D, generator=g, device=dev)
     ms = gpu_time(lambda: map_match(dets, gts, 0.5, "center"), reps=3)
-    print(f"{D:9d} {G:7d} {n_img:7d} {ms:20.3f}")
+    say(f"{D:9d} {G:7d} {n_img:7d} {ms:20.3f}")
+if dist is not None:
+    dist.barrier()
+    dist.destroy_process_group()
