@@ -138,10 +138,24 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // Mish with one exp and one fast divide (the form the training kernels use, csrc/train.cu): with n = e^v,
 // m = n (n + 2):  tanh(softplus(v)) = m / (m + 2).  Agrees with the libm form far below one bf16 ulp and is ~10
 // instructions instead of ~60 -- the libm form inlined 64 times made up nine tenths of the conv kernel's code.
+// Written as v - 2 v / (m + 2) it needs no clamp: m + 2 overflows to +inf for v > 44, the quotient is 0 and the result v.
+// ex2 / rcp are issued as the bare .ftz MUFU forms: __expf / __fdividef wrap each in a denormal-range guard
+// (FSETP + two predicated FMULs), which doubles the instruction count of this 7-operation function; here a flushed
+// e^v = 0 gives m + 2 = 2 and a result of exactly 0 (true value |v| e^v < 1e-36), and m + 2 >= 2 is never denormal.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float mish_fast(float v) {
-  const float n = __expf(fminf(v, 20.f));
-  const float m = n * (n + 2.f);
-  return v > 20.f ? v : v * __fdividef(m, m + 2.f);  // NaN stays NaN
+  const float n = ex2_ftz(v * 1.4426950408889634f);
+  const float a = fmaf(n, n + 2.f, 2.f);
+  return fmaf(-2.f, v * rcp_ftz(a), v);  // NaN stays NaN
 }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }

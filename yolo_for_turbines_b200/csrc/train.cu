@@ -26,6 +26,9 @@ using convptx::pack_bf16;
 
 constexpr int TR_THREADS = 256;
 
+// (Programmatic dependent launch was tried on the row kernels between two convs and measured SLOWER: backward pass
+// 8.67 -> 9.75 ms (LeakyReLU, batch 32, 416^2).  The early-started data-gradient conv CTAs hold their SMs' shared memory
+// while they wait, which keeps the weight-gradient kernels of the side stream off those SMs.)
 __device__ __forceinline__ void unpack8(const uint4 u, float (&f)[8]) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
@@ -37,35 +40,29 @@ __device__ __forceinline__ uint4 ld8(const __nv_bfloat16* base, size_t row, int 
   return __ldg(reinterpret_cast<const uint4*>(base + row * size_t(pitch) + c));
 }
 
-// Mish via one exp: tanh(softplus(y)) = m / (m + 2) with n = e^y, m = n (n + 2); sigmoid(y) = n / (1 + n).
-// (The inference epilogue keeps the libm form; both agree far below one bf16 ulp.)
-__device__ __forceinline__ float mish_tanh_sp(float y, float& sg) {
-  const float n = __expf(fminf(y, 20.f));
-  const float m = n * (n + 2.f);
-  sg = __fdividef(n, 1.f + n);
-  return y > 20.f ? 1.f : __fdividef(m, m + 2.f);
-}
+// Forward Mish in 7 operations with one exp and one reciprocal: with n = e^y and a = n (n + 2) + 2,
+// y tanh(softplus(y)) = y (a - 2) / a = y - 2 y / a.  No clamp is needed: a overflows to +inf for y > 44, 1 / a = 0 and
+// the result is y (exact to fp32 there); for very negative y, a -> 2 and the result cancels to 0 with an absolute
+// error below |y| 2^-23 (the true value is y e^y).  The pass is instruction-issue bound (see EW_ITEMS below).
+__device__ __forceinline__ float mish_fwd(float y) { return convptx::mish_fast(y); }   // 7 SASS operations, conv_ptx.cuh
 __device__ __forceinline__ float act_fwd(float y, int act) {
   if (act == YB_ACT_LEAKY) return fmaxf(y, 0.1f * y);
-  if (act == YB_ACT_MISH) {
-    float sg;
-    return y * mish_tanh_sp(y, sg);
-  }
+  if (act == YB_ACT_MISH) return mish_fwd(y);
   return y;
 }
-// d act(y) / dy.  Mish: with n = e^y, m = n (n + 2): tanh(softplus) = t = m / (m + 2), sigmoid = s = n / (1 + n) and
-// d/dy = t + y s (1 - t^2).  Both quotients share ONE reciprocal, r = 1 / ((m + 2)(1 + n)) -- the kernels that call
-// this are bound by the special-function unit (ncu: XU pipe 40 %, DRAM 28 %), so a MUFU per element matters.
+// d act(y) / dy.  Mish in closed form with one exp and one reciprocal: with n = e^y and a = n (n + 2) + 2,
+//   d/dy [y tanh(softplus(y))] = n w / a^2,   w = 4 (y + 1) + n (4 y + 6 + n (4 + n))
+// (14 operations; the tanh / sigmoid form needed 19, and the kernel that calls this is instruction-issue bound).
+// y is clamped at 20, where the derivative is 1 to fp32 precision and n^3, n w and 1 / a^2 are all still in range.
 __device__ __forceinline__ float act_grad(float y, int act) {
   if (act == YB_ACT_LEAKY) return y > 0.f ? 1.f : 0.1f;
   if (act == YB_ACT_MISH) {
-    const float n = __expf(fminf(y, 20.f));
-    const float m = n * (n + 2.f);
-    const float a = m + 2.f, b = 1.f + n;
-    const float r = __fdividef(1.f, a * b);   // MUFU.RCP; (m + 2)(1 + n) <= 1.2e26 for y <= 20: no overflow
-    const float t = m * b * r, sg = n * a * r;
-    const float g = fmaf(y * sg, fmaf(-t, t, 1.f), t);
-    return y > 20.f ? 1.f : g;
+    y = fminf(y, 20.f);
+    const float n = convptx::ex2_ftz(y * 1.4426950408889634f);   // bare MUFU forms: see mish_fast (conv_ptx.cuh)
+    const float a = fmaf(n, n + 2.f, 2.f);
+    const float w = fmaf(n, fmaf(n, n + 4.f, fmaf(4.f, y, 6.f)), fmaf(4.f, y, 4.f));
+    const float r = convptx::rcp_ftz(a);
+    return (n * w) * (r * r);
   }
   return 1.f;
 }

@@ -193,6 +193,7 @@ class TrainPlan:
             d.ksize, d.stride, d.pad = pc.k_eff, pc.stride_eff, pc.pad_eff
             d.act, d.out_fp32, d.check_nan = 0, int(op.head), 0
             d.want_stats = int(not op.head)
+            d.pdl_hint = 1 if "f" in os.environ.get("YOLO_B200_TRAIN_NO_PDL", "") else 0   # A/B: "f" forward, "b" backward convs
             x_ptr = C.c_void_p(sroot.buf.data_ptr() + soff * 2)
             if op.head:
                 droot, _ = op.dst.resolve()
@@ -226,6 +227,7 @@ class TrainPlan:
                 dd.batch, dd.h_in, dd.w_in = B, op.ho, op.wo
                 dd.c_in, dd.in_pitch = pc.c_out_pad, pc.c_out_pad
                 dd.stride, dd.out_pitch = 1, op.src.C
+                dd.pdl_hint = 1 if "b" in os.environ.get("YOLO_B200_TRAIN_NO_PDL", "") else 0
                 if s2:   # dx[2a+r][2b+t] from dz[a+da][b+db]: stride-1 sub-convolution per output row parity
                     dd.c_out = dd.c_out_pad = 2 * pc.c_in_eff
                     dd.ksize, dd.pad = r + 1, 0
