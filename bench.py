@@ -106,7 +106,7 @@ def workload_config(args, world: int) -> dict:
 def nms_launch_count(batch: int) -> int:
     img_passes = 0 if batch <= 1 else ((max(batch - 1, 1).bit_length() + 7) // 8)
     sort = (4 + img_passes) * 3
-    return 3 + sort + 1 + sort + 1 + 1 + 4  # K4 | sort#1 | class keys | sort#2 | gather | nms | keep+offsets
+    return 3 + sort + 1 + sort + 1 + 2 + 4  # K4 | sort#1 | class keys | sort#2 | gather | nms (warp + CTA kernels) | keep+offsets
 
 
 # ------------------------------------------------------------------------------------------ CPU

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_sort_nms.py tests/test_gpu_model.py -q -m gpu --tb=short -x > gpurun_out/r2_c44_tests.log 2>&1; echo "tests exit $?"; tail -n 3 gpurun_out/r2_c44_tests.log | cut -c1-300
+python scripts/nms_round_profile.py 64 416 0.5 2>&1 | tail -8; python scripts/nms_round_profile.py 32 608 0.01 2>&1 | tail -8
+python scripts/nms_segments_stats.py 64 416 0.5 2>&1 | tail -1; python scripts/nms_segments_stats.py 32 608 0.01 2>&1 | tail -1

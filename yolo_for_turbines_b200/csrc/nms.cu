@@ -11,6 +11,13 @@
 
 namespace {
 
+#ifdef YB_NMS_PROFILE   // dev build only (scripts/nms_round_profile.py): per-phase clock sums of the register path, segments >= 1024 boxes
+__device__ unsigned long long g_nms_prof[8];
+#define NMS_T(i) do { if (prof) { const long long t_ = clock64(); pt[i] += t_ - t_last; t_last = t_; } } while (0)
+#else
+#define NMS_T(i) do { } while (0)
+#endif
+
 
 __device__ __forceinline__ int find_image(const int32_t* __restrict__ off, int batch, int i) {
   int lo = 0, hi = batch;  // largest b with off[b] <= i
@@ -179,6 +186,64 @@ __device__ __forceinline__ uint32_t nms_candidates(uint32_t bins, const uint32_t
   return mx & my;
 }
 
+// position of the (r+1)-th set bit of mask (r < popc(mask)): five popc steps instead of __fns' software loop
+__device__ __forceinline__ int nms_nth_set_bit(uint32_t mask, int r) {
+  int base = 0, c;
+  c = __popc(mask & 0xffffu); if (r >= c) { r -= c; base += 16; mask >>= 16; }
+  c = __popc(mask & 0xffu);   if (r >= c) { r -= c; base += 8;  mask >>= 8; }
+  c = __popc(mask & 0xfu);    if (r >= c) { r -= c; base += 4;  mask >>= 4; }
+  c = __popc(mask & 0x3u);    if (r >= c) { r -= c; base += 2;  mask >>= 2; }
+  c = int(mask & 1u);         if (r >= c) { base += 1; }
+  return base;
+}
+
+// Segments of at most 32 boxes -- every (image, class) group of a trained detector, and most groups of the standalone
+// sweep -- are settled by ONE WARP each, in registers: lane l holds box l, row i of the suppression matrix is one
+// ballot, and only rows of boxes that are still alive are evaluated.  Longer segments are appended to big_list for
+// k_nms_segments (a 512-thread CTA per tiny segment cost ~6 us of barriers and dependent loads each).
+__global__ void __launch_bounds__(256)
+k_nms_small(const float4* __restrict__ cbox, const float* __restrict__ area, const uint64_t* __restrict__ key2,
+            const int32_t* __restrict__ val2, const int32_t* __restrict__ seg_starts, const int32_t* __restrict__ nseg_dev,
+            const int32_t* __restrict__ n_dev, float thr, const uint8_t* __restrict__ flags, uint8_t* __restrict__ keep,
+            const bool int_classes, int32_t* __restrict__ big_list, int32_t* __restrict__ nbig) {
+  const int n = *n_dev, nseg = *nseg_dev;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const bool thr_pos = thr > 0.f;
+  for (int sg = warp; sg < nseg; sg += nwarps) {
+    const int s0 = seg_starts[sg];
+    const uint64_t k = key2[s0];
+    const int q = s0 + lane;
+    const bool mine = q < n && key2[q] == k;          // sorted keys: the members are lanes 0 .. m-1
+    const uint32_t members = __ballot_sync(0xffffffffu, mine);
+    const bool more = (s0 + 32 < n) && key2[s0 + 32] == k;
+    if (members == 0xffffffffu && more) {              // longer than a warp
+      if (lane == 0) big_list[atomicAdd(nbig, 1)] = sg;
+      continue;
+    }
+    if (!int_classes && uint32_t(k) == 0x7fc00000u) {  // NaN class: != is always true (utils.py:178) => all kept
+      if (mine) keep[val2[q]] = 1;
+      continue;
+    }
+    const int m = __popc(members);
+    const float4 b = mine ? cbox[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float a = mine ? area[q] : 0.f;
+    const bool gen = !thr_pos || (mine && (flags[q] & 2));
+    const int out = mine ? val2[q] : 0;
+    uint32_t alive = members;
+    for (int i = 0; i + 1 < m; ++i) {
+      if (!((alive >> i) & 1u)) continue;              // uniform: a suppressed box suppresses nothing
+      const float4 bi = make_float4(__shfl_sync(0xffffffffu, b.x, i), __shfl_sync(0xffffffffu, b.y, i),
+                                    __shfl_sync(0xffffffffu, b.z, i), __shfl_sync(0xffffffffu, b.w, i));
+      const float ai = __shfl_sync(0xffffffffu, a, i);
+      const bool gi = __shfl_sync(0xffffffffu, (int)gen, i) != 0;
+      const bool sup = mine && lane > i && nms_pair(bi, ai, b, a, gi || gen, thr, thr_pos);
+      alive &= ~__ballot_sync(0xffffffffu, sup);
+    }
+    if (mine && ((alive >> lane) & 1u)) keep[out] = 1;  // keep[] is zero-initialised
+  }
+}
+
 // NT threads per segment CTA: 512 suits few long segments, 128 many short ones (4x the resident CTAs per SM: 24 KB of
 // bins and a quarter of the threads each) -- the host picks by the average segment length it can expect.
 template <int NT>
@@ -187,10 +252,13 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
                const uint64_t* __restrict__ key2, const int32_t* __restrict__ val2,
                const int32_t* __restrict__ seg_starts, const int32_t* __restrict__ nseg_dev,
                const int32_t* __restrict__ n_dev, float thr, uint8_t* __restrict__ suppressed,
-               uint8_t* __restrict__ keep, const bool int_classes) {
+               uint8_t* __restrict__ keep, const bool int_classes, const int32_t* __restrict__ big_list) {
   __shared__ float4 s_cbox[32];
   __shared__ float s_carea[32];
   __shared__ uint32_t s_row[32], s_binx[32], s_biny[32];
+  // s_tab[axis][span][b] = OR of the bin masks b .. b + span: the survivors a box with bin range [b, b + span] can meet on
+  // that axis, in ONE shared-memory read (the per-bin loop of nms_candidates made step (c) a chain of dependent reads)
+  __shared__ uint32_t s_tab[256];
   __shared__ uint32_t s_alive, s_cgen, s_kept, s_win[4];
   extern __shared__ uint32_t s_bins[];  // [NMS_QPT][NMS_THREADS] packed spatial bins, 96 KB (dynamic)
   __shared__ int s_cpos[32];
@@ -199,8 +267,8 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
   const bool thr_pos = thr > 0.f;
   const int n = *n_dev, nseg = *nseg_dev;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
-    const int s0 = seg_starts[s];
+  for (int si = blockIdx.x; si < nseg; si += gridDim.x) {   // nseg_dev = number of entries of big_list (k_nms_small)
+    const int s0 = seg_starts[big_list[si]];
     const uint64_t k = key2[s0];
     if (tid == 0) {  // upper bound of k in the sorted keys
       int lo = s0, hi = n;
@@ -238,6 +306,11 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
       // ---- register path: chunks are the next 32 boxes that are still ALIVE (dead boxes are skipped, which
       // cuts the number of serial rounds from m/32 to ~(#survivors)/32), taken from a 128-position window.
       int f = 0;  // frontier: first position (relative to s0) not yet consumed
+#ifdef YB_NMS_PROFILE
+      const bool prof = tid == 0 && m >= 1024;
+      long long pt[6] = {0, 0, 0, 0, 0, 0}, t_last = clock64();
+      unsigned long long rounds = 0;
+#endif
       while (f < m) {
         const int wb = f >> 5;
         // every warp publishes the blocks it owns that fall into the window
@@ -252,6 +325,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
           }
         }
         __syncthreads();
+        NMS_T(0);
         // (0b) every warp selects the members redundantly: lane l takes the (l+1)-th alive position
         const uint32_t w0 = s_win[0], w1 = s_win[1], w2 = s_win[2], w3 = s_win[3];
         const int c0n = __popc(w0), c1n = __popc(w1), c2n = __popc(w2), c3n = __popc(w3);
@@ -269,14 +343,16 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
           if (r >= c0n) { r -= c0n; d = 1; wsel = w1;
             if (r >= c1n) { r -= c1n; d = 2; wsel = w2;
               if (r >= c2n) { r -= c2n; d = 3; wsel = w3; } } }
-          mypos = ((wb + d) << 5) + (int)__fns(wsel, 0, r + 1);
+          mypos = ((wb + d) << 5) + nms_nth_set_bit(wsel, r);
         }
         const int lastpos = __shfl_sync(0xffffffffu, mypos, nmem - 1);
         const int f_new = (total <= 32) ? ((wb + 4) << 5) : (lastpos + 1);
         // (0c) member boxes -> shared memory
+        int my_out = 0;   // warp 0: this member's row in the reference's output order (for step (b): no dependent load there)
         if (warp == 0) {
           const bool valid = lane < nmem;
           const int qi = s0 + (valid ? mypos : 0);
+          my_out = val2[qi];
           s_cbox[lane] = valid ? cbox[qi] : make_float4(0.f, 0.f, 0.f, 0.f);
           s_carea[lane] = valid ? area[qi] : 0.f;
           const int st = valid ? suppressed[qi] : 0;
@@ -285,6 +361,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
           s_cpos[lane] = valid ? qi : -1;
         }
         __syncthreads();
+        NMS_T(1);
         // (a) pair matrix (rows warp and warp+16) and spatial bin masks (bins warp and warp+16)
         {
           const float4 bj = s_cbox[lane];
@@ -305,6 +382,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
           }
         }
         __syncthreads();
+        NMS_T(2);
         // (b) warp 0 resolves the chunk serially; rows are read up front so the dependent chain is pure ALU
         if (warp == 0) {
           uint32_t alive = nmem == 32 ? 0xffffffffu : ((1u << nmem) - 1u);
@@ -315,9 +393,21 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
             if ((alive >> i) & 1u) { kept |= 1u << i; alive &= ~ri; }
           }
           if (lane == 0) s_kept = kept;
-          if ((kept >> lane) & 1u) keep[val2[s_cpos[lane]]] = 1;  // keep[] is zero-initialised
+          if ((kept >> lane) & 1u) keep[my_out] = 1;  // keep[] is zero-initialised
+        } else {
+          // meanwhile the other warps build the span tables from the bin masks of step (a)
+          for (int e = tid - 32; e < 256; e += NMS_THREADS - 32) {
+            const int bsel = e & 31, span = (e >> 5) & 3;
+            const uint32_t* src = (e >> 7) ? s_biny : s_binx;
+            uint32_t o = src[bsel];
+            if (span >= 1 && bsel + 1 < 32) o |= src[bsel + 1];
+            if (span >= 2 && bsel + 2 < 32) o |= src[bsel + 2];
+            if (span >= 3 && bsel + 3 < 32) o |= src[bsel + 3];
+            s_tab[e] = o;
+          }
         }
         __syncthreads();
+        NMS_T(3);
         // (c) the chunk's survivors knock out the later boxes this thread owns: only live slots are visited
         const uint32_t kept = s_kept;
         const uint32_t kgen = kept & s_cgen;
@@ -327,27 +417,69 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
           constexpr uint64_t ALL = (NMS_QPT == 64) ? ~0ull : ((1ull << NMS_QPT) - 1ull);
           uint64_t later = (jf >= NMS_QPT) ? 0ull : (ALL << jf) & ALL;
           if (jf < NMS_QPT && tid < rf) later &= ~(1ull << jf);
+          // survivors of this chunk that could overlap owned box j (superset): general boxes meet every survivor
+          auto cand_of = [&](int j) -> uint32_t {
+            if ((gen >> j) & 1ull) return kept;
+            const uint32_t bins = s_bins[j * NMS_THREADS + tid];
+            const int xl = bins & 31, sx = int((bins >> 8) & 31) - xl, yl = (bins >> 16) & 31, sy = int((bins >> 24) & 31) - yl;
+            const uint32_t mx = sx > 3 ? 0xffffffffu : s_tab[(sx << 5) + xl];
+            const uint32_t my = sy > 3 ? 0xffffffffu : s_tab[128 + (sy << 5) + yl];
+            return (mx & my & kept) | kgen;
+          };
+          // pass 1: which live slots have a candidate at all (shared memory only)
+          uint64_t hit = 0;
           for (uint64_t act = later & ~supp; act; act &= act - 1) {
             const int j = __ffsll((long long)act) - 1;
-            const bool qgen = (gen >> j) & 1ull;
-            uint32_t cand = qgen ? kept : ((nms_candidates(s_bins[j * NMS_THREADS + tid], s_binx, s_biny) & kept) | kgen);
-            if (cand) {
-              const int q = s0 + j * NMS_THREADS + tid;
-              const float4 b = cbox[q];
-              const float al = area[q];
-              while (cand) {
-                const int t = __ffs(cand) - 1;
-                cand &= cand - 1;
-                if (nms_pair(s_cbox[t], s_carea[t], b, al, qgen || ((kgen >> t) & 1u), thr, thr_pos)) {
-                  supp |= 1ull << j;
-                  break;
+            if (cand_of(j)) hit |= 1ull << j;
+          }
+          // pass 2: the few that do fetch their coordinates -- four loads in flight instead of one L2 round trip per slot
+          while (hit) {
+            int js[4];
+            float4 bb[4];
+            float aa[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              js[u] = -1;
+              if (hit) { js[u] = __ffsll((long long)hit) - 1; hit &= hit - 1; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (js[u] >= 0) {
+                const int q = s0 + js[u] * NMS_THREADS + tid;
+                bb[u] = cbox[q];
+                aa[u] = area[q];
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (js[u] >= 0) {
+                const bool qgen = (gen >> js[u]) & 1ull;
+                uint32_t cand = cand_of(js[u]);
+                while (cand) {
+                  const int t = __ffs(cand) - 1;
+                  cand &= cand - 1;
+                  if (nms_pair(s_cbox[t], s_carea[t], bb[u], aa[u], qgen || ((kgen >> t) & 1u), thr, thr_pos)) {
+                    supp |= 1ull << js[u];
+                    break;
+                  }
                 }
               }
             }
           }
         }
         f = f_new;
+#ifdef YB_NMS_PROFILE
+        NMS_T(4);
+        ++rounds;
+#endif
       }
+#ifdef YB_NMS_PROFILE
+      if (prof) {
+        for (int i = 0; i < 5; ++i) atomicAdd(&g_nms_prof[i], (unsigned long long)pt[i]);
+        atomicAdd(&g_nms_prof[5], rounds);
+        atomicAdd(&g_nms_prof[6], 1ull);
+      }
+#endif
       __syncthreads();
       continue;
     }
@@ -494,6 +626,7 @@ struct NmsWs {
   uint8_t* suppressed;
   uint8_t* keep;
   int32_t* seg_starts;
+  int32_t* big_list;
   SortBuffers sb;
   int ctiles;
 };
@@ -513,6 +646,7 @@ void nms_carve(WsCarver& ws, int total, NmsWs* w) {
   w->suppressed = ws.take<uint8_t>(t);
   w->keep = ws.take<uint8_t>(t);
   w->seg_starts = ws.take<int32_t>(t);
+  w->big_list = ws.take<int32_t>(t);
   sort_carve(ws, t, &w->sb);
 }
 
@@ -580,7 +714,8 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
                                            w.cbox, w.area, w.suppressed, w.seg_starts, nseg);
   YB_CHECK_LAUNCH();
 
-  // K6: greedy NMS per (image, class) segment
+  // K6: greedy NMS per (image, class) segment: a warp each for segments of <= 32 boxes, a CTA each for the others
+  int32_t* nbig = w.scalars + 3;
   int dev = 0, sms = 148;
   YB_CHECK_CUDA(cudaGetDevice(&dev));
   YB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -588,6 +723,13 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   // segment is total / (batch * classes) boxes long at most -- short segments want many small CTAs
   // Measured on random-init YOLOv3 heads (class-skewed segments, profiles/r1_nms_cta_size.txt): 128 / 256 / 512 threads
   // give 0.99 / 0.71 / 0.61 ms at 416 (conf 0.5) and 4.6 / 3.1 / 1.9 ms at 608 (conf 0.01), 1024 threads 0.94 / 2.8 ms.
+  {
+    int sgrid = yb_cdiv(total, 8);   // one warp per segment, 8 warps per block; at most `total` segments
+    if (sgrid > sms * 8) sgrid = sms * 8;
+    k_nms_small<<<sgrid, 256, 0, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts, nseg, n_valid, iou_thr, w.suppressed,
+                                          w.keep, class_bits > 0, w.big_list, nbig);
+    YB_CHECK_LAUNCH();
+  }
   const int nt = 512;
   const size_t nms_smem = size_t(NMS_QPT) * nt * sizeof(uint32_t);
   int grid = sms * (nt == 1024 ? 1 : (nt == 512 ? 3 : (nt == 256 ? 6 : 12)));
@@ -595,8 +737,8 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
 #define YB_NMS_LAUNCH(NTV)                                                                                              \
   do {                                                                                                                  \
     YB_CHECK_CUDA(cudaFuncSetAttribute(k_nms_segments<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem)); \
-    k_nms_segments<NTV><<<grid, NTV, nms_smem, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts, nseg, n_valid,    \
-                                                       iou_thr, w.suppressed, w.keep, class_bits > 0);                  \
+    k_nms_segments<NTV><<<grid, NTV, nms_smem, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts, nbig, n_valid,    \
+                                                       iou_thr, w.suppressed, w.keep, class_bits > 0, w.big_list);      \
   } while (0)
   if (nt == 128) YB_NMS_LAUNCH(128); else if (nt == 256) YB_NMS_LAUNCH(256); else if (nt == 1024) YB_NMS_LAUNCH(1024);
   else YB_NMS_LAUNCH(512);
@@ -616,6 +758,14 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   YB_CHECK_LAUNCH();
   return YB_OK;
 }
+
+#ifdef YB_NMS_PROFILE
+extern "C" int yolo_debug_nms_prof(unsigned long long* out8, int reset) {
+  if (out8) cudaMemcpyFromSymbol(out8, g_nms_prof, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_nms_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 // ---- element-wise IoU: utils.py:38-84 calc_iou / utils.py:22-36 iou_aligned --
 namespace {
