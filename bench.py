@@ -104,9 +104,11 @@ def workload_config(args, world: int) -> dict:
 
 
 def nms_launch_count(batch: int) -> int:
+    """Launches of one yolo_nms call with integer class labels (class_bits = 8), as csrc/nms.cu issues them."""
     img_passes = 0 if batch <= 1 else ((max(batch - 1, 1).bit_length() + 7) // 8)
-    sort = (4 + img_passes) * 3
-    return 3 + sort + 1 + sort + 1 + 2 + 4  # K4 | sort#1 | class keys | sort#2 | gather | nms (warp + CTA kernels) | keep+offsets
+    sort1 = (4 + img_passes) * 3     # 32 score bits + image bits, 8 bits per pass, hist + scan + scatter each
+    sort2 = (1 + img_passes) * 3     # (image, class) grouping key
+    return 1 + 3 + sort1 + 1 + sort2 + 1 + 2 + 4  # memset | K4 | sort#1 | class keys | sort#2 | gather | nms x2 | keep+offsets
 
 
 # ------------------------------------------------------------------------------------------ CPU

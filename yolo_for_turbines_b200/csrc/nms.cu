@@ -92,7 +92,9 @@ __global__ void k_class_keys(const float* __restrict__ boxes, const uint64_t* __
     if (cls >= 0.f && cls < lim && cls == floorf(cls)) cb = uint32_t(cls);
     else { cb = 0; atomicAdd(violations, 1); }
   }
-  key2[p] = (key1[p] & 0xffffffff00000000ull) | cb;
+  // integer labels: (image << class_bits) | class, so the grouping sort covers one contiguous bit range; float labels
+  // keep the image in the upper word (k_nms_segments recognises the NaN class by the lower one)
+  key2[p] = class_bits > 0 ? (((key1[p] >> 32) << class_bits) | cb) : ((key1[p] & 0xffffffff00000000ull) | cb);
   val2[p] = p;
 }
 
@@ -636,6 +638,7 @@ void nms_carve(WsCarver& ws, int total, NmsWs* w) {
   w->ctiles = yb_cdiv(t, COMPACT_TILE);
   w->tile_cnt = ws.take<int32_t>(w->ctiles + 1);
   w->scalars = ws.take<int32_t>(8);
+  w->keep = ws.take<uint8_t>(t);     // directly behind the scalars: one memset clears both
   w->key1 = ws.take<uint64_t>(t);
   w->val1 = ws.take<int32_t>(t);
   w->key2 = ws.take<uint64_t>(t);
@@ -644,7 +647,6 @@ void nms_carve(WsCarver& ws, int total, NmsWs* w) {
   w->cbox = ws.take<float4>(t);
   w->area = ws.take<float>(t);
   w->suppressed = ws.take<uint8_t>(t);
-  w->keep = ws.take<uint8_t>(t);
   w->seg_starts = ws.take<int32_t>(t);
   w->big_list = ws.take<int32_t>(t);
   sort_carve(ws, t, &w->sb);
@@ -674,16 +676,18 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
                  yolo_nms_workspace_bytes(total, batch));
     return YB_ERR_WORKSPACE;
   }
-  YB_CHECK_CUDA(cudaMemsetAsync(keep_off, 0, sizeof(int32_t) * (batch + 1), stream));
-  if (total == 0) return YB_OK;
+  if (total == 0) {   // otherwise k_keep_offsets writes every entry
+    YB_CHECK_CUDA(cudaMemsetAsync(keep_off, 0, sizeof(int32_t) * (batch + 1), stream));
+    return YB_OK;
+  }
   YB_REQUIRE(boxes && img_offsets && keep_idx && workspace, "yolo_nms: null pointer");
   WsCarver ws(workspace);
   NmsWs w;
   nms_carve(ws, total, &w);
   int32_t* n_valid = w.scalars;
   int32_t* nseg = w.scalars + 1;
-  YB_CHECK_CUDA(cudaMemsetAsync(w.scalars, 0, sizeof(int32_t) * 8, stream));
-  YB_CHECK_CUDA(cudaMemsetAsync(w.keep, 0, size_t(total), stream));  // k_nms_segments only writes the 1s
+  // counters + keep flags (the NMS kernels only write the 1s) in one memset: keep sits right behind the scalars
+  YB_CHECK_CUDA(cudaMemsetAsync(w.scalars, 0, size_t(reinterpret_cast<uint8_t*>(w.keep) - reinterpret_cast<uint8_t*>(w.scalars)) + size_t(total), stream));
 
   // K4: ordered threshold compaction -> (key, row index) pairs
   k_thr_count<<<w.ctiles, COMPACT_THREADS, 0, stream>>>(boxes, total, obj_thr, w.tile_cnt);
@@ -698,19 +702,20 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   int img_bits = 0;
   while ((1 << img_bits) < batch) ++img_bits;
   const int img_hi = 32 + ((img_bits + 7) / 8) * 8;
-  rc = radix_sort_pairs(w.key1, w.val1, n_valid, total, 0, 32, w.sb, stream);
-  if (rc) return rc;
-  rc = radix_sort_pairs(w.key1, w.val1, n_valid, total, 32, img_hi, w.sb, stream);
+  // one call per sort; the results are followed to whichever buffer the last pass wrote (no copy-back launches).  Sort
+  // #2 ping-pongs between its own buffers and the buffer pair sort #1 did NOT end in (key1's order is needed again below).
+  uint64_t* k1 = nullptr; int32_t* v1 = nullptr;
+  rc = radix_sort_pairs(w.key1, w.val1, n_valid, total, 0, img_hi, w.sb, stream, &k1, &v1);
   if (rc) return rc;
   const int eb = 256, eg = yb_cdiv(total, eb);
-  k_class_keys<<<eg, eb, 0, stream>>>(boxes, w.key1, w.val1, n_valid, w.key2, w.val2, w.idx1, class_bits,
-                                      w.scalars + 2);
+  k_class_keys<<<eg, eb, 0, stream>>>(boxes, k1, v1, n_valid, w.key2, w.val2, w.idx1, class_bits, w.scalars + 2);
   YB_CHECK_LAUNCH();
-  rc = radix_sort_pairs(w.key2, w.val2, n_valid, total, 0, class_bits > 0 ? class_bits : 32, w.sb, stream);
+  SortBuffers sb2 = w.sb;
+  if (k1 != w.key1) { sb2.keys_alt = w.key1; sb2.vals_alt = w.val1; }
+  uint64_t* k2 = nullptr; int32_t* v2 = nullptr;
+  rc = radix_sort_pairs(w.key2, w.val2, n_valid, total, 0, class_bits > 0 ? class_bits + (img_hi - 32) : img_hi, sb2, stream, &k2, &v2);
   if (rc) return rc;
-  rc = radix_sort_pairs(w.key2, w.val2, n_valid, total, 32, img_hi, w.sb, stream);
-  if (rc) return rc;
-  k_gather_segments<<<eg, eb, 0, stream>>>(boxes, w.key2, w.val2, w.idx1, n_valid, box_format,
+  k_gather_segments<<<eg, eb, 0, stream>>>(boxes, k2, v2, w.idx1, n_valid, box_format,
                                            w.cbox, w.area, w.suppressed, w.seg_starts, nseg);
   YB_CHECK_LAUNCH();
 
@@ -726,7 +731,7 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   {
     int sgrid = yb_cdiv(total, 8);   // one warp per segment, 8 warps per block; at most `total` segments
     if (sgrid > sms * 8) sgrid = sms * 8;
-    k_nms_small<<<sgrid, 256, 0, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts, nseg, n_valid, iou_thr, w.suppressed,
+    k_nms_small<<<sgrid, 256, 0, stream>>>(w.cbox, w.area, k2, v2, w.seg_starts, nseg, n_valid, iou_thr, w.suppressed,
                                           w.keep, class_bits > 0, w.big_list, nbig);
     YB_CHECK_LAUNCH();
   }
@@ -737,7 +742,7 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
 #define YB_NMS_LAUNCH(NTV)                                                                                              \
   do {                                                                                                                  \
     YB_CHECK_CUDA(cudaFuncSetAttribute(k_nms_segments<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem)); \
-    k_nms_segments<NTV><<<grid, NTV, nms_smem, stream>>>(w.cbox, w.area, w.key2, w.val2, w.seg_starts, nbig, n_valid,    \
+    k_nms_segments<NTV><<<grid, NTV, nms_smem, stream>>>(w.cbox, w.area, k2, v2, w.seg_starts, nbig, n_valid,              \
                                                        iou_thr, w.suppressed, w.keep, class_bits > 0, w.big_list);      \
   } while (0)
   if (nt == 128) YB_NMS_LAUNCH(128); else if (nt == 256) YB_NMS_LAUNCH(256); else if (nt == 1024) YB_NMS_LAUNCH(1024);
@@ -750,10 +755,10 @@ extern "C" int yolo_nms(const float* boxes, const int32_t* img_offsets, int batc
   YB_CHECK_LAUNCH();
   rc = exclusive_scan_small(w.tile_cnt, w.ctiles + 1, nullptr, stream);
   if (rc) return rc;
-  k_keep_write<<<w.ctiles, COMPACT_THREADS, 0, stream>>>(w.keep, w.key1, w.idx1, n_valid,
+  k_keep_write<<<w.ctiles, COMPACT_THREADS, 0, stream>>>(w.keep, k1, w.idx1, n_valid,
                                                          w.tile_cnt, keep_idx);
   YB_CHECK_LAUNCH();
-  k_keep_offsets<<<yb_cdiv((batch + 1) * 32, 128), 128, 0, stream>>>(w.keep, w.key1, n_valid, w.tile_cnt, batch,
+  k_keep_offsets<<<yb_cdiv((batch + 1) * 32, 128), 128, 0, stream>>>(w.keep, k1, n_valid, w.tile_cnt, batch,
                                                                      keep_off);
   YB_CHECK_LAUNCH();
   return YB_OK;

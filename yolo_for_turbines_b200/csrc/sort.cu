@@ -115,7 +115,9 @@ int exclusive_scan_small(int32_t* data, int n, int32_t* total_out, cudaStream_t 
 }
 
 int radix_sort_pairs(uint64_t* keys, int32_t* vals, const int32_t* n_dev, int max_n, int bit_lo,
-                     int bit_hi, const SortBuffers& sb, cudaStream_t stream) {
+                     int bit_hi, const SortBuffers& sb, cudaStream_t stream, uint64_t** keys_res, int32_t** vals_res) {
+  if (keys_res) *keys_res = keys;
+  if (vals_res) *vals_res = vals;
   if (max_n <= 0 || bit_hi <= bit_lo) return YB_OK;
   YB_REQUIRE(bit_lo % 8 == 0 && bit_hi % 8 == 0 && bit_hi <= 64, "radix_sort_pairs: bad bit range");
   uint64_t* kin = keys;
@@ -134,7 +136,10 @@ int radix_sort_pairs(uint64_t* keys, int32_t* vals, const int32_t* n_dev, int ma
     uint64_t* tk = kin; kin = kout; kout = tk;
     int32_t* tv = vin; vin = vout; vout = tv;
   }
-  if (kin != keys) {
+  if (keys_res && vals_res) {   // the caller follows the result to whichever buffer the last pass wrote: no copy-back
+    *keys_res = kin;
+    *vals_res = vin;
+  } else if (kin != keys) {
     YB_CHECK_CUDA(cudaMemcpyAsync(keys, kin, size_t(max_n) * sizeof(uint64_t),
                                   cudaMemcpyDeviceToDevice, stream));
     YB_CHECK_CUDA(cudaMemcpyAsync(vals, vin, size_t(max_n) * sizeof(int32_t),

@@ -24,10 +24,12 @@ inline void sort_carve(WsCarver& ws, int max_n, SortBuffers* sb) {
   sb->digit_total = ws.take<int32_t>(256);
 }
 
-// Sorts ascending on key bits [bit_lo, bit_hi) (multiples of 8).  Result is in
-// keys/vals on return (a final copy pass is appended for odd pass counts).
+// Sorts ascending on key bits [bit_lo, bit_hi) (multiples of 8).  With keys_res / vals_res null the result is in
+// keys/vals on return (a copy pass is appended for odd pass counts); otherwise they receive the buffers that hold
+// it (keys/vals or sb.keys_alt/vals_alt) and nothing is copied.
 int radix_sort_pairs(uint64_t* keys, int32_t* vals, const int32_t* n_dev, int max_n, int bit_lo,
-                     int bit_hi, const SortBuffers& sb, cudaStream_t stream);
+                     int bit_hi, const SortBuffers& sb, cudaStream_t stream, uint64_t** keys_res = nullptr,
+                     int32_t** vals_res = nullptr);
 
 // Order-preserving compaction support: per-tile counts -> exclusive offsets.
 constexpr int COMPACT_THREADS = 256;
