@@ -43,11 +43,14 @@ def timed(fn, n=steps):
 
 
 t_step = timed(lambda: tr.step(x, tg))
+for _ in range(2):
+    tr.step(x, tg, graph=True)
+t_graph = timed(lambda: tr.step(x, tg, graph=True))
 t_fwd = timed(lambda: plan.forward(x))
 t_loss = timed(lambda: tr._loss_and_head_grads(plan, tg))
 t_bwd = timed(lambda: plan.backward())
 t_rep = timed(lambda: tr.repack())
 gf = {416: 65.297, 320: 38.637}.get(S, 65.297 * (S / 416.0) ** 2) * B * 3
-print(f"B={B} S={S} {act}: step {t_step:.2f} ms -> {B / t_step * 1e3:.1f} img/s, {gf / t_step:.1f} TFLOP/s (3x fwd FLOPs)")
+print(f"B={B} S={S} {act}: step {t_step:.2f} ms -> {B / t_step * 1e3:.1f} img/s, {gf / t_step:.1f} TFLOP/s (3x fwd FLOPs); graph replay {t_graph:.2f} ms")
 print(f"  forward {t_fwd:.2f} ms | loss fwd+bwd {t_loss:.3f} ms | backward {t_bwd:.2f} ms | repack {t_rep:.2f} ms")
 print(f"  losses {tr.losses.tolist()}")

@@ -443,3 +443,43 @@ def test_trainer_state_dict_round_trip():
         ua = (want[k] - before[k]).flatten()
         cos = float(torch.nn.functional.cosine_similarity(ua, ub, dim=0))
         assert cos > 0.98 and 0.8 < float(ub.norm() / ua.norm()) < 1.25, (k, cos)
+
+
+@pytest.mark.gpu
+def test_graphed_step_follows_the_eager_trajectory():
+    """Trainer.step(graph=True): the step captured once (three streams) and replayed follows the eager trajectory up to
+    the run-to-run noise of the atomically accumulated sums (two EAGER runs differ by the same amount:
+    scripts/graph_step_debug.py); static input buffers pick up new batches; an eager step after graphed ones sees
+    current weight packs (the "mixed" run)."""
+    import copy
+
+    from oracle import yolo_oracle as orc
+    from yolo_for_turbines_b200.model import YOLOv3
+    from yolo_for_turbines_b200.train import Trainer
+
+    torch.manual_seed(3)
+    base = YOLOv3(num_classes=2, activation="mish")
+    B, S = 4, 96
+    xs = [torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(10 + i)).cuda() for i in range(3)]
+    tgs = [[t.cuda() for t in orc.synth_targets(B, S, 2, 20 + i)] for i in range(3)]
+    runs = {}
+    for mode in ("eager", "graph", "mixed"):
+        m = copy.deepcopy(base).cuda().train()
+        tr = Trainer(m, orc.TURBINE_ANCHORS, lr=1e-5, momentum=0.9, weight_decay=5e-4)
+        p0 = tr.flat_p[: tr.n_trainable].clone()
+        losses = []
+        for i in range(6):
+            g = mode == "graph" or (mode == "mixed" and i in (2, 3))
+            losses.append(tr.step(xs[i % 3], tgs[i % 3], graph=g).clone())
+        torch.cuda.synchronize()
+        runs[mode] = (torch.stack(losses).cpu(), (tr.flat_p[: tr.n_trainable] - p0).cpu(), len(tr._graphs))
+    assert runs["eager"][2] == 0 and runs["graph"][2] == 1 and runs["mixed"][2] == 1
+    le, de = runs["eager"][0], runs["eager"][1]
+    assert float(de.abs().max()) > 1e-5     # the steps did move the parameters
+    for mode in ("graph", "mixed"):
+        lg, dg = runs[mode][0], runs[mode][1]
+        assert torch.isfinite(lg).all()
+        assert torch.allclose(lg, le, rtol=0.1, atol=0.03), (mode, lg, le)
+        cos = torch.nn.functional.cosine_similarity(dg.flatten(), de.flatten(), dim=0)
+        assert cos > 0.95, (mode, float(cos))            # same accumulated update
+        assert float((dg - de).abs().max()) < 5e-4, mode

@@ -546,6 +546,7 @@ class Trainer:
         self.ev_pack = {id(b): torch.cuda.Event() for b in self.blocks}
         self._ev_sgd = torch.cuda.Event()
         self._packs_pending = False
+        self._graphs: Dict[tuple, dict] = {}
         self.repack(full=True)
         self._packed_sig = self._param_sig()
 
@@ -629,7 +630,10 @@ class Trainer:
         p = self.plans.get(key)
         if p is None:
             while len(self.plans) >= self.max_plans:   # multi-scale training (config.py:43-45): bound the arenas kept
-                self.plans.pop(next(iter(self.plans)))
+                old = next(iter(self.plans))
+                self.plans.pop(old)
+                for gk in [k for k in self._graphs if (k[0][0], k[0][2], k[0][3]) == old]:
+                    self._graphs.pop(gk)   # a captured step points into the evicted plan's buffers
             with torch.cuda.device(self.device):
                 p = TrainPlan(self, B, H, W)
                 for op in p.ops:
@@ -688,9 +692,10 @@ class Trainer:
             plan._bk = make_buckets(firsts, self.n_trainable, self.bucket_elems)
         return plan._bk
 
-    def step(self, x: torch.Tensor, targets: Sequence[torch.Tensor], lr: Optional[float] = None) -> torch.Tensor:
+    def step(self, x: torch.Tensor, targets: Sequence[torch.Tensor], lr: Optional[float] = None, graph: bool = False) -> torch.Tensor:
         """One optimisation step (train.py:42-69).  Returns the device tensor [box, object, no_object, class] of
-        the loss terms summed over the three scales (their sum is the reference's `loss`); no host sync."""
+        the loss terms summed over the three scales (their sum is the reference's `loss`); no host sync.
+        graph=True replays the step as one CUDA graph (see _step_graphed)."""
         require_cuda(x, "Trainer.step input")
         if not self.own_params:
             raise YoloB200Error("Trainer.step needs own_params=True (the autograd wrapper leaves the update to the caller)")
@@ -698,45 +703,103 @@ class Trainer:
             raise YoloB200Error(f"expected (B,{self.model.in_channels},H,W) input, got {tuple(x.shape)}")
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
+        if graph:
+            return self._step_graphed(x, targets, float(self.lr if lr is None else lr))
         dev = self.device
-        plan = self.plan(x.shape[0], x.shape[2], x.shape[3])
         with torch.cuda.device(dev):
-            st = stream_ptr(dev)
             self._repack_if_written_externally()
-            self.dw_packed.zero_()
-            plan.forward(x)
-            plan.generation = getattr(plan, "generation", 0) + 1
-            self.losses = self._loss_and_head_grads(plan, targets)
-            if self.world > 1:
-                main = torch.cuda.current_stream(dev)
-                pending = list(self._buckets(plan))
-
-                def on_op_done(i):
-                    while pending and pending[0][0] >= i:
-                        _, lo, hi = pending.pop(0)
-                        ev = torch.cuda.Event()
-                        ev.record(main)
-                        self.comm_stream.wait_event(ev)
-                        if self.wgrad_stream is not None:   # the bucket's weight gradients are written on the side stream
-                            ev2 = torch.cuda.Event()
-                            ev2.record(self.wgrad_stream)
-                            self.comm_stream.wait_event(ev2)
-                        with torch.cuda.stream(self.comm_stream):
-                            if self.debug_local_grads is not None:   # tests: this rank's gradient before the exchange
-                                self.debug_local_grads[lo:hi].copy_(self.flat_g[lo:hi])
-                            torch.distributed.all_reduce(self.flat_g[lo:hi], group=self.pg)
-                plan.backward(on_op_done)
-                main.wait_stream(self.comm_stream)
-            else:
-                plan.backward()
-            lib.yolo_sgd_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), self.n_trainable,
-                              float(self.lr if lr is None else lr), self.momentum, self.weight_decay, 1.0 / self.world,
-                              int(self.steps_done == 0), st)
-            self.repack_async()
+            self._step_body(x, targets, float(self.lr if lr is None else lr), repack_first=False)
         self.steps_done += 1
         eng = self.model.__dict__.get("_yb_engine")
         if eng is not None:
             eng._sig = None  # the inference engine's packed weights are stale now
+        return self.losses
+
+    def _step_body(self, x, targets, lr: float, repack_first: bool):
+        """The launches of one step on the current stream (+ the side / communication streams forked from and joined
+        back into it).  repack_first=False (eager): forward .. SGD, then the operand repack on the side stream, which the
+        NEXT call's forward waits for layer by layer.  repack_first=True (the CUDA-graph order): the same repack opens the
+        step instead -- it packs the parameters the previous replay's SGD wrote -- so every stream has rejoined the
+        origin when the step ends, as stream capture requires; the overlap with the first forward layers is the same."""
+        dev = self.device
+        plan = self.plan(x.shape[0], x.shape[2], x.shape[3])
+        st = stream_ptr(dev)
+        main = torch.cuda.current_stream(dev)
+        if repack_first:
+            self.repack_async()
+        self.dw_packed.zero_()
+        plan.forward(x)
+        plan.generation = getattr(plan, "generation", 0) + 1
+        self.losses = self._loss_and_head_grads(plan, targets)
+        if self.world > 1:
+            pending = list(self._buckets(plan))
+
+            def on_op_done(i):
+                while pending and pending[0][0] >= i:
+                    _, lo, hi = pending.pop(0)
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    self.comm_stream.wait_event(ev)
+                    if self.wgrad_stream is not None:   # the bucket's weight gradients are written on the side stream
+                        ev2 = torch.cuda.Event()
+                        ev2.record(self.wgrad_stream)
+                        self.comm_stream.wait_event(ev2)
+                    with torch.cuda.stream(self.comm_stream):
+                        if self.debug_local_grads is not None:   # tests: this rank's gradient before the exchange
+                            self.debug_local_grads[lo:hi].copy_(self.flat_g[lo:hi])
+                        torch.distributed.all_reduce(self.flat_g[lo:hi], group=self.pg)
+            plan.backward(on_op_done)
+            main.wait_stream(self.comm_stream)
+        else:
+            plan.backward()
+        lib.yolo_sgd_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), self.n_trainable,
+                          lr, self.momentum, self.weight_decay, 1.0 / self.world, int(self.steps_done == 0), st)
+        if repack_first:
+            if self.wgrad_stream is not None:
+                main.wait_stream(self.wgrad_stream)
+        else:
+            self.repack_async()
+        plan._ran = True
+
+    def _step_graphed(self, x, targets, lr: float):
+        """`step(..., graph=True)`: the ~700 launches of a step (three streams, the NCCL all-reduce included) captured
+        once per (input shape, lr, world size) and replayed -- no host work per launch, which matters when several
+        ranks share few host cores (8 ranks on 16 cores: the eager step loses ~1 ms to launch contention).  The first
+        step of a Trainer runs eagerly (it seeds the momentum buffer), inputs are copied into static buffers, and the
+        returned loss tensor is the graph's own output buffer (rewritten by every replay)."""
+        dev = self.device
+        plan = self.plans.get((x.shape[0], x.shape[2], x.shape[3]))
+        if self.steps_done == 0 or plan is None or not getattr(plan, "_ran", False):
+            return self.step(x, targets, lr=lr, graph=False)   # a shape's first step builds its plan and runs eagerly
+        key = (tuple(x.shape), tuple(tuple(t.shape) for t in targets), lr, self.world)
+        st = self._graphs.get(key)
+        with torch.cuda.device(dev):
+            if st is None:
+                while len(self._graphs) >= self.max_plans:
+                    self._graphs.pop(next(iter(self._graphs)))
+                gx = torch.empty_like(x)
+                gts = [torch.empty_like(t) for t in targets]
+                if self._packs_pending and self.wgrad_stream is not None:
+                    torch.cuda.current_stream(dev).wait_stream(self.wgrad_stream)
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                # thread_local: NCCL's watchdog thread queries events while this thread captures
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._step_body(gx, gts, lr, repack_first=True)
+                    losses = self.losses
+                st = dict(g=g, gx=gx, gts=gts, losses=losses)
+                self._graphs[key] = st
+            st["gx"].copy_(x, non_blocking=True)
+            for d, t in zip(st["gts"], targets):
+                d.copy_(t, non_blocking=True)
+            st["g"].replay()
+        self.losses = st["losses"]
+        self._packs_pending = False
+        self._packed_sig = None   # an eager step after this one repacks first (the graph packs at its own start)
+        self.steps_done += 1
+        eng = self.model.__dict__.get("_yb_engine")
+        if eng is not None:
+            eng._sig = None
         return self.losses
 
     # ---- optimizer state (utils.py:383-416 save_checkpoint / load_checkpoint store {state_dict, optimizer}) --------
