@@ -424,7 +424,15 @@ def stage_train_step(args, dev, dist, rank, world):
         tr.world = saved
         out["ms_per_step_without_allreduce"] = ms_without
         out["exposed_comm_ms"] = max(0.0, ms_with - ms_without)
+    # captured steps hold NCCL kernels: release them (and wait for the device) before the stage returns, so that no graph
+    # outlives the process group's teardown at the end of the run
+    tr._graphs.clear()
+    tr.plans.clear()
     del tr, model
+    import gc
+
+    gc.collect()
+    torch.cuda.synchronize(dev)
     torch.cuda.empty_cache()
     return out
 
@@ -880,7 +888,16 @@ def main():
                                               f"({dtc:.1f} s; torch threads {torch.get_num_threads()}, os.cpu_count {os.cpu_count()})"}
         print(json.dumps(line), flush=True)
     if dist is not None:
+        # the JSON line is out; a communicator teardown that does not come back must not keep the launcher waiting
+        guard = threading.Timer(30.0, lambda: os._exit(0))
+        guard.daemon = True
+        guard.start()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)   # no interpreter-exit destructors behind a destroyed communicator
 
 
 if __name__ == "__main__":
