@@ -179,6 +179,14 @@ __device__ __forceinline__ uint32_t nms_pack_bins(const float4 b) {
   return uint32_t(nms_bin(b.x)) | (uint32_t(nms_bin(b.z)) << 8) | (uint32_t(nms_bin(b.y)) << 16) |
          (uint32_t(nms_bin(b.w)) << 24);
 }
+// packed bins -> the two span-table indices of the register path (x in the low half word, y in the high one):
+// (span << 5) + first bin, y offset by 128; 256 (all ones) when the box spans more than four bins on that axis
+__device__ __forceinline__ uint32_t nms_tab_index(uint32_t bins) {
+  const int xl = bins & 31, sx = int((bins >> 8) & 31) - xl, yl = (bins >> 16) & 31, sy = int((bins >> 24) & 31) - yl;
+  const uint32_t ix = sx > 3 ? 256u : uint32_t((sx << 5) + xl);
+  const uint32_t iy = sy > 3 ? 256u : uint32_t(128 + (sy << 5) + yl);
+  return ix | (iy << 16);
+}
 // survivors of the current chunk that could overlap a box with these bins (superset)
 __device__ __forceinline__ uint32_t nms_candidates(uint32_t bins, const uint32_t* s_binx, const uint32_t* s_biny) {
   const int xl = bins & 31, xh = (bins >> 8) & 31, yl = (bins >> 16) & 31, yh = (bins >> 24) & 31;
@@ -260,9 +268,9 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
   __shared__ uint32_t s_row[32], s_binx[32], s_biny[32];
   // s_tab[axis][span][b] = OR of the bin masks b .. b + span: the survivors a box with bin range [b, b + span] can meet on
   // that axis, in ONE shared-memory read (the per-bin loop of nms_candidates made step (c) a chain of dependent reads)
-  __shared__ uint32_t s_tab[256];
+  __shared__ uint32_t s_tab[257];   // [256] = all ones: the entry of a box that spans more than four bins on an axis
   __shared__ uint32_t s_alive, s_cgen, s_kept, s_win[4];
-  extern __shared__ uint32_t s_bins[];  // [NMS_QPT][NMS_THREADS] packed spatial bins, 96 KB (dynamic)
+  extern __shared__ uint32_t s_bins[];  // [NMS_QPT][NMS_THREADS] span-table indices of the owned boxes (nms_tab_index), 96 KB (dynamic)
   __shared__ int s_cpos[32];
   __shared__ int s_end;
   constexpr int NMS_THREADS = NT, NMS_WARPS = NT / 32, NMS_REG_CAP = NT * NMS_QPT;
@@ -298,7 +306,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
         const int q = s0 + j * NMS_THREADS + tid;
         if (q < s1) {
           if (suppressed[q] & 2) gen |= 1ull << j;
-          s_bins[j * NMS_THREADS + tid] = nms_pack_bins(cbox[q]);
+          s_bins[j * NMS_THREADS + tid] = nms_tab_index(nms_pack_bins(cbox[q]));
         } else {
           supp |= 1ull << j;
         }
@@ -398,6 +406,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
           if ((kept >> lane) & 1u) keep[my_out] = 1;  // keep[] is zero-initialised
         } else {
           // meanwhile the other warps build the span tables from the bin masks of step (a)
+          if (tid == 32) s_tab[256] = 0xffffffffu;
           for (int e = tid - 32; e < 256; e += NMS_THREADS - 32) {
             const int bsel = e & 31, span = (e >> 5) & 3;
             const uint32_t* src = (e >> 7) ? s_biny : s_binx;
@@ -422,11 +431,8 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
           // survivors of this chunk that could overlap owned box j (superset): general boxes meet every survivor
           auto cand_of = [&](int j) -> uint32_t {
             if ((gen >> j) & 1ull) return kept;
-            const uint32_t bins = s_bins[j * NMS_THREADS + tid];
-            const int xl = bins & 31, sx = int((bins >> 8) & 31) - xl, yl = (bins >> 16) & 31, sy = int((bins >> 24) & 31) - yl;
-            const uint32_t mx = sx > 3 ? 0xffffffffu : s_tab[(sx << 5) + xl];
-            const uint32_t my = sy > 3 ? 0xffffffffu : s_tab[128 + (sy << 5) + yl];
-            return (mx & my & kept) | kgen;
+            const uint32_t w = s_bins[j * NMS_THREADS + tid];   // the box's two table indices (nms_tab_index)
+            return (s_tab[w & 0xffffu] & s_tab[w >> 16] & kept) | kgen;
           };
           // pass 1: which live slots have a candidate at all (shared memory only)
           uint64_t hit = 0;
