@@ -434,11 +434,32 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
             const uint32_t w = s_bins[j * NMS_THREADS + tid];   // the box's two table indices (nms_tab_index)
             return (s_tab[w & 0xffffu] & s_tab[w >> 16] & kept) | kgen;
           };
-          // pass 1: which live slots have a candidate at all (shared memory only)
+          // pass 1: which live slots have a candidate at all (shared memory only).  The slot masks are walked as two
+          // 32-bit words: this loop runs once per (live owned box, round) and 64-bit ffs / shift / clear doubled its
+          // bookkeeping (segments of <= 32 * NT boxes never enter the second word)
           uint64_t hit = 0;
-          for (uint64_t act = later & ~supp; act; act &= act - 1) {
-            const int j = __ffsll((long long)act) - 1;
-            if (cand_of(j)) hit |= 1ull << j;
+          {
+            const uint64_t act = later & ~supp;
+#pragma unroll
+            for (int hw = 0; hw < 2; ++hw) {
+              uint32_t a32 = uint32_t(act >> (32 * hw));
+              const uint32_t g32 = uint32_t(gen >> (32 * hw));
+              uint32_t h32 = 0;
+              const uint32_t* bins = s_bins + (32 * hw) * NMS_THREADS + tid;
+              while (a32) {
+                const int jl = __ffs(a32) - 1;
+                a32 &= a32 - 1;
+                uint32_t cand;
+                if ((g32 >> jl) & 1u) {
+                  cand = kept;
+                } else {
+                  const uint32_t w = bins[jl * NMS_THREADS];
+                  cand = (s_tab[w & 0xffffu] & s_tab[w >> 16] & kept) | kgen;
+                }
+                if (cand) h32 |= 1u << jl;
+              }
+              hit |= uint64_t(h32) << (32 * hw);
+            }
           }
           // pass 2: the few that do fetch their coordinates -- four loads in flight instead of one L2 round trip per slot
           while (hit) {
