@@ -272,7 +272,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
   __shared__ uint32_t s_alive, s_cgen, s_kept, s_win[4];
   extern __shared__ uint32_t s_bins[];  // [NMS_QPT][NMS_THREADS] span-table indices of the owned boxes (nms_tab_index), 96 KB (dynamic)
   __shared__ int s_cpos[32];
-  __shared__ int s_end;
+  __shared__ int s_end, s_fnew;
   constexpr int NMS_THREADS = NT, NMS_WARPS = NT / 32, NMS_REG_CAP = NT * NMS_QPT;
   const bool thr_pos = thr > 0.f;
   const int n = *n_dev, nseg = *nseg_dev;
@@ -336,7 +336,9 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
         }
         __syncthreads();
         NMS_T(0);
-        // (0b) every warp selects the members redundantly: lane l takes the (l+1)-th alive position
+        // (0b) warp 0 selects the members -- lane l takes the (l+1)-th alive position -- and publishes the new frontier;
+        // the other warps only need the member count (the selection cost ~80 instructions in each of the 16 warps, and
+        // the kernel is bound by instruction issue: scripts/nms_round_profile.py)
         const uint32_t w0 = s_win[0], w1 = s_win[1], w2 = s_win[2], w3 = s_win[3];
         const int c0n = __popc(w0), c1n = __popc(w1), c2n = __popc(w2), c3n = __popc(w3);
         const int total = c0n + c1n + c2n + c3n;
@@ -347,16 +349,18 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
         }
         const int nmem = total < 32 ? total : 32;
         int mypos = -1;
-        if (lane < nmem) {
-          int r = lane, d = 0;
-          uint32_t wsel = w0;
-          if (r >= c0n) { r -= c0n; d = 1; wsel = w1;
-            if (r >= c1n) { r -= c1n; d = 2; wsel = w2;
-              if (r >= c2n) { r -= c2n; d = 3; wsel = w3; } } }
-          mypos = ((wb + d) << 5) + nms_nth_set_bit(wsel, r);
+        if (warp == 0) {
+          if (lane < nmem) {
+            int r = lane, d = 0;
+            uint32_t wsel = w0;
+            if (r >= c0n) { r -= c0n; d = 1; wsel = w1;
+              if (r >= c1n) { r -= c1n; d = 2; wsel = w2;
+                if (r >= c2n) { r -= c2n; d = 3; wsel = w3; } } }
+            mypos = ((wb + d) << 5) + nms_nth_set_bit(wsel, r);
+          }
+          const int lastpos = __shfl_sync(0xffffffffu, mypos, nmem - 1);
+          if (lane == 0) s_fnew = (total <= 32) ? ((wb + 4) << 5) : (lastpos + 1);
         }
-        const int lastpos = __shfl_sync(0xffffffffu, mypos, nmem - 1);
-        const int f_new = (total <= 32) ? ((wb + 4) << 5) : (lastpos + 1);
         // (0c) member boxes -> shared memory
         int my_out = 0;   // warp 0: this member's row in the reference's output order (for step (b): no dependent load there)
         if (warp == 0) {
@@ -371,6 +375,7 @@ k_nms_segments(const float4* __restrict__ cbox, const float* __restrict__ area,
           s_cpos[lane] = valid ? qi : -1;
         }
         __syncthreads();
+        const int f_new = s_fnew;
         NMS_T(1);
         // (a) pair matrix (rows warp and warp+16) and spatial bin masks (bins warp and warp+16)
         {
