@@ -173,11 +173,24 @@ def test_new_entry_points_refuse_cpu_tensors():
     from yolo_for_turbines_b200._lib import YoloB200Error
     from yolo_for_turbines_b200.dataset import encode_targets
     from yolo_for_turbines_b200.loss import YOLOLoss
-    from yolo_for_turbines_b200.preprocess import letterbox_batch
+    from yolo_for_turbines_b200.preprocess import LetterboxPlan, letterbox_batch
 
     with pytest.raises(YoloB200Error, match="no CPU fallback"):
         letterbox_batch([torch.zeros(4, 4, 3, dtype=torch.uint8)], 32, device="cpu")
     with pytest.raises(YoloB200Error, match="no CPU fallback"):
+        LetterboxPlan(2, 8, 8, 32, device="cpu")
+    with pytest.raises(YoloB200Error, match="no CPU fallback"):
         encode_targets([[[0.5, 0.5, 0.1, 0.1, 0]]], [[(0.1, 0.1)] * 3] * 3, image_size=64, device="cpu")
     with pytest.raises(YoloB200Error, match="no CPU fallback"):
         YOLOLoss()(torch.zeros(1, 3, 2, 2, 7), torch.zeros(1, 3, 2, 2, 6), [[1, 1]] * 3)
+
+
+def test_bench_launch_count_matches_the_nms_pipeline():
+    """`gpu_launches` in the bench line is a claim about csrc/nms.cu's launch list: one memset, the threshold
+    compaction (3), 8-bit radix passes of hist + scan + scatter over (32 score + image) bits and over the (image, class)
+    key, class keys, gather, the two NMS kernels, and keep count / scan / write / offsets."""
+    import bench
+
+    assert bench.nms_launch_count(1) == 1 + 3 + 4 * 3 + 1 + 1 * 3 + 1 + 2 + 4
+    assert bench.nms_launch_count(64) == 1 + 3 + 5 * 3 + 1 + 2 * 3 + 1 + 2 + 4 == 33
+    assert bench.nms_launch_count(300) == 1 + 3 + 6 * 3 + 1 + 3 * 3 + 1 + 2 + 4
