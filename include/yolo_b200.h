@@ -257,6 +257,13 @@ int yolo_map_match(const float* dets, int D, const float* gts, int G, const int3
                    int box_format, float* tp, float* best_iou, int32_t* best_gt,
                    int32_t* gt_claim /* [G] scratch */, yb_stream_t stream);
 
+/* Per-class average precision -- replaces the per-class tail of utils.py:262-272 (cumsum, precision / recall with
+ * (1, 0) prepended, torch.trapz).  tp_sorted [D] = TP flags (fp32 0/1) in evaluation order (class ascending, then
+ * stable descending score); class c owns [cls_start[c], cls_end[c]); n_gt[c] = ground truths of the class.
+ * ap[c] = AP of the class, 0 when it has no ground truth or no detections.                                       */
+int yolo_map_ap(const float* tp_sorted, const int32_t* cls_start, const int32_t* cls_end, const int32_t* n_gt,
+                int num_classes, float* ap, yb_stream_t stream);
+
 /* Accuracy reductions -- replaces the per-scale body of utils.py:356-371 (check_model_accuracy).
  * head (B,3,S,S,5+nc) / target (B,3,S,S,6) fp32 with element strides; counts6 (device u64, accumulated):
  * correct_class, total_class, correct_obj, total_obj, correct_noobj, total_noobj.                          */

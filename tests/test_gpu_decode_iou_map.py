@@ -135,3 +135,38 @@ def test_yolo_loss_forward_matches_reference(gold):
     out = YOLOLoss()(p, torch.zeros(1, 3, 4, 4, 6, device="cuda"), [[1, 1]] * 3)
     sum(out).backward()
     assert p.grad is not None and float(p.grad[..., 4].min()) > 0 and float(p.grad[..., :4].abs().max()) == 0
+
+
+@pytest.mark.gpu
+def test_map_ap_kernel_equals_the_reference_tail_per_class():
+    """yolo_map_ap (one CTA per class) against utils.py:262-272 written out with torch on the CPU: cumsum, precision /
+    recall with (1, 0) prepended, torch.trapz -- per class, including a class without detections, a class without
+    ground truth, a one-detection class and a class longer than several scan chunks."""
+    from yolo_for_turbines_b200._lib import lib, ptr, stream_ptr
+
+    g = torch.Generator().manual_seed(5)
+    sizes = [0, 1, 7, 256, 257, 3000, 0, 12]
+    n_gt = [3, 1, 0, 100, 9, 2500, 0, 40]
+    tps = [(torch.rand(n, generator=g) < 0.4).float() for n in sizes]
+    tp = torch.cat(tps) if sum(sizes) else torch.zeros(0)
+    off = [0]
+    for n in sizes:
+        off.append(off[-1] + n)
+    dev = torch.device("cuda")
+    ap = torch.full((len(sizes),), -1.0, device=dev)
+    tp_d = tp.to(dev)      # named: the launch is asynchronous, temporaries would be recycled under it
+    lo_d = torch.tensor(off[:-1], dtype=torch.int32, device=dev)
+    hi_d = torch.tensor(off[1:], dtype=torch.int32, device=dev)
+    ng_d = torch.tensor(n_gt, dtype=torch.int32, device=dev)
+    lib.yolo_map_ap(ptr(tp_d), ptr(lo_d), ptr(hi_d), ptr(ng_d), len(sizes), ptr(ap), stream_ptr(dev))
+    got = ap.cpu()
+    for c, (t, ng) in enumerate(zip(tps, n_gt)):
+        if ng == 0 or t.numel() == 0:
+            assert float(got[c]) == 0.0
+            continue
+        ctp = torch.cumsum(t, 0)
+        cfp = torch.cumsum(1 - t, 0)
+        prec = torch.cat([torch.ones(1), ctp / (ctp + cfp)])
+        rec = torch.cat([torch.zeros(1), ctp / ng])
+        ref = float(torch.trapz(prec, rec))
+        assert abs(float(got[c]) - ref) <= 1e-6 * max(1.0, abs(ref)), (c, float(got[c]), ref)

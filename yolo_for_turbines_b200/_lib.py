@@ -72,6 +72,7 @@ SIGNATURES = {
     "yolo_nms": (_I, [_P, _P, _I, _I, _F, _D, _I, _I, _P, _P, _P, _SZ, _P]),
     "yolo_iou": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _P, _P]),
     "yolo_map_match": (_I, [_P, _I, _P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P]),
+    "yolo_map_ap": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "yolo_accuracy_counts": (_I, [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64), _I, _I, _I, _F, _P, _P]),
     "yolo_loss_fwd": (_I, [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _I, _P, _P]),
     "yolo_bn_stats": (_I, [_P, _LL, _I, _I, _P, _P]),

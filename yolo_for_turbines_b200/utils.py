@@ -234,8 +234,8 @@ def map_match(dets: torch.Tensor, gts: torch.Tensor, iou_threshold: float = 0.5,
 
 def calc_mAP(pred_boxes, true_boxes, iou_threshold=0.5, box_format="center", num_classes=20):
     """utils.py:193-274.  Rows [img, cx, cy, w, h, score, cls]; returns a 0-dim fp32 tensor.
-    The O(D*G) matching runs on device (K7); the per-class cumsum / trapz tail is a handful of
-    torch ops on the device-resident TP flags."""
+    The O(D*G) matching (yolo_map_match) and the per-class cumsum / precision / recall / trapz tail (yolo_map_ap, one
+    CTA per class) run on device; the host reads back one scalar."""
     dev = pred_boxes.device if torch.is_tensor(pred_boxes) and pred_boxes.is_cuda else _device()
     dets = torch.as_tensor(pred_boxes, dtype=torch.float32).reshape(-1, 7).to(dev)
     gts = torch.as_tensor(true_boxes, dtype=torch.float32).reshape(-1, 7).to(dev)
@@ -248,24 +248,17 @@ def calc_mAP(pred_boxes, true_boxes, iou_threshold=0.5, box_format="center", num
     if dets.shape[0] == 0:
         return torch.zeros((), dtype=torch.float32)
     order, tp_s, cls_s, _, _ = map_match(dets, gts, iou_threshold, box_format)
-    # segmented cumulative sums per class over the evaluation order
-    ctp = torch.cumsum(tp_s, 0)
-    pos = torch.arange(1, tp_s.numel() + 1, dtype=torch.float32, device=dev)
-    start = torch.searchsorted(cls_s.contiguous(), classes, right=False)  # first det of each class
-    end = torch.searchsorted(cls_s.contiguous(), classes, right=True)
-    base_tp = torch.cat([torch.zeros(1, device=dev), ctp])[start]         # TP count before the class
-    aps = []
-    for c in torch.nonzero(valid).flatten().tolist():
-        s, e = int(start[c]), int(end[c])
-        if e == s:  # ground truth but no detections: AP 0 (utils.py:262-272 on empty tensors)
-            aps.append(torch.zeros((), device=dev))
-            continue
-        tp_c = ctp[s:e] - base_tp[c]
-        n_c = pos[s:e] - float(s)
-        prec = torch.cat([torch.ones(1, device=dev), tp_c / n_c])          # cumTP / (cumTP + cumFP)
-        rec = torch.cat([torch.zeros(1, device=dev), tp_c / float(n_gt[c])])
-        aps.append(torch.trapz(prec, rec))
-    return (sum(aps) / len(aps)).cpu()
+    # per-class AP on device (one CTA per class, csrc/map.cu k_map_ap): no per-class host loop, one read-back
+    cls_c = cls_s.contiguous()
+    start = torch.searchsorted(cls_c, classes, right=False).to(torch.int32)   # first det of each class
+    end = torch.searchsorted(cls_c, classes, right=True).to(torch.int32)
+    ap = torch.empty(num_classes, dtype=torch.float32, device=dev)
+    tp_c, n_gt32 = tp_s.contiguous(), n_gt.to(torch.int32).contiguous()   # named: they must outlive the argument evaluation
+    with torch.cuda.device(dev):
+        lib.yolo_map_ap(ptr(tp_c), ptr(start), ptr(end), ptr(n_gt32), int(num_classes), ptr(ap), stream_ptr(dev))
+    # mean over the classes that have ground truth (utils.py:274): sum(aps) / len(aps), accumulated in class order
+    aps = ap[valid]
+    return (aps.double().sum() / float(n_valid)).to(torch.float32).cpu()
 
 
 # ------------------------------------------------------------------- fused detection pipeline
