@@ -252,13 +252,14 @@ def run_train_workload(args, dev, dist, rank, world, local):
 
     sampler = ClockSampler(local)
     sampler.start()
+    use_graph = not args.train_eager      # the step replayed as one CUDA graph (Trainer.step(graph=True)) unless --train-eager
     for i in range(max(args.warmup, 3) + 10):
-        tr.step(xs[i % 3], tgs[i % 3])
+        tr.step(xs[i % 3], tgs[i % 3], graph=use_graph and i >= 2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        losses = tr.step(xs[i % 3], tgs[i % 3])
+        losses = tr.step(xs[i % 3], tgs[i % 3], graph=use_graph)
     e1.record()
     barrier()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
@@ -293,7 +294,7 @@ def run_train_workload(args, dev, dist, rank, world, local):
         if i + 1 < args.steps:
             upload(i + 1)
         main_stream.wait_event(up_done[j])
-        host_loss[j].copy_(tr.step(dx[j], dt[j]), non_blocking=True)
+        host_loss[j].copy_(tr.step(dx[j], dt[j], graph=use_graph), non_blocking=True)
         consumed[j].record(main_stream)
     t1.record()
     barrier()
@@ -321,11 +322,20 @@ def run_train_workload(args, dev, dist, rank, world, local):
                          "note": "algorithmic FLOPs = 3 x forward (SURVEY 8d) over the WHOLE step time; the step is "
                                  "currently dominated by HBM-bound BatchNorm/activation passes, see DESIGN.md", "traffic": None},
             "clocks": clocks, "final_loss_terms": [float(v) for v in losses.tolist()],
+            "launch_mode": "CUDA graph replay" if use_graph else "eager",
         }
         print(json.dumps(line), flush=True)
+    tr._graphs.clear()      # captured steps hold NCCL kernels: gone before the process group is
+    torch.cuda.synchronize(dev)
     if dist is not None:
+        guard = threading.Timer(30.0, lambda: os._exit(0))
+        guard.daemon = True
+        guard.start()
         dist.barrier()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def stage_train_step(args, dev, dist, rank, world):
@@ -509,6 +519,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="detect", choices=["detect", "train"],
                     help="detect = BASELINE configs[1] (the headline); train = configs[3], one SGD step per step")
+    ap.add_argument("--train-eager", action="store_true", help="train workload: one launch per kernel instead of the captured step")
     ap.add_argument("--activation", default="mish", help="train workload: the reference trains with mish (train.py:299)")
     ap.add_argument("--lanes", type=int, default=4,
                     help="independent detector pipelines (buffers + CUDA graph + stream) that consecutive batches alternate "
