@@ -354,6 +354,10 @@ int yolo_pack_weights_dgrad_s2(const float* w_oihw, int c_out, int c_in, int r, 
  * buf = first_step ? g' : momentum*buf + g'; p -= lr*buf                                                      */
 int yolo_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                   float weight_decay, float grad_scale, int first_step, yb_stream_t stream);
+/* The same with the learning rate read from device memory at run time: a step captured in a CUDA graph follows a
+ * per-iteration schedule (train.py:71-74 LinearLR warm-up, CosineAnnealingLR) without being captured again.        */
+int yolo_sgd_step_dev(float* param, const float* grad, float* momentum_buf, long long n, const float* lr_dev,
+                      float momentum, float weight_decay, float grad_scale, int first_step, yb_stream_t stream);
 /* Training-target encoder -- replaces YOLODataset.__getitem__'s anchor assignment (dataset.py:119-167, iou_aligned
  * utils.py:22-36) + collate_fn's per-scale stacking (utils.py:694-700) for a batch.  boxes: device [total][5] doubles
  * x, y, w, h, class in the image's own order; image b owns rows [offsets[b], offsets[b+1]).  anchors18_host: the 9

@@ -470,7 +470,8 @@ def test_graphed_step_follows_the_eager_trajectory():
         losses = []
         for i in range(6):
             g = mode == "graph" or (mode == "mixed" and i in (2, 3))
-            losses.append(tr.step(xs[i % 3], tgs[i % 3], graph=g).clone())
+            lr_i = 1e-5 * (0.5 + 0.25 * i)       # a per-iteration schedule (train.py:71-74): no new capture per value
+            losses.append(tr.step(xs[i % 3], tgs[i % 3], lr=lr_i, graph=g).clone())
         torch.cuda.synchronize()
         runs[mode] = (torch.stack(losses).cpu(), (tr.flat_p[: tr.n_trainable] - p0).cpu(), len(tr._graphs))
     assert runs["eager"][2] == 0 and runs["graph"][2] == 1 and runs["mixed"][2] == 1

@@ -90,6 +90,7 @@ SIGNATURES = {
     "yolo_pack_weights_dgrad": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "yolo_pack_weights_dgrad_s2": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "yolo_sgd_step": (_I, [_P, _P, _P, _LL, _F, _F, _F, _F, _I, _P]),
+    "yolo_sgd_step_dev": (_I, [_P, _P, _P, _LL, _P, _F, _F, _F, _I, _P]),
     "yolo_loss_bwd": (_I, [_P, C.POINTER(C.c_int64), _P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _P, _F,
                            C.POINTER(_F), _P, C.POINTER(C.c_int64), _I, _P]),
     "yolo_encode_targets": (_I, [_P, _P, _I, C.POINTER(_F), _I, _I, _I, _F, _P, _P, _P, _P]),

@@ -575,7 +575,9 @@ __global__ void k_pack_weights_dgrad_s2(const float* __restrict__ w, int c_out, 
 
 // torch.optim.SGD: g' = g * gscale + wd * p;  buf = first ? g' : mu * buf + g';  p -= lr * buf
 __global__ void __launch_bounds__(256) k_sgd(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
-                                            long long n, float lr, float mu, float wd, float gscale, int first) {
+                                            long long n, float lr, const float* __restrict__ lr_dev, float mu, float wd,
+                                            float gscale, int first) {
+  if (lr_dev != nullptr) lr = __ldg(lr_dev);   // a captured step reads its learning rate from device memory
   const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 pv = *reinterpret_cast<float4*>(p + i);
@@ -787,8 +789,21 @@ extern "C" int yolo_sgd_step(float* param, const float* grad, float* momentum_bu
              "yolo_sgd_step: buffers must be 16-byte aligned");
   if (n == 0) return YB_OK;
   const long long threads = (n + 3) / 4;
-  k_sgd<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, n, lr, momentum, weight_decay,
-                                                                            grad_scale, first_step);
+  k_sgd<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, n, lr, nullptr, momentum,
+                                                                            weight_decay, grad_scale, first_step);
+  YB_CHECK_LAUNCH();
+  return YB_OK;
+}
+
+extern "C" int yolo_sgd_step_dev(float* param, const float* grad, float* momentum_buf, long long n, const float* lr_dev,
+                                 float momentum, float weight_decay, float grad_scale, int first_step, yb_stream_t stream) {
+  YB_REQUIRE(param && grad && momentum_buf && lr_dev && n >= 0, "yolo_sgd_step_dev: bad argument");
+  YB_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(momentum_buf)) & 15) == 0,
+             "yolo_sgd_step_dev: buffers must be 16-byte aligned");
+  if (n == 0) return YB_OK;
+  const long long threads = (n + 3) / 4;
+  k_sgd<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, n, 0.f, lr_dev, momentum,
+                                                                            weight_decay, grad_scale, first_step);
   YB_CHECK_LAUNCH();
   return YB_OK;
 }

@@ -547,6 +547,7 @@ class Trainer:
         self._ev_sgd = torch.cuda.Event()
         self._packs_pending = False
         self._graphs: Dict[tuple, dict] = {}
+        self._lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)   # learning rate of the captured step
         self.repack(full=True)
         self._packed_sig = self._param_sig()
 
@@ -752,8 +753,12 @@ class Trainer:
             main.wait_stream(self.comm_stream)
         else:
             plan.backward()
-        lib.yolo_sgd_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), self.n_trainable,
-                          lr, self.momentum, self.weight_decay, 1.0 / self.world, int(self.steps_done == 0), st)
+        if repack_first:   # captured step: the learning rate is a device scalar, set before every replay
+            lib.yolo_sgd_step_dev(ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), self.n_trainable, ptr(self._lr_dev),
+                                  self.momentum, self.weight_decay, 1.0 / self.world, int(self.steps_done == 0), st)
+        else:
+            lib.yolo_sgd_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), self.n_trainable,
+                              lr, self.momentum, self.weight_decay, 1.0 / self.world, int(self.steps_done == 0), st)
         if repack_first:
             if self.wgrad_stream is not None:
                 main.wait_stream(self.wgrad_stream)
@@ -763,7 +768,7 @@ class Trainer:
 
     def _step_graphed(self, x, targets, lr: float):
         """`step(..., graph=True)`: the ~700 launches of a step (three streams, the NCCL all-reduce included) captured
-        once per (input shape, lr, world size) and replayed -- no host work per launch, which matters when several
+        once per (input shape, world size) and replayed (the learning rate is a device scalar: per-iteration schedules replay) -- no host work per launch, which matters when several
         ranks share few host cores (8 ranks on 16 cores: the eager step loses ~1 ms to launch contention).  The first
         step of a Trainer runs eagerly (it seeds the momentum buffer), inputs are copied into static buffers, and the
         returned loss tensor is the graph's own output buffer (rewritten by every replay)."""
@@ -771,7 +776,7 @@ class Trainer:
         plan = self.plans.get((x.shape[0], x.shape[2], x.shape[3]))
         if self.steps_done == 0 or plan is None or not getattr(plan, "_ran", False):
             return self.step(x, targets, lr=lr, graph=False)   # a shape's first step builds its plan and runs eagerly
-        key = (tuple(x.shape), tuple(tuple(t.shape) for t in targets), lr, self.world)
+        key = (tuple(x.shape), tuple(tuple(t.shape) for t in targets), self.world)   # not the learning rate: a device scalar
         st = self._graphs.get(key)
         with torch.cuda.device(dev):
             if st is None:
@@ -789,6 +794,7 @@ class Trainer:
                     losses = self.losses
                 st = dict(g=g, gx=gx, gts=gts, losses=losses)
                 self._graphs[key] = st
+            self._lr_dev.fill_(lr)
             st["gx"].copy_(x, non_blocking=True)
             for d, t in zip(st["gts"], targets):
                 d.copy_(t, non_blocking=True)
