@@ -652,18 +652,26 @@ class Trainer:
         return p
 
     # ------------------------------------------------------------------------------------------------------
+    def _check_targets(self, plan: TrainPlan, targets: Sequence[torch.Tensor]):
+        """Shape / dtype / device of the three target tensors (also called before a step is captured: an error must not
+        surface in the middle of a stream capture)."""
+        if len(targets) != len(plan.heads):
+            raise YoloB200Error(f"expected {len(plan.heads)} target tensors (one per scale), got {len(targets)}")
+        for s, (op, tgt) in enumerate(zip(plan.heads, targets)):
+            if tuple(tgt.shape) != (plan.B, 3, op.ho, op.wo, 6) or tgt.dtype != torch.float32 or tgt.device != self.device:
+                raise YoloB200Error(f"target {s}: expected fp32 {(plan.B, 3, op.ho, op.wo, 6)} on {self.device}, got {tuple(tgt.shape)}")
+            if op.ho != op.wo:
+                raise YoloB200Error("YOLOLoss works on square grids (loss.py:29-81 with the reference's (B,3,S,S,6) targets)")
+
     def _loss_and_head_grads(self, plan: TrainPlan, targets: Sequence[torch.Tensor]):
         dev = self.device
         st = stream_ptr(dev)
         plan.loss_sums.zero_()
         views = plan.head_views()
         calls = []
+        self._check_targets(plan, targets)
         for s, (op, (na, nc), pred, tgt) in enumerate(zip(plan.heads, plan.head_meta, views, targets)):
-            if tuple(tgt.shape) != (plan.B, 3, op.ho, op.wo, 6) or tgt.dtype != torch.float32 or tgt.device != dev:
-                raise YoloB200Error(f"target {s}: expected fp32 {(plan.B, 3, op.ho, op.wo, 6)} on {dev}, got {tuple(tgt.shape)}")
             S = op.ho
-            if op.ho != op.wo:
-                raise YoloB200Error("YOLOLoss works on square grids (loss.py:29-81 with the reference's (B,3,S,S,6) targets)")
             anc = (C.c_float * 6)(*[v * S for a in self.anchors[s] for v in a])   # train.py:195-197 scaled anchors
             ps, ts = (C.c_int64 * 5)(*pred.stride()), (C.c_int64 * 5)(*tgt.stride())
             sums = plan.loss_sums[6 * s:6 * s + 6]
@@ -776,6 +784,7 @@ class Trainer:
         plan = self.plans.get((x.shape[0], x.shape[2], x.shape[3]))
         if self.steps_done == 0 or plan is None or not getattr(plan, "_ran", False):
             return self.step(x, targets, lr=lr, graph=False)   # a shape's first step builds its plan and runs eagerly
+        self._check_targets(plan, targets)
         key = (tuple(x.shape), tuple(tuple(t.shape) for t in targets), self.world)   # not the learning rate: a device scalar
         st = self._graphs.get(key)
         with torch.cuda.device(dev):
