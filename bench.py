@@ -666,18 +666,14 @@ def main():
     ms_conv_burst = min(burst)
 
     # ---- stage timings that explain the step: decode (HBM roofline) and the NMS pipeline (boxes/s) -----
-    from yolo_for_turbines_b200.utils import batched_nms, decode_boxes, _scaled_anchors
+    from yolo_for_turbines_b200.utils import batched_nms, decode_boxes_multi, _scaled_anchors
 
     heads = plan.head_views()
     stt = det._get_state(B, [h.shape[2] for h in heads], dev)
     fused_decode = plan.cand is not None and det.fuse_decode
 
-    def run_decode():
-        off = 0
-        for i, h in enumerate(heads):
-            s = h.shape[2]
-            decode_boxes(h, _scaled_anchors(cfg.ANCHORS, i, s), s, True, out=stt["cand"], out_offset=off)
-            off += 3 * s * s
+    def run_decode():   # all three scales in one launch (yolo_decode_multi) on the model's dense heads
+        decode_boxes_multi(heads, [_scaled_anchors(cfg.ANCHORS, i, h.shape[2]) for i, h in enumerate(heads)], stt["cand"])
 
     def run_nms():
         batched_nms(cand_t.view(-1, 6), stt["off"], args.iou, args.conf, "center", workspace=stt["ws"], class_bits=8)
@@ -877,7 +873,7 @@ def main():
                            "peak_gbs": pk["hbm"], "frac": B * n_cand * ((5 + args.classes) * 4 + 24) / ms_decode / 1e6 / pk["hbm"],
                            "bound": "hbm", "bytes_per_candidate": (5 + args.classes) * 4 + 24,
                            "in_timed_step": not fused_decode,
-                           "note": "standalone yolo_decode x3 on stored fp32 heads; the Detector's step fuses the decode into the "
+                           "note": "standalone decode of the three stored fp32 heads in one launch (yolo_decode_multi); the Detector's step fuses the decode into the "
                                    "head convs' epilogue (no head tensor in HBM), so this stage is NOT part of `value` when "
                                    "in_timed_step is false"},
                 "e2e_uint8": e2e_u8,

@@ -222,6 +222,12 @@ int yolo_letterbox_u8(const void* descs_dev, int batch, int size, int channels, 
 int yolo_decode(const float* head, const int64_t* strides5_host, int batch, int S, int nc,
                 const float* anchors6_host, int is_pred, int writeback, float* out,
                 int out_boxes_per_image, int out_offset, yb_stream_t stream);
+/* The scales of a detector (<= 4) in one launch, concatenated per image in the given order as utils.py:300-309 does.
+ * Every head must be the dense [B*S*S pixels][pitch] fp32 layout the model produces (is_pred, no write-back);
+ * YB_ERR_UNSUPPORTED otherwise (call yolo_decode per scale).  strides5_host: 5 per scale; anchors6_host: 6 per scale. */
+int yolo_decode_multi(const float* const* heads_host, const int64_t* strides5_host, int batch, const int32_t* S_host,
+                      int nc, const float* anchors6_host, int num_scales, float* out, int out_boxes_per_image,
+                      yb_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * K4+K5+K6  threshold compaction, stable segmented sort, class-aware greedy

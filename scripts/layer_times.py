@@ -108,22 +108,18 @@ ms_in = timed(lambda: plan._launch_input(x))
 print(f"input patchify: {ms_in:.4f} ms  ({x.numel() * 4 / 1e6:.0f} MB in, {args.batch * args.size ** 2 * 64 / 1e6:.0f} MB out)")
 ms_graph = timed(lambda: (plan._launch_input(x) if plan.stem_direct else None, plan.graph.replay()), do_flush=False)
 print(f"conv graph replay (back to back): {ms_graph:.3f} ms -> {tot_gf / ms_graph:.1f} TFLOP/s, {args.batch / ms_graph * 1e3:.0f} img/s conv-only")
-from yolo_for_turbines_b200.utils import batched_nms, decode_boxes  # noqa: E402
+from yolo_for_turbines_b200.utils import batched_nms, decode_boxes_multi  # noqa: E402
 heads = plan.head_views()
 stt = det._get_state(args.batch, [h.shape[2] for h in heads], dev)
 
 
-def dec():
-    off = 0
-    for i, h in enumerate(heads):
-        s = h.shape[2]
-        decode_boxes(h, torch.tensor(cfg.ANCHORS[i]) * s, s, True, out=stt["cand"], out_offset=off)
-        off += 3 * s * s
+def dec():   # the three stored heads in one launch (yolo_decode_multi)
+    decode_boxes_multi(heads, [torch.tensor(cfg.ANCHORS[i]) * h.shape[2] for i, h in enumerate(heads)], stt["cand"])
 
 
 ms_dec = timed(dec)
 n = stt["cand"].shape[1]
-print(f"decode x3: {ms_dec:.4f} ms  ({args.batch * n} candidates, {args.batch * n * ((5 + args.classes) * 4 + 24) / ms_dec / 1e6:.1f} GB/s algorithmic)")
+print(f"decode (3 scales, one launch): {ms_dec:.4f} ms  ({args.batch * n} candidates, {args.batch * n * ((5 + args.classes) * 4 + 24) / ms_dec / 1e6:.1f} GB/s algorithmic)")
 ms_nms = timed(lambda: batched_nms(stt["cand"].view(-1, 6), stt["off"], 0.45, args.conf, "center", workspace=stt["ws"]))
 kept = int(stt["ws"].keep_off[-1].item())
 print(f"nms pipeline: {ms_nms:.4f} ms  ({args.batch * n / ms_nms / 1e3:.2f} M candidates/s, kept {kept})")

@@ -170,3 +170,31 @@ def test_map_ap_kernel_equals_the_reference_tail_per_class():
         rec = torch.cat([torch.zeros(1), ctp / ng])
         ref = float(torch.trapz(prec, rec))
         assert abs(float(got[c]) - ref) <= 1e-6 * max(1.0, abs(ref)), (c, float(got[c]), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nc,pitch", [(80, 256), (2, 32)])
+def test_decode_multi_equals_per_scale_decode(nc, pitch):
+    """yolo_decode_multi (all scales in one launch) writes exactly what three yolo_decode calls write; heads that are
+    not the model's dense layout take the per-scale route through the same wrapper."""
+    from yolo_for_turbines_b200.utils import decode_boxes, decode_boxes_multi
+
+    g = torch.Generator().manual_seed(9)
+    B, C = 3, 5 + nc
+    heads, anchors = [], []
+    for S in (4, 8, 16):
+        buf = (torch.randn(B * S * S, pitch, generator=g) * 2).cuda()       # [pixels][pitch], channels (a, c) = a * C + c
+        heads.append(buf[:, : 3 * C].view(B, S, S, 3, C).permute(0, 3, 1, 2, 4))
+        anchors.append(torch.rand(3, 2, generator=g) * S)
+    n = sum(3 * h.shape[2] ** 2 for h in heads)
+    ref = torch.zeros(B, n, 6, device="cuda")
+    off = 0
+    for h, a in zip(heads, anchors):
+        decode_boxes(h, a, h.shape[2], True, out=ref, out_offset=off)
+        off += 3 * h.shape[2] ** 2
+    got = torch.zeros(B, n, 6, device="cuda")
+    decode_boxes_multi(heads, anchors, got)
+    assert torch.equal(got, ref)
+    got2 = torch.zeros(B, n, 6, device="cuda")
+    decode_boxes_multi([h.contiguous() for h in heads], anchors, got2)       # (B,3,S,S,C)-contiguous: generic kernel
+    assert torch.equal(got2, ref)

@@ -68,6 +68,7 @@ SIGNATURES = {
     "yolo_letterbox_desc_bytes": (_SZ, []),
     "yolo_letterbox_u8": (_I, [_P, _I, _I, _I, _P, _P]),
     "yolo_decode": (_I, [_P, C.POINTER(C.c_int64), _I, _I, _I, C.POINTER(_F), _I, _I, _P, _I, _I, _P]),
+    "yolo_decode_multi": (_I, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _I, C.POINTER(C.c_int32), _I, C.POINTER(_F), _I, _P, _I, _P]),
     "yolo_nms_workspace_bytes": (_SZ, [_I, _I]),
     "yolo_nms": (_I, [_P, _P, _I, _I, _F, _D, _I, _I, _P, _P, _P, _SZ, _P]),
     "yolo_iou": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _P, _P]),

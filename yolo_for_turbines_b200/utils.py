@@ -115,6 +115,46 @@ def decode_boxes(predictions: torch.Tensor, anchors, grid_size: int, is_pred: bo
     return out
 
 
+def _dense_head(h: torch.Tensor) -> bool:
+    """(B,3,S,S,C) view of the model's own [B*S*S pixels][pitch] fp32 head buffer (what yolo_decode_multi reads)."""
+    if not (h.is_cuda and h.dtype == torch.float32 and h.dim() == 5 and h.shape[1] == 3 and h.shape[2] == h.shape[3]):
+        return False
+    S, Cc = h.shape[2], h.shape[4]
+    st = h.stride()
+    pitch = st[3]
+    return st[4] == 1 and st[1] == Cc and 3 * Cc <= pitch <= 384 and st[2] == S * pitch and st[0] == S * S * pitch
+
+
+def decode_boxes_multi(heads: Sequence[torch.Tensor], anchors_per_scale, out: torch.Tensor) -> torch.Tensor:
+    """decode_boxes for all scales of a detector, concatenated per image in the given order (utils.py:300-309), into
+    `out` (B, sum 3*S*S, 6).  One launch when every head is the model's dense layout (yolo_decode_multi: the small
+    scales are launch-latency bound on their own); otherwise one yolo_decode call per scale."""
+    heads = list(heads)
+    if 1 <= len(heads) <= 4 and all(_dense_head(h) for h in heads) and len({h.shape[-1] for h in heads}) == 1 \
+            and len({h.device for h in heads}) == 1 and out.data_ptr() % 8 == 0:
+        n = len(heads)
+        B, nc = heads[0].shape[0], heads[0].shape[-1] - 5
+        ptrs = (C.c_void_p * n)(*[h.data_ptr() for h in heads])
+        strides = (C.c_int64 * (5 * n))(*[v for h in heads for v in h.stride()])
+        sizes = (C.c_int32 * n)(*[h.shape[2] for h in heads])
+        anc = []
+        for a in anchors_per_scale:
+            a = torch.as_tensor(a, dtype=torch.float32).reshape(-1).cpu()
+            if a.numel() != 6:
+                raise YoloB200Error("anchors must hold 3 (w, h) pairs per scale")
+            anc += a.tolist()
+        anc_c = (C.c_float * (6 * n))(*anc)
+        with torch.cuda.device(heads[0].device):
+            lib.yolo_decode_multi(ptrs, strides, B, sizes, nc, anc_c, n, ptr(out), out.shape[1], stream_ptr(heads[0].device))
+        return out
+    off = 0
+    for h, a in zip(heads, anchors_per_scale):
+        s = h.shape[2]
+        decode_boxes(h, a, s, True, out=out, out_offset=off)
+        off += 3 * s * s
+    return out
+
+
 def cells_to_boxes(predictions, anchors, grid_size, is_pred=True):
     """utils.py:86-148: returns the nested list B x 3*S*S x [cx,cy,w,h,obj,cls] and, like the
     reference, rewrites predictions[..., 0:4] in place when is_pred (utils.py:102-110)."""
@@ -307,11 +347,8 @@ class Detector:
             nc = max(m[1] for m in plan.head_meta)
         else:
             heads = plan.head_views()
-            cand, off = st["cand"], 0
-            for i, h in enumerate(heads):
-                s = h.shape[2]
-                decode_boxes(h, _scaled_anchors(self.anchors, i, s), s, True, out=cand, out_offset=off)
-                off += 3 * s * s
+            cand = st["cand"]
+            decode_boxes_multi(heads, [_scaled_anchors(self.anchors, i, h.shape[2]) for i, h in enumerate(heads)], cand)
             nc = max(h.shape[-1] - 5 for h in heads)
         # classes come from the decode's argmax: integers < num_classes, so the grouping sort needs one pass
         return batched_nms(cand.view(-1, 6), st["off"], self.iou_threshold, self.obj_threshold, self.box_format,
@@ -398,11 +435,7 @@ def detect_from_heads(heads, anchors, iou_threshold, obj_threshold, box_format="
     dev, B = heads[0].device, heads[0].shape[0]
     n = sum(3 * h.shape[2] * h.shape[2] for h in heads)
     cand = torch.empty(B, n, 6, dtype=torch.float32, device=dev)
-    off = 0
-    for i, h in enumerate(heads):
-        s = h.shape[2]
-        decode_boxes(h, _scaled_anchors(anchors, i, s), s, True, out=cand, out_offset=off)
-        off += 3 * s * s
+    decode_boxes_multi(heads, [_scaled_anchors(anchors, i, h.shape[2]) for i, h in enumerate(heads)], cand)
     img_off = (torch.arange(B + 1, dtype=torch.int32, device=dev) * n).contiguous()
     return batched_nms(cand.view(-1, 6), img_off, iou_threshold, obj_threshold, box_format)
 
